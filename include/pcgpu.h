@@ -1,0 +1,134 @@
+/*
+ * pcgpu.h -- C ABI of the B200-native polynomial-commitment compute engine.
+ *
+ * This is the drop-in boundary for the hot path of arkworks-rs/poly-commit (reference mounted at
+ * /root/reference; all file:line citations below are relative to it).  The reference has no FFI of
+ * its own: the path sits behind Rust trait methods of un-vendored crates (ark-ec / ark-poly 0.5.0).
+ * Each entry point therefore names the Rust call it replaces; INTEGRATION.md shows the Rust-side
+ * `extern "C"` declarations and the patched call sites.
+ *
+ * Conventions
+ *   - Field elements: little-endian 64-bit limbs, least-significant first; 4 limbs for every Fr and for
+ *     BN254/Pallas Fq, 6 limbs for BLS12-381 Fq (== ark-ff BigInt<N>([u64; N])).
+ *   - "mont": Montgomery form with R = 2^(64*limbs) (the in-memory form of ark-ff Fp).
+ *     "canonical": plain integer (what F::into_bigint returns).
+ *   - Affine G1 point: x || y (2*limbs u64, Montgomery) plus a separate infinity byte (1 = identity;
+ *     x, y are then written as zero).  Byte-identical to ark-ec's (x, y) so equality is a memcmp.
+ *   - Every call is synchronous: on return the outputs are written.  The caller owns all host buffers;
+ *     the library owns device memory behind the opaque handles.  Nothing unwinds across the ABI:
+ *     0 = success, negative = error (pcgpu_strerror).
+ *   - Thread safety: calls on one pcgpu_ctx are serialised by an internal mutex; use one context
+ *     per host thread for concurrency (hyrax/mod.rs:233-242 calls msm from a Rayon par_iter).
+ *   - There is no CPU fallback: every entry point fails with PCGPU_E_CUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef PCGPU_H
+#define PCGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcgpu_ctx pcgpu_ctx;
+typedef struct pcgpu_srs pcgpu_srs;
+
+/* curve ids mirror the type parameter E / G of the reference's schemes */
+enum { PCGPU_BLS12_381 = 0, PCGPU_BN254 = 1, PCGPU_PALLAS = 2 };
+
+enum {
+  PCGPU_OK = 0,
+  PCGPU_E_CUDA = -1,   /* CUDA runtime / launch failure, or no usable device */
+  PCGPU_E_OOM = -2,    /* device allocation failed */
+  PCGPU_E_BADARG = -3, /* null pointer, unknown curve id, ... */
+  PCGPU_E_LEN = -4,    /* base_offset + n exceeds the registered bases (msm() returns Err(len) in ark-ec) */
+  PCGPU_E_RANGE = -5,  /* a canonical scalar is >= 2^255 (2^254 for BN254): not a reduced field element */
+  PCGPU_E_DEGREE = -6, /* Error::TooManyCoefficients, kzg10/mod.rs:392-402 */
+  PCGPU_E_HIDING = -7  /* Error::HidingBoundToolarge, kzg10/mod.rs:404-422 */
+};
+
+/* flags */
+enum {
+  PCGPU_SCALARS_MONT = 1u,   /* scalars are Montgomery Fr; F::into_bigint is fused into the digit pass */
+  PCGPU_DEVICE_PTRS = 2u,    /* bulk array arguments are device pointers (results stay host pointers) */
+  PCGPU_SRS_PRECOMPUTE = 4u  /* srs_register: also store 2^(c*k)-multiples of the bases (window folding) */
+};
+
+/* ---- context ---------------------------------------------------------------------------------- */
+int pcgpu_init(int device, pcgpu_ctx **out);
+void pcgpu_destroy(pcgpu_ctx *ctx);
+const char *pcgpu_strerror(int code);
+/* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL restores the context's own stream. */
+int pcgpu_set_stream(pcgpu_ctx *ctx, void *cuda_stream);
+/* Per-stage device timings (CUDA events on the launching stream).  stage: 0 digits/count, 1 scan,
+ * 2 scatter, 3 tasks, 4 bucket accumulate, 5 bucket reduce, 6 final, 7 fr division, 8 fr axpy.
+ * enable=1 starts recording; get returns accumulated milliseconds and launch count since enable. */
+int pcgpu_profile_enable(pcgpu_ctx *ctx, int enable);
+int pcgpu_profile_get(pcgpu_ctx *ctx, int stage, double *ms, uint64_t *count);
+
+/* ---- SRS / committer key ---------------------------------------------------------------------- */
+/* Upload n affine bases once (kzg10 Powers::powers_of_g, data_structures.rs:124-129; ipa CommitterKey::comm_key;
+ * hyrax com_key).  inf may be NULL (no identity points). */
+int pcgpu_srs_register(pcgpu_ctx *ctx, int curve, const void *bases_xy, const uint8_t *inf, size_t n, uint32_t flags,
+                       pcgpu_srs **out);
+void pcgpu_srs_release(pcgpu_ctx *ctx, pcgpu_srs *srs);
+size_t pcgpu_srs_len(const pcgpu_srs *srs);
+int pcgpu_srs_curve(const pcgpu_srs *srs);
+
+/* ---- MSM -------------------------------------------------------------------------------------- */
+/* <G as VariableBaseMSM>::msm_bigint(&bases[base_offset..], scalars)   kzg10/mod.rs:175-178, :199-203, :255-258,
+ * :270-273; ipa_pc/mod.rs:64; hyrax/mod.rs:92, :501.  Sums the first n pairs; n == 0 returns the identity
+ * (kzg10/mod.rs:197-203 on the non-hiding path).  base_offset models `&powers_of_g[num_leading_zeros..]`.
+ * scalars: n x 4 u64, canonical unless PCGPU_SCALARS_MONT.  out_xy: affine Montgomery x||y; *out_inf: 1 if identity. */
+int pcgpu_msm(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n, uint32_t flags,
+              void *out_xy, uint8_t *out_inf);
+/* Same, result left projective (XYZZ: X, Y, ZZ, ZZZ each `limbs` u64, Montgomery; ZZ == 0 is the identity) -- the
+ * per-GPU partial of an index-range-sharded MSM before the point-sum (partitioning B). */
+int pcgpu_msm_partial(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n,
+                      uint32_t flags, void *out_xyzz);
+/* Point-sum of `count` XYZZ partials (host memory) -> affine.  The "NCCL point-sum": ranks all-gather their
+ * partials as bytes and each adds them locally (NCCL has no reduction operator for curve points). */
+int pcgpu_g1_sum_xyzz(pcgpu_ctx *ctx, int curve, const void *xyzz, size_t count, void *out_xy, uint8_t *out_inf);
+
+/* g.batch_mul(scalars): out[i] = scalars[i] * base -- KZG10::setup, kzg10/mod.rs:76, :82-86 (used to build synthetic
+ * SRSs on the device).  base_xy: one affine point (host).  scalars: n canonical.  out_xy: n affine points, x||y only
+ * (an identity result is written as x = y = 0).  With PCGPU_DEVICE_PTRS scalars and out_xy are device pointers. */
+int pcgpu_g1_fixed_base_mul(pcgpu_ctx *ctx, int curve, const void *base_xy, const void *scalars, size_t n, uint32_t flags,
+                            void *out_xy);
+
+/* ---- Fr vector work around the MSM (all elements Montgomery) ----------------------------------- */
+/* F::into_bigint over a slice -- convert_to_bigints, kzg10/mod.rs:463-470 */
+int pcgpu_fr_from_mont(pcgpu_ctx *ctx, int curve, const void *in, void *out, size_t n, uint32_t flags);
+/* y += c * x -- DensePolynomial AddAssign<(F, &P)>, marlin_pc/mod.rs:286; ipa_pc/mod.rs:691-697.  c: host, 1 element */
+int pcgpu_fr_axpy(pcgpu_ctx *ctx, int curve, void *y, const void *c, const void *x, size_t n, uint32_t flags);
+/* q = p / (X - z), rem = p(z) -- compute_witness_polynomial, kzg10/mod.rs:217-240.  p: n coefficients, q: n-1,
+ * z and rem: host, 1 element each (rem may be NULL) */
+int pcgpu_fr_div_linear(pcgpu_ctx *ctx, int curve, const void *p, size_t n, const void *z, void *q, void *rem,
+                        uint32_t flags);
+/* <a, b> -- utils.rs:150-155.  out: host, 1 element */
+int pcgpu_fr_inner_product(pcgpu_ctx *ctx, int curve, const void *a, const void *b, size_t n, void *out, uint32_t flags);
+/* out = v * M, M rows x cols row-major -- Matrix::row_mul, utils.rs:127-146 */
+int pcgpu_fr_row_mul(pcgpu_ctx *ctx, int curve, const void *v, const void *m, size_t rows, size_t cols, void *out,
+                     uint32_t flags);
+
+/* ---- KZG10 fused prover calls ------------------------------------------------------------------ */
+/* KZG10::commit -- kzg10/mod.rs:157-210.  coeffs: n Montgomery Fr (low degree first; trailing zeros allowed and
+ * ignored like DensePolynomial's truncation).  Hiding: pass gamma (powers_of_gamma_g) and n_blind > 0 blinding
+ * coefficients (the reference samples them from its RNG, :182-195; here they are an input so results are
+ * reproducible); gamma may be NULL when n_blind == 0.  Errors: PCGPU_E_DEGREE, PCGPU_E_HIDING. */
+int pcgpu_kzg_commit(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coeffs, size_t n,
+                     const pcgpu_srs *powers_of_gamma_g, const void *blind, size_t n_blind, uint32_t flags,
+                     void *out_xy, uint8_t *out_inf);
+/* KZG10::open -- kzg10/mod.rs:287-310 (compute_witness_polynomial :217-240 then open_with_witness_polynomial
+ * :243-284): witness = p / (X - z) on the device, then the MSM over the witness.  out_random_v (may be NULL)
+ * receives blind(z) when n_blind > 0 (:264). */
+int pcgpu_kzg_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coeffs, size_t n, const void *z,
+                   const pcgpu_srs *powers_of_gamma_g, const void *blind, size_t n_blind, uint32_t flags,
+                   void *out_w_xy, uint8_t *out_w_inf, void *out_random_v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCGPU_H */

@@ -1,0 +1,261 @@
+"""ctypes binding of include/pcgpu.h.  Arrays are numpy uint64 in the ABI's packed layout
+(little-endian limbs; Montgomery unless stated) or raw device pointers (ints) with DEVICE_PTRS."""
+import ctypes
+import os
+
+import numpy as np
+
+BLS12_381, BN254, PALLAS = 0, 1, 2
+CURVES = {"bls12_381": BLS12_381, "bn254": BN254, "pallas": PALLAS}
+SCALARS_MONT, DEVICE_PTRS, SRS_PRECOMPUTE = 1, 2, 4
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def fq_limbs(curve):
+    return 6 if curve == BLS12_381 else 4
+
+
+def library_path():
+    return os.path.join(_HERE, "libpcgpu.so")
+
+
+class PcgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pcgpu error {code}: {msg}")
+        self.code = code
+
+
+_sz = ctypes.c_size_t
+_vp = ctypes.c_void_p
+
+
+def _load(path):
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: the CUDA library is required (build it with `python -c 'import __graft_entry__ as g; "
+            f"g.build()'`); there is no CPU fallback")
+    lib = ctypes.CDLL(path)
+    lib.pcgpu_strerror.restype = ctypes.c_char_p
+    lib.pcgpu_strerror.argtypes = [ctypes.c_int]
+    lib.pcgpu_srs_len.restype = _sz
+    lib.pcgpu_srs_len.argtypes = [_vp]
+    lib.pcgpu_srs_curve.argtypes = [_vp]
+    sigs = {
+        "pcgpu_init": [ctypes.c_int, ctypes.POINTER(_vp)],
+        "pcgpu_destroy": [_vp],
+        "pcgpu_set_stream": [_vp, _vp],
+        "pcgpu_profile_enable": [_vp, ctypes.c_int],
+        "pcgpu_profile_get": [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)],
+        "pcgpu_srs_register": [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_uint32, ctypes.POINTER(_vp)],
+        "pcgpu_srs_release": [_vp, _vp],
+        "pcgpu_msm": [_vp, _vp, _sz, _vp, _sz, ctypes.c_uint32, _vp, _vp],
+        "pcgpu_msm_partial": [_vp, _vp, _sz, _vp, _sz, ctypes.c_uint32, _vp],
+        "pcgpu_g1_sum_xyzz": [_vp, ctypes.c_int, _vp, _sz, _vp, _vp],
+        "pcgpu_g1_fixed_base_mul": [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_uint32, _vp],
+        "pcgpu_fr_from_mont": [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_uint32],
+        "pcgpu_fr_axpy": [_vp, ctypes.c_int, _vp, _vp, _vp, _sz, ctypes.c_uint32],
+        "pcgpu_fr_div_linear": [_vp, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, ctypes.c_uint32],
+        "pcgpu_fr_inner_product": [_vp, ctypes.c_int, _vp, _vp, _sz, _vp, ctypes.c_uint32],
+        "pcgpu_fr_row_mul": [_vp, ctypes.c_int, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint32],
+        "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
+        "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = None if name in ("pcgpu_destroy", "pcgpu_srs_release") else ctypes.c_int
+    return lib
+
+
+def _ptr(a):
+    """numpy array -> pointer; int -> device pointer; None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return ctypes.c_void_p(int(a))
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _u64(a):
+    if a is None or isinstance(a, (int, np.integer)):
+        return a
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class Srs:
+    """Device-resident bases (kzg10 Powers::powers_of_g / powers_of_gamma_g, ipa comm_key, hyrax com_key)."""
+
+    def __init__(self, engine, handle, curve, n):
+        self.engine, self.handle, self.curve, self.n = engine, handle, curve, n
+
+    def __len__(self):
+        return self.n
+
+    def release(self):
+        if self.handle is not None:
+            self.engine.lib.pcgpu_srs_release(self.engine.ctx, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One pcgpu context (one CUDA device, one stream).  `lib_path` exists so the host-emulation unit tests
+    can drive the identical C ABI of tests/host_emul/libpcgpu_hostcheck.so; product code never passes it."""
+
+    def __init__(self, device=0, lib_path=None):
+        self.lib = _load(lib_path or library_path())
+        ctx = _vp()
+        rc = self.lib.pcgpu_init(device, ctypes.byref(ctx))
+        if rc:
+            raise PcgpuError(rc, self.lib.pcgpu_strerror(rc).decode())
+        self.ctx = ctx
+        self.device = device
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pcgpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise PcgpuError(rc, self.lib.pcgpu_strerror(rc).decode())
+
+    # ---- context ----
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.pcgpu_set_stream(self.ctx, _vp(cuda_stream) if cuda_stream else None))
+
+    def profile_enable(self, on=True):
+        self._ck(self.lib.pcgpu_profile_enable(self.ctx, 1 if on else 0))
+
+    def profile_get(self, stage):
+        ms, cnt = ctypes.c_double(), ctypes.c_uint64()
+        self._ck(self.lib.pcgpu_profile_get(self.ctx, stage, ctypes.byref(ms), ctypes.byref(cnt)))
+        return ms.value, cnt.value
+
+    # ---- SRS ----
+    def srs_register(self, curve, bases_xy, inf=None, n=None, flags=0):
+        bases_xy = _u64(bases_xy)
+        if n is None:
+            n = bases_xy.size // (2 * fq_limbs(curve))
+        inf = None if inf is None else np.ascontiguousarray(inf, dtype=np.uint8)
+        h = _vp()
+        self._ck(self.lib.pcgpu_srs_register(self.ctx, curve, _ptr(bases_xy), _ptr(inf), n, flags, ctypes.byref(h)))
+        return Srs(self, h, curve, n)
+
+    # ---- MSM ----
+    def msm(self, srs, scalars, n=None, base_offset=0, flags=0):
+        """msm_bigint(&bases[base_offset..], scalars) -> (xy uint64[2*limbs], is_identity)."""
+        scalars = _u64(scalars)
+        if n is None:
+            n = scalars.size // 4
+        out = np.zeros(2 * fq_limbs(srs.curve), dtype=np.uint64)
+        inf = np.zeros(1, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_msm(self.ctx, srs.handle, base_offset, _ptr(scalars), n, flags, _ptr(out), _ptr(inf)))
+        return out, int(inf[0])
+
+    def msm_partial(self, srs, scalars, n=None, base_offset=0, flags=0):
+        scalars = _u64(scalars)
+        if n is None:
+            n = scalars.size // 4
+        out = np.zeros(4 * fq_limbs(srs.curve), dtype=np.uint64)
+        self._ck(self.lib.pcgpu_msm_partial(self.ctx, srs.handle, base_offset, _ptr(scalars), n, flags, _ptr(out)))
+        return out
+
+    def g1_sum_xyzz(self, curve, xyzz):
+        xyzz = _u64(xyzz)
+        count = xyzz.size // (4 * fq_limbs(curve))
+        out = np.zeros(2 * fq_limbs(curve), dtype=np.uint64)
+        inf = np.zeros(1, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_g1_sum_xyzz(self.ctx, curve, _ptr(xyzz), count, _ptr(out), _ptr(inf)))
+        return out, int(inf[0])
+
+    def fixed_base_mul(self, curve, base_xy, scalars, n=None, flags=0, out=None):
+        base_xy, scalars = _u64(base_xy), _u64(scalars)
+        if n is None:
+            n = scalars.size // 4
+        if out is None:
+            out = np.zeros((n, 2 * fq_limbs(curve)), dtype=np.uint64)
+        self._ck(self.lib.pcgpu_g1_fixed_base_mul(self.ctx, curve, _ptr(base_xy), _ptr(scalars), n, flags, _ptr(out)))
+        return out
+
+    # ---- Fr ----
+    def fr_from_mont(self, curve, a, n=None, flags=0, out=None):
+        a = _u64(a)
+        if n is None:
+            n = a.size // 4
+        if out is None:
+            out = np.zeros((n, 4), dtype=np.uint64)
+        self._ck(self.lib.pcgpu_fr_from_mont(self.ctx, curve, _ptr(a), _ptr(out), n, flags))
+        return out
+
+    def fr_axpy(self, curve, y, c, x, n=None, flags=0):
+        """y += c * x (in place when y is a device pointer; returns the updated host copy otherwise)."""
+        c, x = _u64(c), _u64(x)
+        if not isinstance(y, (int, np.integer)):
+            y = _u64(y).copy()
+        if n is None:
+            n = x.size // 4
+        self._ck(self.lib.pcgpu_fr_axpy(self.ctx, curve, _ptr(y), _ptr(c), _ptr(x), n, flags))
+        return y
+
+    def fr_div_linear(self, curve, p, z, n=None, flags=0, q=None):
+        p, z = _u64(p), _u64(z)
+        if n is None:
+            n = p.size // 4
+        if q is None:
+            q = np.zeros((max(n - 1, 0), 4), dtype=np.uint64)
+        rem = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.pcgpu_fr_div_linear(self.ctx, curve, _ptr(p), n, _ptr(z), _ptr(q), _ptr(rem), flags))
+        return q, rem
+
+    def fr_inner_product(self, curve, a, b, n=None, flags=0):
+        a, b = _u64(a), _u64(b)
+        if n is None:
+            n = a.size // 4
+        out = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.pcgpu_fr_inner_product(self.ctx, curve, _ptr(a), _ptr(b), n, _ptr(out), flags))
+        return out
+
+    def fr_row_mul(self, curve, v, m, rows, cols, flags=0):
+        v, m = _u64(v), _u64(m)
+        out = np.zeros((cols, 4), dtype=np.uint64)
+        self._ck(self.lib.pcgpu_fr_row_mul(self.ctx, curve, _ptr(v), _ptr(m), rows, cols, _ptr(out), flags))
+        return out
+
+    # ---- KZG10 ----
+    def kzg_commit(self, powers_of_g, coeffs, n=None, powers_of_gamma_g=None, blind=None, flags=0):
+        coeffs, blind = _u64(coeffs), _u64(blind)
+        if n is None:
+            n = coeffs.size // 4
+        nb = 0 if blind is None else blind.size // 4
+        out = np.zeros(2 * fq_limbs(powers_of_g.curve), dtype=np.uint64)
+        inf = np.zeros(1, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_kzg_commit(self.ctx, powers_of_g.handle, _ptr(coeffs), n,
+                                           None if powers_of_gamma_g is None else powers_of_gamma_g.handle,
+                                           _ptr(blind), nb, flags, _ptr(out), _ptr(inf)))
+        return out, int(inf[0])
+
+    def kzg_open(self, powers_of_g, coeffs, z, n=None, powers_of_gamma_g=None, blind=None, flags=0):
+        coeffs, blind, z = _u64(coeffs), _u64(blind), _u64(z)
+        if n is None:
+            n = coeffs.size // 4
+        nb = 0 if blind is None else blind.size // 4
+        out = np.zeros(2 * fq_limbs(powers_of_g.curve), dtype=np.uint64)
+        inf = np.zeros(1, dtype=np.uint8)
+        rv = np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.pcgpu_kzg_open(self.ctx, powers_of_g.handle, _ptr(coeffs), n, _ptr(z),
+                                         None if powers_of_gamma_g is None else powers_of_gamma_g.handle,
+                                         _ptr(blind), nb, flags, _ptr(out), _ptr(inf), _ptr(rv)))
+        return out, int(inf[0]), (rv if nb else None)

@@ -1,0 +1,421 @@
+// G1 multi-scalar multiplication: Pippenger bucket method, all stages on the device.
+//
+// Replaces <E::G1 as VariableBaseMSM>::msm_bigint (ark-ec 0.5.0, un-vendored) at the reference call
+// sites kzg10/mod.rs:175-178, :199-203, :255-258, :270-273; ipa_pc/mod.rs:64; hyrax/mod.rs:92, :501,
+// with F::into_bigint (kzg10/mod.rs:463-470) fused into the digit pass when scalars arrive in
+// Montgomery form.
+//
+// Pipeline (one stream, no host round trip until the 1-point result):
+//   1 count      thread/scalar : signed-digit recoding, histogram of (bucket set, |digit|)   [atomics]
+//   2 scan       exclusive prefix sum of the histogram -> bucket offsets
+//   3 scatter    thread/scalar : recompute digits, place (table group, base index, sign) by bucket
+//   4 tasks      split every bucket into tasks of <= L entries (bounds the longest serial chain
+//                whatever the scalar distribution), scan, fill task -> bucket map
+//   5 accumulate thread/task   : XYZZ mixed additions of the gathered affine bases  (DOMINANT)
+//   6 reduce     thread/segment: running-sum  sum_k (k+1) B_k  over a segment of buckets,
+//                then pairwise tree over segments
+//   7 final      Horner over the bucket sets (c doublings each) and conversion to affine
+//
+// Window <-> table layout: window w = g*S + s uses table group g (bases pre-multiplied by
+// 2^(c*S*g) at SRS registration) and bucket set s.  S = W, G = 1 is the plain method on raw bases;
+// S = 1, G = W removes every doubling from the tail.
+#pragma once
+#include "ec.cuh"
+#include "rt.cuh"
+
+namespace pcgpu {
+
+struct alignas(16) u32x4 { uint32_t x, y, z, w; };
+
+struct MsmGeom {
+  uint32_t n;            // pairs
+  uint32_t c;            // window bits
+  uint32_t W;            // windows
+  uint32_t S;            // bucket sets
+  uint32_t G;            // table groups (W <= S*G)
+  uint32_t NB;           // buckets per set = 2^(c-1)
+  uint32_t TB;           // S * NB
+  uint32_t L;            // max entries per accumulate task
+  uint32_t seg_len;      // buckets per reduce segment
+  uint32_t nseg;         // segments per set
+  uint32_t scalar_bits;  // scalars must be < 2^scalar_bits
+  uint32_t scalars_mont; // 1: scalars are Montgomery Fr (convert in the digit pass)
+  uint64_t table_stride; // points per table group
+  uint64_t base_off;     // first base used inside each group
+};
+
+enum : uint32_t { ENTRY_SIGN = 0x80000000u, ENTRY_GROUP_SHIFT = 26, ENTRY_IDX_MASK = (1u << 26) - 1 };
+
+// ---------------------------------------------------------------------------------------------
+// scalar loading + signed-digit recoding
+// ---------------------------------------------------------------------------------------------
+template <class C>
+PCGPU_DEV void load_scalar(const uint32_t *scalars, size_t i, bool mont, uint32_t *k) {
+  using R = typename C::Fr;
+  static_assert(R::N == 8, "256-bit scalar fields only");
+  const u32x4 *p = reinterpret_cast<const u32x4 *>(scalars) + 2 * i;
+  u32x4 lo = p[0], hi = p[1];
+  Fp<R> v;
+  v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+  v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+  if (mont) v = fp_from_mont<R>(v);
+#pragma unroll
+  for (int j = 0; j < 8; j++) k[j] = v.l[j];
+}
+
+// raw c-bit field starting at bit position pos of a 256-bit little-endian integer
+PCGPU_DEV uint32_t scalar_bits_at(const uint32_t *k, uint32_t pos, uint32_t c) {
+  uint32_t q = pos >> 5, sh = pos & 31;
+  uint64_t lo = q < 8 ? k[q] : 0u;
+  uint64_t hi = q + 1 < 8 ? k[q + 1] : 0u;
+  uint64_t v = (lo | (hi << 32)) >> sh;
+  return (uint32_t)v & ((1u << c) - 1);
+}
+
+// Calls f(w, magnitude in 1..2^(c-1), negative) for every non-zero signed digit.
+template <class Fn>
+PCGPU_DEV void for_each_digit(const uint32_t *k, const MsmGeom &g, Fn f) {
+  uint32_t carry = 0;
+  const uint32_t half = 1u << (g.c - 1);
+  for (uint32_t w = 0; w < g.W; w++) {
+    uint32_t d = scalar_bits_at(k, w * g.c, g.c) + carry;
+    bool neg = d > half;
+    carry = neg ? 1u : 0u;
+    uint32_t mag = neg ? (1u << g.c) - d : d;
+    if (mag) f(w, mag, neg);
+  }
+}
+
+PCGPU_DEV bool scalar_in_range(const uint32_t *k, uint32_t bits) {
+  if (bits >= 256) return true;
+  uint32_t q = bits >> 5, sh = bits & 31;
+  uint32_t o = k[q] >> sh;
+  for (uint32_t j = q + 1; j < 8; j++) o |= k[j];
+  return o == 0;
+}
+
+template <class C>
+struct MsmCountBody {
+  const uint32_t *scalars; MsmGeom g; uint32_t *counts; uint32_t *err;
+  PCGPU_KERNEL_DEV void operator()(size_t i) const {
+    uint32_t k[8];
+    load_scalar<C>(scalars, i, g.scalars_mont != 0, k);
+    if (!scalar_in_range(k, g.scalar_bits)) { rt::atomic_or(err, 1u); return; }
+    uint32_t *cnt = counts; const MsmGeom gg = g;
+    for_each_digit(k, gg, [&](uint32_t w, uint32_t mag, bool) {
+      uint32_t s = w % gg.S;
+      rt::atomic_add(cnt + (size_t)s * gg.NB + (mag - 1), 1u);
+    });
+  }
+};
+
+template <class C>
+struct MsmScatterBody {
+  const uint32_t *scalars; MsmGeom g; uint32_t *cursor; uint32_t *entries;
+  PCGPU_KERNEL_DEV void operator()(size_t i) const {
+    uint32_t k[8];
+    load_scalar<C>(scalars, i, g.scalars_mont != 0, k);
+    if (!scalar_in_range(k, g.scalar_bits)) return;
+    uint32_t *cur = cursor; uint32_t *ent = entries; const MsmGeom gg = g;
+    for_each_digit(k, gg, [&](uint32_t w, uint32_t mag, bool neg) {
+      uint32_t s = w % gg.S, grp = w / gg.S;
+      uint32_t pos = rt::atomic_add(cur + (size_t)s * gg.NB + (mag - 1), 1u);
+      ent[pos] = (neg ? ENTRY_SIGN : 0u) | (grp << ENTRY_GROUP_SHIFT) | (uint32_t)i;
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of uint32 (out has n+1 entries; out[n] = total).  Three tiny kernels.
+// ---------------------------------------------------------------------------------------------
+enum { SCAN_CHUNK = 256 };
+struct ScanChunkSumBody {
+  const uint32_t *in; size_t n; uint32_t *partial;
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    size_t lo = t * SCAN_CHUNK, hi = lo + SCAN_CHUNK < n ? lo + SCAN_CHUNK : n;
+    uint32_t s = 0;
+    for (size_t i = lo; i < hi; i++) s += in[i];
+    partial[t] = s;
+  }
+};
+struct ScanPartialsBody {
+  uint32_t *partial; size_t m;
+  PCGPU_KERNEL_DEV void operator()(size_t) const {
+    uint32_t run = 0;
+    for (size_t i = 0; i < m; i++) { uint32_t v = partial[i]; partial[i] = run; run += v; }
+    partial[m] = run;
+  }
+};
+struct ScanApplyBody {
+  const uint32_t *in; size_t n; const uint32_t *partial; uint32_t *out; size_t m;
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    size_t lo = t * SCAN_CHUNK, hi = lo + SCAN_CHUNK < n ? lo + SCAN_CHUNK : n;
+    uint32_t run = partial[t];
+    for (size_t i = lo; i < hi; i++) { uint32_t v = in[i]; out[i] = run; run += v; }
+    if (t + 1 == m) out[n] = partial[m];
+  }
+};
+
+// scratch: (n/SCAN_CHUNK + 2) uint32
+inline size_t scan_scratch_words(size_t n) { return (n + SCAN_CHUNK - 1) / SCAN_CHUNK + 2; }
+inline int exclusive_scan_u32(const uint32_t *in, size_t n, uint32_t *out, uint32_t *scratch, rt::stream_t st) {
+  size_t m = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  if (m == 0) { return rt::dev_memset(out, 0, sizeof(uint32_t), st); }
+  int rc;
+  if ((rc = rt::launch<128>(ScanChunkSumBody{in, n, scratch}, m, st))) return rc;
+  if ((rc = rt::launch<32>(ScanPartialsBody{scratch, m}, 1, st))) return rc;
+  return rt::launch<128>(ScanApplyBody{in, n, scratch, out, m}, m, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tasks
+// ---------------------------------------------------------------------------------------------
+struct TaskCountBody {
+  const uint32_t *offsets; uint32_t L; uint32_t *ntasks;
+  PCGPU_KERNEL_DEV void operator()(size_t b) const {
+    uint32_t cnt = offsets[b + 1] - offsets[b];
+    ntasks[b] = (cnt + L - 1) / L;
+  }
+};
+struct TaskFillBody {
+  const uint32_t *task_off; uint32_t *task_bucket;
+  PCGPU_KERNEL_DEV void operator()(size_t b) const {
+    uint32_t lo = task_off[b], hi = task_off[b + 1];
+    for (uint32_t t = lo; t < hi; t++) task_bucket[t] = (uint32_t)b;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// accumulate: one thread per task
+// ---------------------------------------------------------------------------------------------
+template <class C>
+PCGPU_DEV Affine<C> load_affine(const Affine<C> *p) {
+  constexpr int N = C::Fq::N;
+  const u32x4 *q = reinterpret_cast<const u32x4 *>(p);
+  Affine<C> a;
+  uint32_t tmp[2 * N];
+#pragma unroll
+  for (int j = 0; j < 2 * N / 4; j++) { u32x4 v = q[j]; tmp[4 * j] = v.x; tmp[4 * j + 1] = v.y; tmp[4 * j + 2] = v.z; tmp[4 * j + 3] = v.w; }
+#pragma unroll
+  for (int j = 0; j < N; j++) { a.x.l[j] = tmp[j]; a.y.l[j] = tmp[N + j]; }
+  return a;
+}
+
+template <class C>
+PCGPU_DEV void store_xyzz(XYZZ<C> *dst, const XYZZ<C> &p) {
+  constexpr int N = C::Fq::N;
+  u32x4 *q = reinterpret_cast<u32x4 *>(dst);
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(&p);
+#pragma unroll
+  for (int j = 0; j < 4 * N / 4; j++) { u32x4 v; v.x = src[4 * j]; v.y = src[4 * j + 1]; v.z = src[4 * j + 2]; v.w = src[4 * j + 3]; q[j] = v; }
+}
+
+template <class C>
+PCGPU_DEV XYZZ<C> load_xyzz(const XYZZ<C> *src) {
+  constexpr int N = C::Fq::N;
+  const u32x4 *q = reinterpret_cast<const u32x4 *>(src);
+  XYZZ<C> p;
+  uint32_t *dst = reinterpret_cast<uint32_t *>(&p);
+#pragma unroll
+  for (int j = 0; j < 4 * N / 4; j++) { u32x4 v = q[j]; dst[4 * j] = v.x; dst[4 * j + 1] = v.y; dst[4 * j + 2] = v.z; dst[4 * j + 3] = v.w; }
+  return p;
+}
+
+template <class C>
+struct MsmAccumulateBody {
+  const Affine<C> *tables; MsmGeom g;
+  const uint32_t *offsets;      // TB+1 bucket offsets into entries
+  const uint32_t *task_off;     // TB+1
+  const uint32_t *task_bucket;  // per task
+  const uint32_t *entries;
+  XYZZ<C> *partial;             // per task
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    if (t >= task_off[g.TB]) return;
+    uint32_t b = task_bucket[t];
+    uint32_t j = (uint32_t)t - task_off[b];
+    uint32_t lo = offsets[b] + j * g.L;
+    uint32_t end = offsets[b + 1];
+    uint32_t hi = lo + g.L < end ? lo + g.L : end;
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (uint32_t e = lo; e < hi; e++) {
+      uint32_t v = entries[e];
+      uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
+      size_t idx = (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK);
+      Affine<C> a = load_affine<C>(tables + idx);
+      xyzz_madd<C>(acc, a, (v & ENTRY_SIGN) != 0);
+    }
+    store_xyzz<C>(partial + t, acc);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// bucket reduction
+// ---------------------------------------------------------------------------------------------
+template <class C>
+struct MsmSegmentBody {
+  MsmGeom g; const uint32_t *task_off; const XYZZ<C> *partial; XYZZ<C> *seg_out;
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    uint32_t s = (uint32_t)(t / g.nseg), seg = (uint32_t)(t % g.nseg);
+    uint32_t lo = seg * g.seg_len;
+    uint32_t hi = lo + g.seg_len < g.NB ? lo + g.seg_len : g.NB;
+    XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
+    for (uint32_t k = hi; k-- > lo;) {
+      size_t b = (size_t)s * g.NB + k;
+      uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+      for (uint32_t q = t0; q < t1; q++) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add<C>(run, p); }
+      xyzz_add<C>(acc, run);
+    }
+    // sum_{k=lo}^{hi-1} (k+1) B_k = acc + lo * run
+    if (lo) { XYZZ<C> m = xyzz_mul_small<C>(run, lo); xyzz_add<C>(acc, m); }
+    store_xyzz<C>(seg_out + t, acc);
+  }
+};
+
+template <class C>
+struct MsmTreeAddBody {
+  XYZZ<C> *a; uint32_t stride; uint32_t m; uint32_t half;  // per set: a[i] += a[i+half] for i+half < m
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    uint32_t cnt = m - half;
+    uint32_t s = (uint32_t)(t / cnt), i = (uint32_t)(t % cnt);
+    XYZZ<C> *base = a + (size_t)s * stride;
+    XYZZ<C> x = load_xyzz<C>(base + i), y = load_xyzz<C>(base + i + half);
+    xyzz_add<C>(x, y);
+    store_xyzz<C>(base + i, x);
+  }
+};
+
+template <class C>
+struct MsmFinalBody {
+  MsmGeom g; const XYZZ<C> *sets; uint32_t stride; XYZZ<C> *out_xyzz; Affine<C> *out_aff;
+  PCGPU_KERNEL_DEV void operator()(size_t) const {
+    XYZZ<C> acc = load_xyzz<C>(sets + (size_t)(g.S - 1) * stride);
+    for (uint32_t s = g.S - 1; s-- > 0;) {
+      for (uint32_t k = 0; k < g.c; k++) acc = xyzz_dbl<C>(acc);
+      XYZZ<C> p = load_xyzz<C>(sets + (size_t)s * stride);
+      xyzz_add<C>(acc, p);
+    }
+    if (out_xyzz) store_xyzz<C>(out_xyzz, acc);
+    if (out_aff) *out_aff = xyzz_to_affine<C>(acc);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------
+struct MsmWorkspace {
+  uint32_t *counts, *offsets, *cursor, *ntasks, *task_off, *task_bucket, *entries, *scan_scratch, *err;
+  void *partial, *seg_out;
+  size_t max_tasks;
+};
+
+inline uint32_t ilog2_floor(uint64_t v) { uint32_t l = 0; while (v >>= 1) l++; return l; }
+
+// Window size for the plain (no precomputation) method.
+inline uint32_t msm_pick_c(size_t n) {
+  uint32_t lg = ilog2_floor(n ? n : 1);
+  int c = (int)lg - 4;
+  if (c < 8) c = 8;
+  if (c > 16) c = 16;
+  return (uint32_t)c;
+}
+
+inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scalar_bits, bool mont,
+                            uint64_t table_stride, uint64_t base_off) {
+  MsmGeom g;
+  g.n = (uint32_t)n; g.c = c;
+  g.W = scalar_bits / c + 1;
+  g.G = groups < 1 ? 1 : groups;
+  g.S = (g.W + g.G - 1) / g.G;
+  g.NB = 1u << (c - 1);
+  g.TB = g.S * g.NB;
+  g.L = 64;
+  g.seg_len = g.NB >= 4096 ? 32 : (g.NB >= 256 ? 16 : 8);
+  g.nseg = (g.NB + g.seg_len - 1) / g.seg_len;
+  g.scalar_bits = scalar_bits; g.scalars_mont = mont ? 1 : 0;
+  g.table_stride = table_stride; g.base_off = base_off;
+  return g;
+}
+
+template <class C>
+inline size_t msm_workspace_bytes(const MsmGeom &g) {
+  size_t max_entries = (size_t)g.n * g.W;
+  size_t max_tasks = max_entries / g.L + g.TB + 1;
+  size_t b = 0;
+  b += 5 * rt::Arena::pad((g.TB + 2) * sizeof(uint32_t));
+  b += rt::Arena::pad(max_tasks * sizeof(uint32_t));
+  b += rt::Arena::pad((max_entries + 1) * sizeof(uint32_t));
+  b += rt::Arena::pad(scan_scratch_words(g.TB + 1) * sizeof(uint32_t));
+  b += rt::Arena::pad(64);
+  b += rt::Arena::pad(max_tasks * sizeof(XYZZ<C>));
+  b += rt::Arena::pad((size_t)g.S * g.nseg * sizeof(XYZZ<C>));
+  return b + 4096;
+}
+
+struct StageTimer;  // api.cu
+
+// Runs the whole pipeline on `st`.  d_scalars: n x 8 uint32 on the device.  Results are written to
+// d_out_xyzz / d_out_aff (device, either may be null).  *d_err (device word) is OR-ed with 1 when a
+// scalar is out of range.  `prof` (optional) brackets stages with events.
+template <class C, class Prof>
+inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_scalars, rt::Arena &arena,
+                   XYZZ<C> *d_out_xyzz, Affine<C> *d_out_aff, uint32_t **d_err_out, rt::stream_t st, Prof &prof) {
+  int rc;
+  if ((rc = arena.reserve(msm_workspace_bytes<C>(g)))) return rc;
+  size_t max_entries = (size_t)g.n * g.W;
+  size_t max_tasks = max_entries / g.L + g.TB + 1;
+  uint32_t *counts = arena.take<uint32_t>(g.TB + 2);
+  uint32_t *offsets = arena.take<uint32_t>(g.TB + 2);
+  uint32_t *cursor = arena.take<uint32_t>(g.TB + 2);
+  uint32_t *ntasks = arena.take<uint32_t>(g.TB + 2);
+  uint32_t *task_off = arena.take<uint32_t>(g.TB + 2);
+  uint32_t *task_bucket = arena.take<uint32_t>(max_tasks);
+  uint32_t *entries = arena.take<uint32_t>(max_entries + 1);
+  uint32_t *scratch = arena.take<uint32_t>(scan_scratch_words(g.TB + 1));
+  uint32_t *err = arena.take<uint32_t>(16);
+  XYZZ<C> *partial = arena.take<XYZZ<C>>(max_tasks);
+  XYZZ<C> *seg_out = arena.take<XYZZ<C>>((size_t)g.S * g.nseg);
+  if (!counts || !offsets || !cursor || !ntasks || !task_off || !task_bucket || !entries || !scratch || !err || !partial || !seg_out)
+    return rt::E_OOM;
+  if (d_err_out) *d_err_out = err;
+
+  prof.begin(0, st);
+  if ((rc = rt::dev_memset(counts, 0, (g.TB + 2) * sizeof(uint32_t), st))) return rc;
+  if ((rc = rt::dev_memset(err, 0, 64, st))) return rc;
+  if ((rc = rt::launch<256>(MsmCountBody<C>{d_scalars, g, counts, err}, g.n, st))) return rc;
+  prof.end(0, st);
+
+  prof.begin(1, st);
+  if ((rc = exclusive_scan_u32(counts, g.TB, offsets, scratch, st))) return rc;
+  if ((rc = rt::copy_d2d(cursor, offsets, (g.TB + 1) * sizeof(uint32_t), st))) return rc;
+  prof.end(1, st);
+
+  prof.begin(2, st);
+  if ((rc = rt::launch<256>(MsmScatterBody<C>{d_scalars, g, cursor, entries}, g.n, st))) return rc;
+  prof.end(2, st);
+
+  prof.begin(3, st);
+  if ((rc = rt::launch<256>(TaskCountBody{offsets, g.L, ntasks}, g.TB, st))) return rc;
+  if ((rc = exclusive_scan_u32(ntasks, g.TB, task_off, scratch, st))) return rc;
+  if ((rc = rt::launch<256>(TaskFillBody{task_off, task_bucket}, g.TB, st))) return rc;
+  prof.end(3, st);
+
+  prof.begin(4, st);
+  if ((rc = rt::launch<128>(MsmAccumulateBody<C>{tables, g, offsets, task_off, task_bucket, entries, partial}, max_tasks, st))) return rc;
+  prof.end(4, st);
+
+  prof.begin(5, st);
+  if ((rc = rt::launch<64>(MsmSegmentBody<C>{g, task_off, partial, seg_out}, (size_t)g.S * g.nseg, st))) return rc;
+  for (uint32_t m = g.nseg; m > 1;) {
+    uint32_t half = (m + 1) / 2;
+    if ((rc = rt::launch<64>(MsmTreeAddBody<C>{seg_out, g.nseg, m, half}, (size_t)g.S * (m - half), st))) return rc;
+    m = half;
+  }
+  prof.end(5, st);
+
+  prof.begin(6, st);
+  if ((rc = rt::launch<32>(MsmFinalBody<C>{g, seg_out, g.nseg, d_out_xyzz, d_out_aff}, 1, st))) return rc;
+  prof.end(6, st);
+  return rt::OK;
+}
+
+}  // namespace pcgpu

@@ -1,0 +1,122 @@
+// Thin runtime layer: kernel launch, device memory and stream helpers.
+//
+// Every kernel in this library is a functor ("body") invoked once per logical thread by one of the
+// generic __global__ wrappers below.  When the sources are compiled by a host compiler with
+// -DPCGPU_EMUL (tests/host_emul only -- a unit-test harness, never shipped, never loaded by the
+// package) the same bodies run in a serial loop and "device" memory is host memory, which lets the
+// limb schedules, digit recoding, bucket bookkeeping and scan logic be checked on a machine
+// without a GPU.  The product build (nvcc, sm_100a) contains no host execution path.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef PCGPU_EMUL
+#include <cuda_runtime.h>
+#endif
+
+namespace pcgpu {
+namespace rt {
+
+enum : int {
+  OK = 0,
+  E_CUDA = -1,
+  E_OOM = -2,
+  E_BADARG = -3,
+  E_LEN = -4,
+  E_RANGE = -5,
+  E_DEGREE = -6,
+  E_HIDING = -7,
+};
+
+#ifdef PCGPU_EMUL
+// ------------------------------------------------------------------ host emulation (tests only)
+typedef void *stream_t;
+struct event_t { int dummy; };
+inline int dev_malloc(void **p, size_t bytes) { *p = ::malloc(bytes ? bytes : 1); return *p ? OK : E_OOM; }
+inline void dev_free(void *p) { ::free(p); }
+inline int dev_memset(void *p, int v, size_t bytes, stream_t) { memset(p, v, bytes); return OK; }
+inline int copy_h2d(void *d, const void *h, size_t bytes, stream_t) { memcpy(d, h, bytes); return OK; }
+inline int copy_d2h(void *h, const void *d, size_t bytes, stream_t) { memcpy(h, d, bytes); return OK; }
+inline int copy_d2d(void *d, const void *s, size_t bytes, stream_t) { memmove(d, s, bytes); return OK; }
+inline int stream_sync(stream_t) { return OK; }
+inline int last_error() { return OK; }
+
+template <int BLOCK, class Body>
+inline int launch(const Body &body, size_t n, stream_t) {
+  for (size_t i = 0; i < n; i++) body(i);
+  return OK;
+}
+template <class T> inline T atomic_add(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomic_or(T *p, T v) { T o = *p; *p = o | v; return o; }
+#define PCGPU_KERNEL_DEV inline
+
+#else
+// ------------------------------------------------------------------ CUDA (the product)
+typedef cudaStream_t stream_t;
+
+#define PCGPU_CUDA_TRY(expr)                         \
+  do {                                               \
+    cudaError_t _e = (expr);                         \
+    if (_e != cudaSuccess) return ::pcgpu::rt::map_cuda(_e); \
+  } while (0)
+
+inline int map_cuda(cudaError_t e) {
+  if (e == cudaSuccess) return OK;
+  if (e == cudaErrorMemoryAllocation) return E_OOM;
+  return E_CUDA;
+}
+inline int dev_malloc(void **p, size_t bytes) { return map_cuda(cudaMalloc(p, bytes ? bytes : 1)); }
+inline void dev_free(void *p) { if (p) cudaFree(p); }
+inline int dev_memset(void *p, int v, size_t bytes, stream_t s) { return map_cuda(cudaMemsetAsync(p, v, bytes, s)); }
+inline int copy_h2d(void *d, const void *h, size_t bytes, stream_t s) { return map_cuda(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s)); }
+inline int copy_d2h(void *h, const void *d, size_t bytes, stream_t s) { return map_cuda(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s)); }
+inline int copy_d2d(void *d, const void *s_, size_t bytes, stream_t s) { return map_cuda(cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, s)); }
+inline int stream_sync(stream_t s) { return map_cuda(cudaStreamSynchronize(s)); }
+inline int last_error() { return map_cuda(cudaGetLastError()); }
+
+template <class Body, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) run_kernel(const Body body, size_t n) {
+  size_t tid = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (tid < n) body(tid);
+}
+
+template <int BLOCK, class Body>
+inline int launch(const Body &body, size_t n, stream_t s) {
+  if (n == 0) return OK;
+  size_t grid = (n + BLOCK - 1) / BLOCK;
+  run_kernel<Body, BLOCK><<<(unsigned)grid, BLOCK, 0, s>>>(body, n);
+  return last_error();
+}
+template <class T> __device__ __forceinline__ T atomic_add(T *p, T v) { return atomicAdd(p, v); }
+template <class T> __device__ __forceinline__ T atomic_or(T *p, T v) { return atomicOr(p, v); }
+#define PCGPU_KERNEL_DEV __device__ __forceinline__
+#endif
+
+// Bump allocator over one device arena (re-used across calls; grown on demand).
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) { used = 0; return OK; }
+    if (base) dev_free(base);
+    base = nullptr; cap = 0; used = 0;
+    int rc = dev_malloc((void **)&base, bytes);
+    if (rc) return rc;
+    cap = bytes;
+    return OK;
+  }
+  template <class T> T *take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (used + bytes > cap) return nullptr;
+    T *p = (T *)(base + used);
+    used += bytes;
+    return p;
+  }
+  static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+  void release() { if (base) dev_free(base); base = nullptr; cap = used = 0; }
+};
+
+}  // namespace rt
+}  // namespace pcgpu

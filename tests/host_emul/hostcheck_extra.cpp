@@ -1,0 +1,38 @@
+// TEST HARNESS ONLY: exposes individual device functions (compiled for the host with emulated
+// carry flags) so tests can compare the production limb schedule against the 64-bit reference
+// multiplier and the Python big-integer oracle.
+#include <stddef.h>
+#include "../../poly-commit_b200/csrc/ec.cuh"
+using namespace pcgpu;
+
+template <class P>
+static void mul_many(const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int which) {
+  for (size_t i = 0; i < n; i++) {
+    Fp<P> x, y, r;
+    for (int j = 0; j < P::N; j++) { x.l[j] = a[i * P::N + j]; y.l[j] = b[i * P::N + j]; }
+    switch (which) {
+      case 0: r = mont_mul<P>(x, y); break;
+      case 1: r = mont_mul_ref<P>(x, y); break;
+      case 2: r = fp_add<P>(x, y); break;
+      case 3: r = fp_sub<P>(x, y); break;
+      case 4: r = fp_neg<P>(x); break;
+      case 5: r = fp_inv<P>(x); break;
+      default: r = Fp<P>::zero();
+    }
+    for (int j = 0; j < P::N; j++) out[i * P::N + j] = r.l[j];
+  }
+}
+
+// field: 0 bls Fq, 1 bls Fr, 2 bn Fq, 3 bn Fr, 4 pallas Fq, 5 pallas Fr
+extern "C" int hostcheck_field_op(int field, int which, const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n) {
+  switch (field) {
+    case 0: mul_many<Bls12381Fq>(a, b, out, n, which); break;
+    case 1: mul_many<Bls12381Fr>(a, b, out, n, which); break;
+    case 2: mul_many<Bn254Fq>(a, b, out, n, which); break;
+    case 3: mul_many<Bn254Fr>(a, b, out, n, which); break;
+    case 4: mul_many<PallasFq>(a, b, out, n, which); break;
+    case 5: mul_many<PallasFr>(a, b, out, n, which); break;
+    default: return -1;
+  }
+  return 0;
+}
