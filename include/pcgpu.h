@@ -128,6 +128,14 @@ int pcgpu_kzg_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coe
                    const pcgpu_srs *powers_of_gamma_g, const void *blind, size_t n_blind, uint32_t flags,
                    void *out_w_xy, uint8_t *out_w_inf, void *out_random_v);
 
+/* ---- diagnostics -------------------------------------------------------------------------------- */
+/* Device self-test of the field layer: n pseudo-random pairs per field (Fq and Fr of `curve`), production
+ * multiplier (carry-chained mad.lo/mad.hi schedule) against the plain 64-bit-accumulate multiplier compiled into
+ * the same kernel, plus a*a^-1 == 1 on a few elements.  *mismatches receives the number of disagreeing results. */
+/* Kernels launched by this library in the calling process so far (bench.py's gpu_launches). */
+uint64_t pcgpu_launch_count(void);
+int pcgpu_selftest_field(pcgpu_ctx *ctx, int curve, uint64_t seed, size_t n, uint64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,8 @@ def _load(path):
     lib.pcgpu_srs_len.restype = _sz
     lib.pcgpu_srs_len.argtypes = [_vp]
     lib.pcgpu_srs_curve.argtypes = [_vp]
+    lib.pcgpu_launch_count.restype = ctypes.c_uint64
+    lib.pcgpu_launch_count.argtypes = []
     sigs = {
         "pcgpu_init": [ctypes.c_int, ctypes.POINTER(_vp)],
         "pcgpu_destroy": [_vp],
@@ -58,6 +60,7 @@ def _load(path):
         "pcgpu_fr_div_linear": [_vp, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, ctypes.c_uint32],
         "pcgpu_fr_inner_product": [_vp, ctypes.c_int, _vp, _vp, _sz, _vp, ctypes.c_uint32],
         "pcgpu_fr_row_mul": [_vp, ctypes.c_int, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint32],
+        "pcgpu_selftest_field": [_vp, ctypes.c_int, ctypes.c_uint64, _sz, ctypes.POINTER(ctypes.c_uint64)],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
     }
@@ -143,6 +146,14 @@ class Engine:
         ms, cnt = ctypes.c_double(), ctypes.c_uint64()
         self._ck(self.lib.pcgpu_profile_get(self.ctx, stage, ctypes.byref(ms), ctypes.byref(cnt)))
         return ms.value, cnt.value
+
+    def launch_count(self):
+        return int(self.lib.pcgpu_launch_count())
+
+    def selftest_field(self, curve, seed=1, n=4096):
+        bad = ctypes.c_uint64()
+        self._ck(self.lib.pcgpu_selftest_field(self.ctx, curve, seed, n, ctypes.byref(bad)))
+        return bad.value
 
     # ---- SRS ----
     def srs_register(self, curve, bases_xy, inf=None, n=None, flags=0):

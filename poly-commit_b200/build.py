@@ -1,0 +1,50 @@
+#!/usr/bin/env python3
+"""Builds poly-commit_b200/libpcgpu.so: nvcc, sm_100a only, one translation unit per curve in parallel.
+No GPU is needed to build (nvcc cross-compiles).  Re-builds only when a source is newer than the library."""
+import concurrent.futures
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libpcgpu.so")
+UNITS = ["api", "inst_bls12_381", "inst_bn254", "inst_pallas"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def _newest_source():
+    srcs = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        [os.path.join(HERE, "..", "include", "pcgpu.h")]
+    return max(os.path.getmtime(s) for s in srcs)
+
+
+def _compile(unit, extra):
+    out = os.path.join(OBJ, unit + ".o")
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, unit + ".cu"), "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return unit, r.returncode, r.stdout + r.stderr, out
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    extra = list(extra) + (["-Xptxas", "-v"] if verbose else [])
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+        results = list(ex.map(lambda u: _compile(u, extra), UNITS))
+    objs = []
+    for unit, rc, log, out in results:
+        if verbose or rc:
+            sys.stderr.write(log)
+        if rc:
+            raise RuntimeError(f"nvcc failed on {unit}.cu")
+        objs.append(out)
+    subprocess.check_call(["nvcc", "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,553 @@
+// Host-side implementation templates behind the C ABI (include/pcgpu.h).  Host logic only: argument checks that mirror the
+// reference's error behaviour, staging of host buffers, stage timing, and curve dispatch.
+//
+// Compiled by nvcc for sm_100a into libpcgpu.so (the product).  The same file is also compiled by
+// g++ with -DPCGPU_EMUL into tests/host_emul/libpcgpu_hostcheck.so, a unit-test harness that runs
+// the kernel bodies serially; the package never loads that library.
+#pragma once
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/pcgpu.h"
+#include "frops.cuh"
+#include "msm.cuh"
+#include "srs.cuh"
+
+using namespace pcgpu;
+
+// ---------------------------------------------------------------------------------------------
+// profiling (CUDA events on the launching stream)
+// ---------------------------------------------------------------------------------------------
+enum { PROF_STAGES = 16 };
+struct Prof {
+  bool on = false;
+  double ms[PROF_STAGES] = {0};
+  uint64_t cnt[PROF_STAGES] = {0};
+#ifndef PCGPU_EMUL
+  cudaEvent_t ev[PROF_STAGES][2];
+  bool created = false, pending[PROF_STAGES] = {false};
+  void ensure() {
+    if (created) return;
+    for (int s = 0; s < PROF_STAGES; s++) { cudaEventCreate(&ev[s][0]); cudaEventCreate(&ev[s][1]); }
+    created = true;
+  }
+  void begin(int s, rt::stream_t st) { if (on) { ensure(); collect_one(s); cudaEventRecord(ev[s][0], st); } }
+  void end(int s, rt::stream_t st) { if (on) { cudaEventRecord(ev[s][1], st); pending[s] = true; } }
+  void collect_one(int s) {
+    if (!pending[s]) return;
+    cudaEventSynchronize(ev[s][1]);
+    float t = 0; cudaEventElapsedTime(&t, ev[s][0], ev[s][1]);
+    ms[s] += t; cnt[s]++; pending[s] = false;
+  }
+  void collect() { if (on) for (int s = 0; s < PROF_STAGES; s++) collect_one(s); }
+  void destroy() { if (created) for (int s = 0; s < PROF_STAGES; s++) { cudaEventDestroy(ev[s][0]); cudaEventDestroy(ev[s][1]); } created = false; }
+#else
+  void begin(int, rt::stream_t) {}
+  void end(int, rt::stream_t) {}
+  void collect() {}
+  void destroy() {}
+#endif
+  void reset() { for (int s = 0; s < PROF_STAGES; s++) { ms[s] = 0; cnt[s] = 0; } }
+};
+
+struct pcgpu_srs {
+  int curve;
+  size_t n;          // bases per table group
+  uint32_t c;        // window bits the groups were built for (0: raw bases only)
+  uint32_t groups;   // table groups (1: raw bases)
+  void *d_tables;    // groups * n affine points
+};
+
+struct pcgpu_ctx {
+  int device;
+  rt::stream_t own_stream, stream;
+  rt::Arena msm_arena, stage;
+  void *d_slots;    // 8 XYZZ result slots + 1 affine + err word, generously sized
+  Prof prof;
+  std::mutex mu;
+};
+
+static const size_t SLOT_BYTES = 256;  // >= sizeof(XYZZ<Bls12381>) = 192
+static const int NSLOTS = 8;
+
+#ifndef PCGPU_EMUL
+#define SET_DEVICE(ctx) do { if (cudaSetDevice((ctx)->device) != cudaSuccess) return PCGPU_E_CUDA; } while (0)
+#else
+#define SET_DEVICE(ctx) do { } while (0)
+#endif
+
+#define DISPATCH_CURVE(curve, CALL)                 \
+  switch (curve) {                                  \
+    case PCGPU_BLS12_381: { using C = Bls12381; CALL; } \
+    case PCGPU_BN254: { using C = Bn254; CALL; }    \
+    case PCGPU_PALLAS: { using C = Pallas; CALL; }  \
+    default: return PCGPU_E_BADARG;                 \
+  }
+
+
+
+
+
+
+
+// ---------------------------------------------------------------------------------------------
+// SRS
+// ---------------------------------------------------------------------------------------------
+template <class C>
+int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, size_t n, uint32_t flags, pcgpu_srs *srs) {
+  const size_t psz = sizeof(Affine<C>);
+  uint32_t groups = 1, c = 0;
+  if ((flags & PCGPU_SRS_PRECOMPUTE) && n > 0) {
+    c = srs_precompute_window(n);
+    groups = C::Fr::BITS / c + 1;
+  }
+  int rc = rt::dev_malloc(&srs->d_tables, psz * (n ? n : 1) * groups);
+  if (rc) return rc;
+  rt::stream_t st = ctx->stream;
+  if (n) {
+    if (flags & PCGPU_DEVICE_PTRS) rc = rt::copy_d2d(srs->d_tables, bases, psz * n, st);
+    else rc = rt::copy_h2d(srs->d_tables, bases, psz * n, st);
+    if (rc) return rc;
+    if (inf && !(flags & PCGPU_DEVICE_PTRS))
+      for (size_t i = 0; i < n; i++)
+        if (inf[i] && (rc = rt::dev_memset((char *)srs->d_tables + psz * i, 0, psz, st))) return rc;
+    if (groups > 1 && (rc = srs_build_groups<C>((Affine<C> *)srs->d_tables, n, c, groups, ctx->stage, st))) return rc;
+  }
+  srs->c = c; srs->groups = groups;
+  return rt::stream_sync(st);
+}
+
+
+
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+template <class C> static XYZZ<C> *slot_xyzz(pcgpu_ctx *ctx, int k) { return (XYZZ<C> *)((char *)ctx->d_slots + SLOT_BYTES * k); }
+template <class C> static Affine<C> *slot_aff(pcgpu_ctx *ctx) { return (Affine<C> *)((char *)ctx->d_slots + SLOT_BYTES * NSLOTS); }
+
+// sum of `count` XYZZ slots -> affine (single thread: count is tiny)
+template <class C>
+struct G1SumBody {
+  const XYZZ<C> *pts; size_t stride_bytes; size_t count; Affine<C> *out;
+  PCGPU_KERNEL_DEV void operator()(size_t) const {
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (size_t i = 0; i < count; i++) {
+      XYZZ<C> p = load_xyzz<C>((const XYZZ<C> *)((const char *)pts + stride_bytes * i));
+      xyzz_add<C>(acc, p);
+    }
+    *out = xyzz_to_affine<C>(acc);
+  }
+};
+
+template <class C>
+static void write_affine_out(const Affine<C> &a, void *out_xy, uint8_t *out_inf) {
+  bool inf = a.is_inf();
+  if (out_xy) memcpy(out_xy, &a, sizeof a);
+  if (out_inf) *out_inf = inf ? 1 : 0;
+}
+
+// One MSM into device slot `slot` (XYZZ).  d_scalars: device, n x 8 u32.
+template <class C>
+int msm_to_slot(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const uint32_t *d_scalars, size_t n,
+                       bool mont, int slot, uint32_t **d_err) {
+  rt::stream_t st = ctx->stream;
+  if (d_err) *d_err = nullptr;
+  if (n == 0) return rt::dev_memset(slot_xyzz<C>(ctx, slot), 0, sizeof(XYZZ<C>), st);
+  uint32_t c, groups;
+  if (srs->groups > 1 && n >= SRS_PRECOMPUTE_MIN_N) { c = srs->c; groups = srs->groups; }
+  else { c = msm_pick_c(n); groups = 1; }
+  MsmGeom g = msm_geometry(n, c, groups, C::Fr::BITS, mont, srs->n, base_offset);
+  int rc = msm_run<C>((const Affine<C> *)srs->d_tables, g, d_scalars, ctx->msm_arena, slot_xyzz<C>(ctx, slot),
+                      (Affine<C> *)nullptr, d_err, st, ctx->prof);
+  return rc;
+}
+
+// copies scalars (n x 32 bytes) to the staging arena unless they already live on the device
+static int stage_words(pcgpu_ctx *ctx, const void *src, size_t bytes, uint32_t flags, const uint32_t **out, uint32_t *dst) {
+  if (flags & PCGPU_DEVICE_PTRS) { *out = (const uint32_t *)src; return PCGPU_OK; }
+  int rc = rt::copy_h2d(dst, src, bytes, ctx->stream);
+  *out = dst;
+  return rc;
+}
+
+static int check_err_word(pcgpu_ctx *ctx, uint32_t *d_err) {
+  if (!d_err) return PCGPU_OK;
+  uint32_t h = 0;
+  int rc = rt::copy_d2h(&h, d_err, sizeof h, ctx->stream);
+  if (rc) return rc;
+  if ((rc = rt::stream_sync(ctx->stream))) return rc;
+  return h ? PCGPU_E_RANGE : PCGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MSM entry points
+// ---------------------------------------------------------------------------------------------
+template <class C>
+int msm_impl(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n, uint32_t flags,
+                    void *out_xy, uint8_t *out_inf, void *out_xyzz) {
+  if (base_offset > srs->n || n > srs->n - base_offset) return PCGPU_E_LEN;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  const uint32_t *d_scalars = nullptr;
+  if (n) {
+    if (!(flags & PCGPU_DEVICE_PTRS)) {
+      if ((rc = ctx->stage.reserve(rt::Arena::pad(n * 32) + 4096))) return rc;
+    }
+    uint32_t *buf = (flags & PCGPU_DEVICE_PTRS) ? nullptr : ctx->stage.take<uint32_t>(n * 8);
+    if ((rc = stage_words(ctx, scalars, n * 32, flags, &d_scalars, buf))) return rc;
+  }
+  uint32_t *d_err = nullptr;
+  if ((rc = msm_to_slot<C>(ctx, srs, base_offset, d_scalars, n, (flags & PCGPU_SCALARS_MONT) != 0, 0, &d_err))) return rc;
+  if (out_xyzz) {
+    XYZZ<C> h;
+    if ((rc = rt::copy_d2h(&h, slot_xyzz<C>(ctx, 0), sizeof h, st))) return rc;
+    if ((rc = check_err_word(ctx, d_err))) return rc;
+    if ((rc = rt::stream_sync(st))) return rc;
+    memcpy(out_xyzz, &h, sizeof h);
+    ctx->prof.collect();
+    return PCGPU_OK;
+  }
+  ctx->prof.begin(6, st);
+  if ((rc = rt::launch<32>(G1SumBody<C>{slot_xyzz<C>(ctx, 0), SLOT_BYTES, 1, slot_aff<C>(ctx)}, 1, st))) return rc;
+  ctx->prof.end(6, st);
+  Affine<C> h;
+  if ((rc = rt::copy_d2h(&h, slot_aff<C>(ctx), sizeof h, st))) return rc;
+  if ((rc = check_err_word(ctx, d_err))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  write_affine_out<C>(h, out_xy, out_inf);
+  ctx->prof.collect();
+  return PCGPU_OK;
+}
+
+
+
+template <class C>
+int g1_sum_impl(pcgpu_ctx *ctx, const void *xyzz, size_t count, void *out_xy, uint8_t *out_inf) {
+  rt::stream_t st = ctx->stream;
+  int rc;
+  if ((rc = ctx->stage.reserve(rt::Arena::pad(count * sizeof(XYZZ<C>)) + 4096))) return rc;
+  XYZZ<C> *d = ctx->stage.take<XYZZ<C>>(count ? count : 1);
+  if (count && (rc = rt::copy_h2d(d, xyzz, count * sizeof(XYZZ<C>), st))) return rc;
+  if ((rc = rt::launch<32>(G1SumBody<C>{d, sizeof(XYZZ<C>), count, slot_aff<C>(ctx)}, 1, st))) return rc;
+  Affine<C> h;
+  if ((rc = rt::copy_d2h(&h, slot_aff<C>(ctx), sizeof h, st))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  write_affine_out<C>(h, out_xy, out_inf);
+  return PCGPU_OK;
+}
+
+
+template <class C>
+int fixed_base_impl(pcgpu_ctx *ctx, const void *base_xy, const void *scalars, size_t n, uint32_t flags, void *out_xy) {
+  rt::stream_t st = ctx->stream;
+  int rc;
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  size_t need = rt::Arena::pad(64 * 15 * sizeof(Affine<C>)) + (dev ? 0 : rt::Arena::pad(n * 32 + 32) + rt::Arena::pad(n * sizeof(Affine<C>) + 32)) + 8192;
+  if ((rc = ctx->stage.reserve(need))) return rc;
+  Affine<C> *table = ctx->stage.take<Affine<C>>(64 * 15);
+  Affine<C> base;
+  memcpy(&base, base_xy, sizeof base);
+  if ((rc = rt::launch<64>(FixedBaseTableBody<C>{base, table}, 64, st))) return rc;
+  const uint32_t *d_s = (const uint32_t *)scalars; Affine<C> *d_o = (Affine<C> *)out_xy;
+  if (!dev) {
+    uint32_t *ts = ctx->stage.take<uint32_t>(n * 8 + 8); d_o = ctx->stage.take<Affine<C>>(n + 1);
+    if (n && (rc = rt::copy_h2d(ts, scalars, n * 32, st))) return rc;
+    d_s = ts;
+  }
+  if ((rc = rt::launch<128>(FixedBaseMulBody<C>{table, d_s, d_o}, n, st))) return rc;
+  if (!dev && n && (rc = rt::copy_d2h(out_xy, d_o, n * sizeof(Affine<C>), st))) return rc;
+  return rt::stream_sync(st);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Fr vector entry points
+// ---------------------------------------------------------------------------------------------
+template <class C>
+int fr_from_mont_impl(pcgpu_ctx *ctx, const void *in, void *out, size_t n, uint32_t flags) {
+  using R = typename C::Fr;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  if (n == 0) return PCGPU_OK;
+  if (flags & PCGPU_DEVICE_PTRS) {
+    if ((rc = rt::launch<256>(FrFromMontBody<R>{(const uint32_t *)in, (uint32_t *)out}, n, st))) return rc;
+    return rt::stream_sync(st);
+  }
+  if ((rc = ctx->stage.reserve(2 * rt::Arena::pad(n * 32) + 4096))) return rc;
+  uint32_t *d_in = ctx->stage.take<uint32_t>(n * 8), *d_out = ctx->stage.take<uint32_t>(n * 8);
+  if ((rc = rt::copy_h2d(d_in, in, n * 32, st))) return rc;
+  if ((rc = rt::launch<256>(FrFromMontBody<R>{d_in, d_out}, n, st))) return rc;
+  if ((rc = rt::copy_d2h(out, d_out, n * 32, st))) return rc;
+  return rt::stream_sync(st);
+}
+
+template <class C>
+int fr_axpy_impl(pcgpu_ctx *ctx, void *y, const void *c, const void *x, size_t n, uint32_t flags) {
+  using R = typename C::Fr;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  if (n == 0) return PCGPU_OK;
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  if ((rc = ctx->stage.reserve((dev ? 0 : 2 * rt::Arena::pad(n * 32)) + 4096))) return rc;
+  uint32_t *d_c = ctx->stage.take<uint32_t>(8);
+  if ((rc = rt::copy_h2d(d_c, c, 32, st))) return rc;
+  uint32_t *d_y = (uint32_t *)y; const uint32_t *d_x = (const uint32_t *)x;
+  if (!dev) {
+    uint32_t *ty = ctx->stage.take<uint32_t>(n * 8), *tx = ctx->stage.take<uint32_t>(n * 8);
+    if ((rc = rt::copy_h2d(ty, y, n * 32, st))) return rc;
+    if ((rc = rt::copy_h2d(tx, x, n * 32, st))) return rc;
+    d_y = ty; d_x = tx;
+  }
+  ctx->prof.begin(8, st);
+  if ((rc = rt::launch<256>(FrAxpyBody<R>{d_y, d_c, d_x}, n, st))) return rc;
+  ctx->prof.end(8, st);
+  if (!dev && (rc = rt::copy_d2h(y, d_y, n * 32, st))) return rc;
+  rc = rt::stream_sync(st);
+  ctx->prof.collect();
+  return rc;
+}
+
+
+template <class C>
+int fr_div_impl(pcgpu_ctx *ctx, const void *p, size_t n, const void *z, void *q, void *rem, uint32_t flags) {
+  using R = typename C::Fr;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  size_t need = rt::Arena::pad(div_scratch_words(n) * 4) + (dev ? 0 : 2 * rt::Arena::pad(n * 32 + 32)) + 8192;
+  if ((rc = ctx->stage.reserve(need))) return rc;
+  uint32_t *d_z = ctx->stage.take<uint32_t>(8), *d_rem = ctx->stage.take<uint32_t>(8);
+  uint32_t *scratch = ctx->stage.take<uint32_t>(div_scratch_words(n));
+  if ((rc = rt::copy_h2d(d_z, z, 32, st))) return rc;
+  const uint32_t *d_p = (const uint32_t *)p; uint32_t *d_q = (uint32_t *)q;
+  if (!dev) {
+    uint32_t *tp = ctx->stage.take<uint32_t>(n * 8 + 8); d_q = ctx->stage.take<uint32_t>(n * 8 + 8);
+    if (n && (rc = rt::copy_h2d(tp, p, n * 32, st))) return rc;
+    d_p = tp;
+  }
+  ctx->prof.begin(7, st);
+  if ((rc = fr_div_linear<R>(d_p, n, d_z, d_q, d_rem, scratch, st))) return rc;
+  ctx->prof.end(7, st);
+  if (!dev && n > 1 && (rc = rt::copy_d2h(q, d_q, (n - 1) * 32, st))) return rc;
+  uint32_t hrem[8];
+  if ((rc = rt::copy_d2h(hrem, d_rem, 32, st))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  if (rem) memcpy(rem, hrem, 32);
+  ctx->prof.collect();
+  return PCGPU_OK;
+}
+
+
+template <class C>
+int fr_ip_impl(pcgpu_ctx *ctx, const void *a, const void *b, size_t n, void *out, uint32_t flags) {
+  using R = typename C::Fr;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  if ((rc = ctx->stage.reserve((dev ? 0 : 2 * rt::Arena::pad(n * 32 + 32)) + rt::Arena::pad(IP_THREADS * 32) + 8192))) return rc;
+  uint32_t *scratch = ctx->stage.take<uint32_t>(IP_THREADS * 8), *d_out = ctx->stage.take<uint32_t>(8);
+  const uint32_t *d_a = (const uint32_t *)a, *d_b = (const uint32_t *)b;
+  if (!dev) {
+    uint32_t *ta = ctx->stage.take<uint32_t>(n * 8 + 8), *tb = ctx->stage.take<uint32_t>(n * 8 + 8);
+    if (n && (rc = rt::copy_h2d(ta, a, n * 32, st))) return rc;
+    if (n && (rc = rt::copy_h2d(tb, b, n * 32, st))) return rc;
+    d_a = ta; d_b = tb;
+  }
+  if ((rc = fr_inner_product<R>(d_a, d_b, n, d_out, scratch, st))) return rc;
+  if ((rc = rt::copy_d2h(out, d_out, 32, st))) return rc;
+  return rt::stream_sync(st);
+}
+
+
+template <class C>
+int fr_row_mul_impl(pcgpu_ctx *ctx, const void *v, const void *m, size_t rows, size_t cols, void *out, uint32_t flags) {
+  using R = typename C::Fr;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  if (cols == 0) return PCGPU_OK;
+  if (dev) {
+    if ((rc = rt::launch<128>(FrRowMulBody<R>{(const uint32_t *)v, (const uint32_t *)m, rows, cols, (uint32_t *)out}, cols, st))) return rc;
+    return rt::stream_sync(st);
+  }
+  if ((rc = ctx->stage.reserve(rt::Arena::pad(rows * 32 + 32) + rt::Arena::pad(rows * cols * 32 + 32) + rt::Arena::pad(cols * 32) + 8192))) return rc;
+  uint32_t *dv = ctx->stage.take<uint32_t>(rows * 8 + 8), *dm = ctx->stage.take<uint32_t>(rows * cols * 8 + 8),
+           *dout = ctx->stage.take<uint32_t>(cols * 8);
+  if (rows && (rc = rt::copy_h2d(dv, v, rows * 32, st))) return rc;
+  if (rows && (rc = rt::copy_h2d(dm, m, rows * cols * 32, st))) return rc;
+  if ((rc = rt::launch<128>(FrRowMulBody<R>{dv, dm, rows, cols, dout}, cols, st))) return rc;
+  if ((rc = rt::copy_d2h(out, dout, cols * 32, st))) return rc;
+  return rt::stream_sync(st);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// KZG10 fused calls
+// ---------------------------------------------------------------------------------------------
+static size_t trim_trailing_zeros(const void *coeffs, size_t n) {
+  const uint64_t *c = (const uint64_t *)coeffs;
+  while (n > 0 && !(c[4 * (n - 1)] | c[4 * (n - 1) + 1] | c[4 * (n - 1) + 2] | c[4 * (n - 1) + 3])) n--;
+  return n;
+}
+
+template <class C>
+int finish_sum(pcgpu_ctx *ctx, int nslots, uint32_t *e0, uint32_t *e1, void *out_xy, uint8_t *out_inf) {
+  rt::stream_t st = ctx->stream;
+  int rc;
+  ctx->prof.begin(6, st);
+  if ((rc = rt::launch<32>(G1SumBody<C>{slot_xyzz<C>(ctx, 0), SLOT_BYTES, (size_t)nslots, slot_aff<C>(ctx)}, 1, st))) return rc;
+  ctx->prof.end(6, st);
+  Affine<C> h;
+  if ((rc = rt::copy_d2h(&h, slot_aff<C>(ctx), sizeof h, st))) return rc;
+  if ((rc = check_err_word(ctx, e0))) return rc;
+  if ((rc = check_err_word(ctx, e1))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  write_affine_out<C>(h, out_xy, out_inf);
+  ctx->prof.collect();
+  return PCGPU_OK;
+}
+
+template <class C>
+int kzg_commit_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, size_t n, const pcgpu_srs *gamma,
+                           const void *blind, size_t n_blind, uint32_t flags, void *out_xy, uint8_t *out_inf) {
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  if (!dev) { n = trim_trailing_zeros(coeffs, n); n_blind = trim_trailing_zeros(blind, n_blind); }
+  if (n > pg->n) return PCGPU_E_DEGREE;                      // check_degree_is_too_large, kzg10/mod.rs:163
+  if (n_blind && (!gamma || n_blind > gamma->n)) return PCGPU_E_HIDING;  // check_hiding_bound, :190-193
+  rt::stream_t st = ctx->stream;
+  int rc;
+  if ((rc = ctx->stage.reserve(dev ? 4096 : rt::Arena::pad(n * 32 + 32) + rt::Arena::pad(n_blind * 32 + 32) + 4096))) return rc;
+  const uint32_t *d_c = (const uint32_t *)coeffs, *d_b = (const uint32_t *)blind;
+  if (!dev) {
+    uint32_t *tc = ctx->stage.take<uint32_t>(n * 8 + 8), *tb = ctx->stage.take<uint32_t>(n_blind * 8 + 8);
+    if (n && (rc = rt::copy_h2d(tc, coeffs, n * 32, st))) return rc;
+    if (n_blind && (rc = rt::copy_h2d(tb, blind, n_blind * 32, st))) return rc;
+    d_c = tc; d_b = tb;
+  }
+  uint32_t *e0 = nullptr, *e1 = nullptr;
+  // the two MSMs share ctx->msm_arena; the error word of the first is read before the second starts
+  if ((rc = msm_to_slot<C>(ctx, pg, 0, d_c, n, true, 0, &e0))) return rc;
+  if (n_blind) {
+    if ((rc = check_err_word(ctx, e0))) return rc;
+    e0 = nullptr;
+    ctx->prof.collect();
+    if ((rc = msm_to_slot<C>(ctx, gamma, 0, d_b, n_blind, true, 1, &e1))) return rc;
+  }
+  return finish_sum<C>(ctx, n_blind ? 2 : 1, e0, e1, out_xy, out_inf);
+}
+
+
+template <class C>
+int kzg_open_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, size_t n, const void *z,
+                         const pcgpu_srs *gamma, const void *blind, size_t n_blind, uint32_t flags, void *out_xy,
+                         uint8_t *out_inf, void *out_random_v) {
+  using R = typename C::Fr;
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  if (!dev) { n = trim_trailing_zeros(coeffs, n); n_blind = trim_trailing_zeros(blind, n_blind); }
+  if (n > pg->n) return PCGPU_E_DEGREE;  // kzg10/mod.rs:292
+  if (n_blind && (!gamma || n_blind - 1 > gamma->n)) return PCGPU_E_HIDING;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  size_t need = rt::Arena::pad(div_scratch_words(n > n_blind ? n : n_blind) * 4) + 2 * rt::Arena::pad(n * 32 + 32) +
+                2 * rt::Arena::pad(n_blind * 32 + 32) + 8192;
+  if ((rc = ctx->stage.reserve(need))) return rc;
+  uint32_t *d_z = ctx->stage.take<uint32_t>(8), *d_rem = ctx->stage.take<uint32_t>(8), *d_rv = ctx->stage.take<uint32_t>(8);
+  uint32_t *scratch = ctx->stage.take<uint32_t>(div_scratch_words(n > n_blind ? n : n_blind));
+  uint32_t *d_q = ctx->stage.take<uint32_t>(n * 8 + 8), *d_bq = ctx->stage.take<uint32_t>(n_blind * 8 + 8);
+  if ((rc = rt::copy_h2d(d_z, z, 32, st))) return rc;
+  const uint32_t *d_c = (const uint32_t *)coeffs, *d_b = (const uint32_t *)blind;
+  if (!dev) {
+    uint32_t *tc = ctx->stage.take<uint32_t>(n * 8 + 8), *tb = ctx->stage.take<uint32_t>(n_blind * 8 + 8);
+    if (n && (rc = rt::copy_h2d(tc, coeffs, n * 32, st))) return rc;
+    if (n_blind && (rc = rt::copy_h2d(tb, blind, n_blind * 32, st))) return rc;
+    d_c = tc; d_b = tb;
+  }
+  // witness = p / (X - z)   (kzg10/mod.rs:222-226)
+  ctx->prof.begin(7, st);
+  if ((rc = fr_div_linear<R>(d_c, n, d_z, d_q, d_rem, scratch, st))) return rc;
+  ctx->prof.end(7, st);
+  uint32_t *e0 = nullptr, *e1 = nullptr;
+  if ((rc = msm_to_slot<C>(ctx, pg, 0, d_q, n ? n - 1 : 0, true, 0, &e0))) return rc;
+  if (n_blind) {
+    if ((rc = check_err_word(ctx, e0))) return rc;
+    e0 = nullptr;
+    ctx->prof.collect();
+    if ((rc = fr_div_linear<R>(d_b, n_blind, d_z, d_bq, d_rv, scratch, st))) return rc;  // rem = blind(z), :264
+    if ((rc = msm_to_slot<C>(ctx, gamma, 0, d_bq, n_blind - 1, true, 1, &e1))) return rc;
+    if (out_random_v) {
+      if ((rc = rt::copy_d2h(out_random_v, d_rv, 32, st))) return rc;
+    }
+  }
+  return finish_sum<C>(ctx, n_blind ? 2 : 1, e0, e1, out_xy, out_inf);
+}
+
+
+
+// ---------------------------------------------------------------------------------------------
+// device self-test of the field layer
+// ---------------------------------------------------------------------------------------------
+template <class P>
+struct FieldSelfTestBody {
+  uint64_t seed; uint32_t *bad;
+  static PCGPU_DEV uint64_t mix(uint64_t x) {  // splitmix64
+    x += 0x9e3779b97f4a7c15ull; x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+  }
+  PCGPU_KERNEL_DEV void operator()(size_t i) const {
+    Fp<P> a, b;
+    uint64_t s = seed + 0x1000003ull * i;
+    for (int j = 0; j < P::N; j += 2) {
+      s = mix(s); a.l[j] = (uint32_t)s; a.l[j + 1] = (uint32_t)(s >> 32);
+      s = mix(s); b.l[j] = (uint32_t)s; b.l[j + 1] = (uint32_t)(s >> 32);
+    }
+    // force the operands below p: clear the top bits, then one conditional subtraction
+    const uint32_t topmask = (P::BITS % 32) ? ((1u << (P::BITS % 32)) - 1) : 0xffffffffu;
+    a.l[P::N - 1] &= topmask; b.l[P::N - 1] &= topmask;
+    fp_reduce_once<P>(a.l); fp_reduce_once<P>(b.l);
+    if (i % 7 == 0) a = fp_neg<P>(Fp<P>::one());      // p - R
+    if (i % 11 == 0) b = fp_sub<P>(Fp<P>::zero(), Fp<P>::one());
+    Fp<P> x = mont_mul<P>(a, b), y = mont_mul_ref<P>(a, b);
+    uint32_t wrong = (x != y) ? 1u : 0u;
+    Fp<P> c = fp_sub<P>(fp_add<P>(a, b), b);
+    wrong += (c != a) ? 1u : 0u;
+    if (i < 64 && !a.is_zero()) {
+      Fp<P> inv = fp_inv<P>(a);
+      wrong += (mont_mul<P>(a, inv) != Fp<P>::one()) ? 1u : 0u;
+    }
+    if (wrong) rt::atomic_add(bad, wrong);
+  }
+};
+
+template <class C>
+int selftest_field_impl(pcgpu_ctx *ctx, uint64_t seed, size_t n, uint64_t *mismatches) {
+  rt::stream_t st = ctx->stream;
+  int rc;
+  uint32_t *d_bad = (uint32_t *)((char *)ctx->d_slots + SLOT_BYTES * (NSLOTS + 1));
+  if ((rc = rt::dev_memset(d_bad, 0, 8, st))) return rc;
+  if ((rc = rt::launch<128>(FieldSelfTestBody<typename C::Fq>{seed, d_bad}, n, st))) return rc;
+  if ((rc = rt::launch<128>(FieldSelfTestBody<typename C::Fr>{seed ^ 0x5555, d_bad}, n, st))) return rc;
+  uint32_t h = 0;
+  if ((rc = rt::copy_d2h(&h, d_bad, 4, st))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  *mismatches = h;
+  return PCGPU_OK;
+}
+
+// Explicit instantiation list: `PCGPU_INSTANTIATE(Curve, extern)` declares, `PCGPU_INSTANTIATE(Curve, )` defines.
+#define PCGPU_INSTANTIATE(C, EXT)                                                                                          \
+  EXT template int srs_register_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, pcgpu_srs *);        \
+  EXT template int msm_impl<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const void *, size_t, uint32_t, void *, uint8_t *, void *); \
+  EXT template int g1_sum_impl<C>(pcgpu_ctx *, const void *, size_t, void *, uint8_t *);                                   \
+  EXT template int fixed_base_impl<C>(pcgpu_ctx *, const void *, const void *, size_t, uint32_t, void *);                  \
+  EXT template int fr_from_mont_impl<C>(pcgpu_ctx *, const void *, void *, size_t, uint32_t);                              \
+  EXT template int fr_axpy_impl<C>(pcgpu_ctx *, void *, const void *, const void *, size_t, uint32_t);                     \
+  EXT template int fr_div_impl<C>(pcgpu_ctx *, const void *, size_t, const void *, void *, void *, uint32_t);              \
+  EXT template int fr_ip_impl<C>(pcgpu_ctx *, const void *, const void *, size_t, void *, uint32_t);                       \
+  EXT template int fr_row_mul_impl<C>(pcgpu_ctx *, const void *, const void *, size_t, size_t, void *, uint32_t);          \
+  EXT template int kzg_commit_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const pcgpu_srs *, const void *, \
+                                      size_t, uint32_t, void *, uint8_t *);                                                \
+  EXT template int kzg_open_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const void *, const pcgpu_srs *, \
+                                    const void *, size_t, uint32_t, void *, uint8_t *, void *); \
+  EXT template int selftest_field_impl<C>(pcgpu_ctx *, uint64_t, size_t, uint64_t *);

@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 
 #ifndef PCGPU_EMUL
 #include <cuda_runtime.h>
@@ -29,6 +30,9 @@ enum : int {
   E_DEGREE = -6,
   E_HIDING = -7,
 };
+
+// number of kernels this library has launched in the process (bench.py reports it as gpu_launches)
+inline std::atomic<uint64_t> &launch_counter() { static std::atomic<uint64_t> c{0}; return c; }
 
 #ifdef PCGPU_EMUL
 // ------------------------------------------------------------------ host emulation (tests only)
@@ -87,6 +91,7 @@ inline int launch(const Body &body, size_t n, stream_t s) {
   if (n == 0) return OK;
   size_t grid = (n + BLOCK - 1) / BLOCK;
   run_kernel<Body, BLOCK><<<(unsigned)grid, BLOCK, 0, s>>>(body, n);
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
   return last_error();
 }
 template <class T> __device__ __forceinline__ T atomic_add(T *p, T v) { return atomicAdd(p, v); }

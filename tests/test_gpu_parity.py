@@ -1,0 +1,146 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA library through its C ABI against the CPU oracle
+on the same seeded inputs -- bit-exact (all arithmetic is integer / finite field; tolerance = 0).
+
+Small and medium sizes compare directly against the oracle (definition-level MSM or its Pippenger); the
+BASELINE.json size (2^20, BLS12-381) is compared directly as well (the C oracle's Pippenger finishes it in
+seconds on the box's cores) and additionally through size-independent properties: linearity
+(kzg10/mod.rs:520-544 add_commitments_test), index-range additivity, q*(X-z)+p(z) == p.
+"""
+import numpy as np
+import pytest
+
+from oracle import orc, pyref
+from tests import util
+# the same case bodies that run under host emulation, here against the real device
+from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_fr_vector_ops,  # noqa: F401
+                                  test_kzg_commit_open, test_msm_edge_scalars, test_msm_infinity_bases,
+                                  test_msm_partial_and_sum, test_msm_precomputed_tables, test_msm_vs_oracle,
+                                  test_row_mul_reference_kat)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(gpu_engine):
+    return gpu_engine
+
+
+def gpu_srs(eng, cname, n, seed=1):
+    """powers_of_g = beta^i * G built ON THE DEVICE (pcgpu_g1_fixed_base_mul), spot-checked against the oracle."""
+    C = pyref.Curve(cname)
+    beta = util.rand_fr(cname, 1, 1000 + seed, mont=True)[0]
+    pows = orc.fr_powers_canonical(C.id, beta, n)
+    xy = eng.fixed_base_mul(C.id, orc.g1_generator(C.id), pows)
+    idx = np.unique(np.concatenate([[0, 1, n - 1], util.rng(seed).integers(0, n, size=12)]))
+    exp, _ = orc.fixed_base_batch_mul(C.id, orc.g1_generator(C.id), pows[idx])
+    assert (xy[idx] == exp).all()
+    assert orc.g1_on_curve(C.id, xy[:: max(1, n // 4096)]) == 0
+    return xy
+
+
+@pytest.mark.parametrize("curve", [0, 1, 2])
+def test_field_selftest(eng, curve):
+    assert eng.selftest_field(curve, seed=3, n=1 << 16) == 0
+
+
+@pytest.mark.parametrize("cname,logn", [("bls12_381", 10), ("bls12_381", 14), ("bls12_381", 16), ("bn254", 15), ("pallas", 15)])
+def test_msm_medium(eng, pc, cname, logn):
+    """cfg1 shape (2^10 + 1 coefficients) and medium sizes, raw bases and window-folded tables."""
+    C = pyref.Curve(cname)
+    n = (1 << logn) + 1
+    bases = gpu_srs(eng, cname, n, seed=logn)
+    sc = util.rand_fr(cname, n, seed=50 + logn, mont=False)
+    exp = orc.msm(C.id, bases, sc)
+    for flags in (0, pc.SRS_PRECOMPUTE):
+        srs = eng.srs_register(C.id, bases, flags=flags)
+        got = eng.msm(srs, sc)
+        assert got[1] == exp[1] and (got[0] == exp[0]).all(), (cname, logn, flags)
+        srs.release()
+
+
+def test_msm_skewed_scalars(eng, pc):
+    """'witness-like' distribution: 50% zeros, 25% < 2^16, 25% uniform."""
+    cname, n = "bls12_381", 1 << 15
+    C = pyref.Curve(cname)
+    bases = gpu_srs(eng, cname, n, seed=7)
+    sc = util.rand_fr(cname, n, seed=60, mont=False)
+    g = util.rng(61)
+    kind = g.integers(0, 4, size=n)
+    sc[kind < 2] = 0
+    small = kind == 2
+    sc[small, 1:] = 0
+    sc[small, 0] &= np.uint64(0xFFFF)
+    exp = orc.msm(C.id, bases, sc)
+    for flags in (0, pc.SRS_PRECOMPUTE):
+        srs = eng.srs_register(C.id, bases, flags=flags)
+        got = eng.msm(srs, sc)
+        assert (got[0] == exp[0]).all()
+        srs.release()
+
+
+@pytest.fixture(scope="module")
+def big(eng, pc):
+    """BASELINE.json cfg2 inputs: BLS12-381, 2^20 + 1 powers, a degree-2^20 polynomial."""
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    n = (1 << 20) + 1
+    bases = gpu_srs(eng, cname, n, seed=20)
+    coeffs = util.rand_fr(cname, n, seed=70, mont=True)
+    srs = eng.srs_register(C.id, bases, flags=pc.SRS_PRECOMPUTE)
+    raw = eng.srs_register(C.id, bases)
+    return dict(C=C, n=n, bases=bases, coeffs=coeffs, srs=srs, raw=raw)
+
+
+def test_cfg2_commit_open_vs_oracle(eng, big):
+    """MarlinKZG10 commit+open, degree 2^20, BLS12-381: bit-exact against the C oracle (both MSM paths)."""
+    C, n = big["C"], big["n"]
+    z = util.rand_fr("bls12_381", 1, seed=71, mont=True)[0]
+    rc, exy, einf = orc.kzg_commit(C.id, big["bases"], big["coeffs"])
+    assert rc == 0
+    for srs in (big["srs"], big["raw"]):
+        got = eng.kzg_commit(srs, big["coeffs"])
+        assert got[1] == einf and (got[0] == exy).all()
+    rc, wxy, winf, _ = orc.kzg_open(C.id, big["bases"], big["coeffs"], z)
+    assert rc == 0
+    got = eng.kzg_open(big["srs"], big["coeffs"], z)
+    assert got[1] == winf and (got[0] == wxy).all()
+
+
+def test_cfg2_properties(eng, pc, big):
+    """size-independent properties at 2^20: linearity, index-range additivity, division identity."""
+    C, n = big["C"], big["n"]
+    srs = big["srs"]
+    p = big["coeffs"]
+    f = util.rand_fr("bls12_381", 1, seed=72, mont=True)[0]
+    # commit(f * p) == f * commit(p)     (add_commitments_test, kzg10/mod.rs:520-544)
+    fp = eng.fr_axpy(C.id, np.zeros_like(p), f, p)
+    c1 = eng.kzg_commit(srs, fp)
+    c0 = eng.kzg_commit(srs, p)
+    f_canon = orc.field_unop("orc_fr_from_mont", C.id, f.reshape(1, 4))
+    exp, _ = orc.g1_mul(C.id, c0[0], f_canon)
+    assert (c1[0] == exp).all()
+    # sum of index-range partials == whole
+    cuts = [0, n // 3, n // 2, n]
+    parts = [eng.msm_partial(srs, p[a:b], n=b - a, base_offset=a, flags=pc.SCALARS_MONT) for a, b in zip(cuts[:-1], cuts[1:])]
+    tot = eng.g1_sum_xyzz(C.id, np.concatenate(parts))
+    assert (tot[0] == c0[0]).all()
+    # division: q*(X - z) + rem == p, checked at a second random point t:  q(t)*(t - z) + rem == p(t)
+    z = util.rand_fr("bls12_381", 1, seed=73, mont=True)[0]
+    t = util.rand_fr("bls12_381", 1, seed=74, mont=True)[0]
+    q, rem = eng.fr_div_linear(C.id, p, z)
+    _, qt = eng.fr_div_linear(C.id, q, t)
+    _, pt = eng.fr_div_linear(C.id, p, t)
+    zi, ti, qi, ri, pi = (C.fr_from_limbs(a, True)[0] for a in (z, t, qt, rem, pt))
+    assert (qi * (ti - zi) + ri) % C.r == pi
+    assert (rem == orc.fr_eval(C.id, p, z)).all()
+
+
+def test_device_pointer_path(eng, pc, big):
+    """PCGPU_DEVICE_PTRS: scalars already resident in HBM (the bench's `value` leg) give the same point."""
+    import torch
+    C, n = big["C"], big["n"]
+    p = big["coeffs"]
+    d = torch.from_numpy(p.view(np.int64)).cuda()
+    got = eng.kzg_commit(big["srs"], d.data_ptr(), n=n, flags=pc.DEVICE_PTRS)
+    exp = eng.kzg_commit(big["srs"], p)
+    assert (got[0] == exp[0]).all()

@@ -30,25 +30,39 @@ def rand_fr_ints(curve, n, seed):
     return out
 
 
-def rand_fr(curve, n, seed, mont):
-    """(n, 4) uint64 uniform field elements; canonical integers or Montgomery form."""
-    C = pyref.Curve(curve)
-    g = rng(seed)
-    arr = g.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+def _uniform_below_r(C, n, g):
+    """(n, 4) uint64, uniform integers in [0, r): vectorised rejection sampling on 255/254-bit draws."""
     top_bits = C.r.bit_length() - 192
-    arr[:, 3] &= np.uint64((1 << top_bits) - 1)
-    # rejection: redraw rows >= r (vectorised check on the top limb is enough to be rare; fix exactly below)
-    r_l = [(C.r >> (64 * j)) & (2**64 - 1) for j in range(4)]
-    for i in range(n):
-        while True:
-            v = sum(int(arr[i, j]) << (64 * j) for j in range(4))
-            if v < C.r:
-                break
-            arr[i] = g.integers(0, 1 << 64, size=4, dtype=np.uint64)
-            arr[i, 3] &= np.uint64((1 << top_bits) - 1)
-    if mont:
+    r_l = [np.uint64((C.r >> (64 * j)) & (2**64 - 1)) for j in range(4)]
+    out = np.empty((n, 4), dtype=np.uint64)
+    todo = np.arange(n)
+    while todo.size:
+        a = g.integers(0, 1 << 64, size=(todo.size, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << top_bits) - 1)
+        lt = np.zeros(todo.size, dtype=bool)
+        eq = np.ones(todo.size, dtype=bool)
+        for j in (3, 2, 1, 0):
+            lt |= eq & (a[:, j] < r_l[j])
+            eq &= a[:, j] == r_l[j]
+        out[todo[lt]] = a[lt]
+        todo = todo[~lt]
+    return out
+
+
+def rand_fr(curve, n, seed, mont):
+    """(n, 4) uint64 uniform field elements: canonical integers (mont=False) or Montgomery form (mont=True;
+    converted through the oracle so that the canonical values are the seeded draws)."""
+    C = pyref.Curve(curve)
+    arr = _uniform_below_r(C, n, rng(seed))
+    if mont and n:
         arr = orc.field_unop("orc_fr_to_mont", C.id, arr)
     return arr
+
+
+def rand_fr_fast(curve, n, seed):
+    """(n, 4) uint64 uniform field elements in Montgomery form: the uniform draw IS the Montgomery
+    representation (x -> x*R^-1 is a bijection of Z_r), so no conversion pass is needed at 2^20+ sizes."""
+    return _uniform_below_r(pyref.Curve(curve), n, rng(seed))
 
 
 def fr_const(curve, value, mont=True):
