@@ -11,6 +11,8 @@
 
 #include "../../include/pcgpu.h"
 #include "frops.cuh"
+#include "host_ec.hpp"
+#include <chrono>
 #include "msm.cuh"
 #include "srs.cuh"
 
@@ -124,44 +126,37 @@ int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, siz
 // ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
-template <class C> static XYZZ<C> *slot_xyzz(pcgpu_ctx *ctx, int k) { return (XYZZ<C> *)((char *)ctx->d_slots + SLOT_BYTES * k); }
-template <class C> static Affine<C> *slot_aff(pcgpu_ctx *ctx) { return (Affine<C> *)((char *)ctx->d_slots + SLOT_BYTES * NSLOTS); }
-
-// sum of `count` XYZZ slots -> affine (single thread: count is tiny)
+// One MSM: device pipeline, then the S*c bit-plane sums come back to the host, which combines them
+// (host_ec.hpp).  d_scalars: device, n x 8 u32.  Synchronises the stream.
 template <class C>
-struct G1SumBody {
-  const XYZZ<C> *pts; size_t stride_bytes; size_t count; Affine<C> *out;
-  PCGPU_KERNEL_DEV void operator()(size_t) const {
-    XYZZ<C> acc = XYZZ<C>::inf();
-    for (size_t i = 0; i < count; i++) {
-      XYZZ<C> p = load_xyzz<C>((const XYZZ<C> *)((const char *)pts + stride_bytes * i));
-      xyzz_add<C>(acc, p);
-    }
-    *out = xyzz_to_affine<C>(acc);
-  }
-};
-
-template <class C>
-static void write_affine_out(const Affine<C> &a, void *out_xy, uint8_t *out_inf) {
-  bool inf = a.is_inf();
-  if (out_xy) memcpy(out_xy, &a, sizeof a);
-  if (out_inf) *out_inf = inf ? 1 : 0;
-}
-
-// One MSM into device slot `slot` (XYZZ).  d_scalars: device, n x 8 u32.
-template <class C>
-int msm_to_slot(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const uint32_t *d_scalars, size_t n,
-                       bool mont, int slot, uint32_t **d_err) {
+static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const uint32_t *d_scalars, size_t n,
+                       bool mont, host::HXYZZ<C> *out) {
   rt::stream_t st = ctx->stream;
-  if (d_err) *d_err = nullptr;
-  if (n == 0) return rt::dev_memset(slot_xyzz<C>(ctx, slot), 0, sizeof(XYZZ<C>), st);
+  *out = host::HXYZZ<C>::inf();
+  if (n == 0) return PCGPU_OK;
   uint32_t c, groups;
   if (srs->groups > 1 && n >= SRS_PRECOMPUTE_MIN_N) { c = srs->c; groups = srs->groups; }
   else { c = msm_pick_c(n); groups = 1; }
   MsmGeom g = msm_geometry(n, c, groups, C::Fr::BITS, mont, srs->n, base_offset);
-  int rc = msm_run<C>((const Affine<C> *)srs->d_tables, g, d_scalars, ctx->msm_arena, slot_xyzz<C>(ctx, slot),
-                      (Affine<C> *)nullptr, d_err, st, ctx->prof);
-  return rc;
+  const XYZZ<C> *d_planes = nullptr; size_t stride = 0; uint32_t *d_err = nullptr;
+  int rc = msm_run<C>((const Affine<C> *)srs->d_tables, g, d_scalars, ctx->msm_arena, &d_planes, &stride, &d_err, st, ctx->prof);
+  if (rc) return rc;
+  size_t np = (size_t)g.S * g.c;
+  std::vector<host::HXYZZ<C>> planes(np);
+  static_assert(sizeof(host::HXYZZ<C>) == sizeof(XYZZ<C>), "host/device point layouts must agree");
+  uint32_t herr = 0;
+  if ((rc = rt::copy_d2h_2d(planes.data(), sizeof(XYZZ<C>), d_planes, stride * sizeof(XYZZ<C>), sizeof(XYZZ<C>), np, st))) return rc;
+  if ((rc = rt::copy_d2h(&herr, d_err, sizeof herr, st))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  ctx->prof.collect();
+  if (herr) return PCGPU_E_RANGE;
+  auto t0 = std::chrono::steady_clock::now();
+  *out = host::combine_bit_planes<C>(planes.data(), g.S, g.c);
+  if (ctx->prof.on) {
+    ctx->prof.ms[6] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->prof.cnt[6]++;
+  }
+  return PCGPU_OK;
 }
 
 // copies scalars (n x 32 bytes) to the staging arena unless they already live on the device
@@ -172,23 +167,13 @@ static int stage_words(pcgpu_ctx *ctx, const void *src, size_t bytes, uint32_t f
   return rc;
 }
 
-static int check_err_word(pcgpu_ctx *ctx, uint32_t *d_err) {
-  if (!d_err) return PCGPU_OK;
-  uint32_t h = 0;
-  int rc = rt::copy_d2h(&h, d_err, sizeof h, ctx->stream);
-  if (rc) return rc;
-  if ((rc = rt::stream_sync(ctx->stream))) return rc;
-  return h ? PCGPU_E_RANGE : PCGPU_OK;
-}
-
 // ---------------------------------------------------------------------------------------------
 // MSM entry points
 // ---------------------------------------------------------------------------------------------
 template <class C>
 int msm_impl(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n, uint32_t flags,
-                    void *out_xy, uint8_t *out_inf, void *out_xyzz) {
+             void *out_xy, uint8_t *out_inf, void *out_xyzz) {
   if (base_offset > srs->n || n > srs->n - base_offset) return PCGPU_E_LEN;
-  rt::stream_t st = ctx->stream;
   int rc;
   const uint32_t *d_scalars = nullptr;
   if (n) {
@@ -198,46 +183,25 @@ int msm_impl(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const voi
     uint32_t *buf = (flags & PCGPU_DEVICE_PTRS) ? nullptr : ctx->stage.take<uint32_t>(n * 8);
     if ((rc = stage_words(ctx, scalars, n * 32, flags, &d_scalars, buf))) return rc;
   }
-  uint32_t *d_err = nullptr;
-  if ((rc = msm_to_slot<C>(ctx, srs, base_offset, d_scalars, n, (flags & PCGPU_SCALARS_MONT) != 0, 0, &d_err))) return rc;
-  if (out_xyzz) {
-    XYZZ<C> h;
-    if ((rc = rt::copy_d2h(&h, slot_xyzz<C>(ctx, 0), sizeof h, st))) return rc;
-    if ((rc = check_err_word(ctx, d_err))) return rc;
-    if ((rc = rt::stream_sync(st))) return rc;
-    memcpy(out_xyzz, &h, sizeof h);
-    ctx->prof.collect();
-    return PCGPU_OK;
-  }
-  ctx->prof.begin(6, st);
-  if ((rc = rt::launch<32>(G1SumBody<C>{slot_xyzz<C>(ctx, 0), SLOT_BYTES, 1, slot_aff<C>(ctx)}, 1, st))) return rc;
-  ctx->prof.end(6, st);
-  Affine<C> h;
-  if ((rc = rt::copy_d2h(&h, slot_aff<C>(ctx), sizeof h, st))) return rc;
-  if ((rc = check_err_word(ctx, d_err))) return rc;
-  if ((rc = rt::stream_sync(st))) return rc;
-  write_affine_out<C>(h, out_xy, out_inf);
-  ctx->prof.collect();
+  host::HXYZZ<C> r;
+  if ((rc = msm_to_host<C>(ctx, srs, base_offset, d_scalars, n, (flags & PCGPU_SCALARS_MONT) != 0, &r))) return rc;
+  if (out_xyzz) { memcpy(out_xyzz, &r, sizeof r); return PCGPU_OK; }
+  host::to_affine<C>(r, out_xy, out_inf);
   return PCGPU_OK;
 }
 
-
-
+// point-sum of XYZZ partials: a handful of additions and one inversion -- host work (host_ec.hpp)
 template <class C>
-int g1_sum_impl(pcgpu_ctx *ctx, const void *xyzz, size_t count, void *out_xy, uint8_t *out_inf) {
-  rt::stream_t st = ctx->stream;
-  int rc;
-  if ((rc = ctx->stage.reserve(rt::Arena::pad(count * sizeof(XYZZ<C>)) + 4096))) return rc;
-  XYZZ<C> *d = ctx->stage.take<XYZZ<C>>(count ? count : 1);
-  if (count && (rc = rt::copy_h2d(d, xyzz, count * sizeof(XYZZ<C>), st))) return rc;
-  if ((rc = rt::launch<32>(G1SumBody<C>{d, sizeof(XYZZ<C>), count, slot_aff<C>(ctx)}, 1, st))) return rc;
-  Affine<C> h;
-  if ((rc = rt::copy_d2h(&h, slot_aff<C>(ctx), sizeof h, st))) return rc;
-  if ((rc = rt::stream_sync(st))) return rc;
-  write_affine_out<C>(h, out_xy, out_inf);
+int g1_sum_impl(pcgpu_ctx *, const void *xyzz, size_t count, void *out_xy, uint8_t *out_inf) {
+  host::HXYZZ<C> acc = host::HXYZZ<C>::inf();
+  for (size_t i = 0; i < count; i++) {
+    host::HXYZZ<C> p;
+    memcpy(&p, (const char *)xyzz + i * sizeof p, sizeof p);
+    acc = host::padd<C>(acc, p);
+  }
+  host::to_affine<C>(acc, out_xy, out_inf);
   return PCGPU_OK;
 }
-
 
 template <class C>
 int fixed_base_impl(pcgpu_ctx *ctx, const void *base_xy, const void *scalars, size_t n, uint32_t flags, void *out_xy) {
@@ -393,23 +357,6 @@ static size_t trim_trailing_zeros(const void *coeffs, size_t n) {
 }
 
 template <class C>
-int finish_sum(pcgpu_ctx *ctx, int nslots, uint32_t *e0, uint32_t *e1, void *out_xy, uint8_t *out_inf) {
-  rt::stream_t st = ctx->stream;
-  int rc;
-  ctx->prof.begin(6, st);
-  if ((rc = rt::launch<32>(G1SumBody<C>{slot_xyzz<C>(ctx, 0), SLOT_BYTES, (size_t)nslots, slot_aff<C>(ctx)}, 1, st))) return rc;
-  ctx->prof.end(6, st);
-  Affine<C> h;
-  if ((rc = rt::copy_d2h(&h, slot_aff<C>(ctx), sizeof h, st))) return rc;
-  if ((rc = check_err_word(ctx, e0))) return rc;
-  if ((rc = check_err_word(ctx, e1))) return rc;
-  if ((rc = rt::stream_sync(st))) return rc;
-  write_affine_out<C>(h, out_xy, out_inf);
-  ctx->prof.collect();
-  return PCGPU_OK;
-}
-
-template <class C>
 int kzg_commit_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, size_t n, const pcgpu_srs *gamma,
                            const void *blind, size_t n_blind, uint32_t flags, void *out_xy, uint8_t *out_inf) {
   bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
@@ -426,16 +373,14 @@ int kzg_commit_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, siz
     if (n_blind && (rc = rt::copy_h2d(tb, blind, n_blind * 32, st))) return rc;
     d_c = tc; d_b = tb;
   }
-  uint32_t *e0 = nullptr, *e1 = nullptr;
-  // the two MSMs share ctx->msm_arena; the error word of the first is read before the second starts
-  if ((rc = msm_to_slot<C>(ctx, pg, 0, d_c, n, true, 0, &e0))) return rc;
+  host::HXYZZ<C> comm, rnd;
+  if ((rc = msm_to_host<C>(ctx, pg, 0, d_c, n, true, &comm))) return rc;            // :175-178
   if (n_blind) {
-    if ((rc = check_err_word(ctx, e0))) return rc;
-    e0 = nullptr;
-    ctx->prof.collect();
-    if ((rc = msm_to_slot<C>(ctx, gamma, 0, d_b, n_blind, true, 1, &e1))) return rc;
+    if ((rc = msm_to_host<C>(ctx, gamma, 0, d_b, n_blind, true, &rnd))) return rc;  // :199-203
+    comm = host::padd<C>(comm, rnd);                                                  // :206
   }
-  return finish_sum<C>(ctx, n_blind ? 2 : 1, e0, e1, out_xy, out_inf);
+  host::to_affine<C>(comm, out_xy, out_inf);                                           // :209
+  return PCGPU_OK;
 }
 
 
@@ -468,19 +413,19 @@ int kzg_open_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, size_
   ctx->prof.begin(7, st);
   if ((rc = fr_div_linear<R>(d_c, n, d_z, d_q, d_rem, scratch, st))) return rc;
   ctx->prof.end(7, st);
-  uint32_t *e0 = nullptr, *e1 = nullptr;
-  if ((rc = msm_to_slot<C>(ctx, pg, 0, d_q, n ? n - 1 : 0, true, 0, &e0))) return rc;
+  host::HXYZZ<C> w, rw;
+  if ((rc = msm_to_host<C>(ctx, pg, 0, d_q, n ? n - 1 : 0, true, &w))) return rc;     // :255-258
   if (n_blind) {
-    if ((rc = check_err_word(ctx, e0))) return rc;
-    e0 = nullptr;
-    ctx->prof.collect();
     if ((rc = fr_div_linear<R>(d_b, n_blind, d_z, d_bq, d_rv, scratch, st))) return rc;  // rem = blind(z), :264
-    if ((rc = msm_to_slot<C>(ctx, gamma, 0, d_bq, n_blind - 1, true, 1, &e1))) return rc;
+    if ((rc = msm_to_host<C>(ctx, gamma, 0, d_bq, n_blind - 1, true, &rw))) return rc;  // :270-273
     if (out_random_v) {
       if ((rc = rt::copy_d2h(out_random_v, d_rv, 32, st))) return rc;
+      if ((rc = rt::stream_sync(st))) return rc;
     }
+    w = host::padd<C>(w, rw);
   }
-  return finish_sum<C>(ctx, n_blind ? 2 : 1, e0, e1, out_xy, out_inf);
+  host::to_affine<C>(w, out_xy, out_inf);                                              // :281
+  return PCGPU_OK;
 }
 
 

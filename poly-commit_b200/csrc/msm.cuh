@@ -249,31 +249,41 @@ struct MsmAccumulateBody {
 };
 
 // ---------------------------------------------------------------------------------------------
-// bucket reduction
+// bucket reduction: bucket sums, then bit-plane sums  T[s][j] = sum_{k : bit j of (k+1)} B[s][k]
+// (every stage is a plain sum, so the serial depth stays at chunk + log2(chunks) additions; the
+// c-term Horner combination  sum_j 2^j T[s][j]  and the final inversion run on the host, host_ec.hpp)
 // ---------------------------------------------------------------------------------------------
 template <class C>
-struct MsmSegmentBody {
-  MsmGeom g; const uint32_t *task_off; const XYZZ<C> *partial; XYZZ<C> *seg_out;
+struct MsmBucketSumBody {
+  const uint32_t *task_off; const XYZZ<C> *partial; XYZZ<C> *buckets;
+  PCGPU_KERNEL_DEV void operator()(size_t b) const {
+    uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (uint32_t q = t0; q < t1; q++) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add<C>(acc, p); }
+    store_xyzz<C>(buckets + b, acc);
+  }
+};
+
+template <class C>
+struct MsmBitPlaneBody {
+  MsmGeom g; const XYZZ<C> *buckets; XYZZ<C> *planes;  // planes[((s*c + j) * nseg) + q]
   PCGPU_KERNEL_DEV void operator()(size_t t) const {
-    uint32_t s = (uint32_t)(t / g.nseg), seg = (uint32_t)(t % g.nseg);
-    uint32_t lo = seg * g.seg_len;
+    uint32_t q = (uint32_t)(t % g.nseg);
+    uint32_t j = (uint32_t)((t / g.nseg) % g.c);
+    uint32_t s = (uint32_t)(t / ((size_t)g.nseg * g.c));
+    uint32_t lo = q * g.seg_len;
     uint32_t hi = lo + g.seg_len < g.NB ? lo + g.seg_len : g.NB;
-    XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
-    for (uint32_t k = hi; k-- > lo;) {
-      size_t b = (size_t)s * g.NB + k;
-      uint32_t t0 = task_off[b], t1 = task_off[b + 1];
-      for (uint32_t q = t0; q < t1; q++) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add<C>(run, p); }
-      xyzz_add<C>(acc, run);
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (uint32_t k = lo; k < hi; k++) {
+      if (((k + 1) >> j) & 1) { XYZZ<C> p = load_xyzz<C>(buckets + (size_t)s * g.NB + k); xyzz_add<C>(acc, p); }
     }
-    // sum_{k=lo}^{hi-1} (k+1) B_k = acc + lo * run
-    if (lo) { XYZZ<C> m = xyzz_mul_small<C>(run, lo); xyzz_add<C>(acc, m); }
-    store_xyzz<C>(seg_out + t, acc);
+    store_xyzz<C>(planes + t, acc);
   }
 };
 
 template <class C>
 struct MsmTreeAddBody {
-  XYZZ<C> *a; uint32_t stride; uint32_t m; uint32_t half;  // per set: a[i] += a[i+half] for i+half < m
+  XYZZ<C> *a; uint32_t stride; uint32_t m; uint32_t half;  // per row: a[i] += a[i+half] for i+half < m
   PCGPU_KERNEL_DEV void operator()(size_t t) const {
     uint32_t cnt = m - half;
     uint32_t s = (uint32_t)(t / cnt), i = (uint32_t)(t % cnt);
@@ -281,21 +291,6 @@ struct MsmTreeAddBody {
     XYZZ<C> x = load_xyzz<C>(base + i), y = load_xyzz<C>(base + i + half);
     xyzz_add<C>(x, y);
     store_xyzz<C>(base + i, x);
-  }
-};
-
-template <class C>
-struct MsmFinalBody {
-  MsmGeom g; const XYZZ<C> *sets; uint32_t stride; XYZZ<C> *out_xyzz; Affine<C> *out_aff;
-  PCGPU_KERNEL_DEV void operator()(size_t) const {
-    XYZZ<C> acc = load_xyzz<C>(sets + (size_t)(g.S - 1) * stride);
-    for (uint32_t s = g.S - 1; s-- > 0;) {
-      for (uint32_t k = 0; k < g.c; k++) acc = xyzz_dbl<C>(acc);
-      XYZZ<C> p = load_xyzz<C>(sets + (size_t)s * stride);
-      xyzz_add<C>(acc, p);
-    }
-    if (out_xyzz) store_xyzz<C>(out_xyzz, acc);
-    if (out_aff) *out_aff = xyzz_to_affine<C>(acc);
   }
 };
 
@@ -329,7 +324,7 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
   g.NB = 1u << (c - 1);
   g.TB = g.S * g.NB;
   g.L = 64;
-  g.seg_len = g.NB >= 4096 ? 32 : (g.NB >= 256 ? 16 : 8);
+  g.seg_len = 16;
   g.nseg = (g.NB + g.seg_len - 1) / g.seg_len;
   g.scalar_bits = scalar_bits; g.scalars_mont = mont ? 1 : 0;
   g.table_stride = table_stride; g.base_off = base_off;
@@ -347,18 +342,17 @@ inline size_t msm_workspace_bytes(const MsmGeom &g) {
   b += rt::Arena::pad(scan_scratch_words(g.TB + 1) * sizeof(uint32_t));
   b += rt::Arena::pad(64);
   b += rt::Arena::pad(max_tasks * sizeof(XYZZ<C>));
-  b += rt::Arena::pad((size_t)g.S * g.nseg * sizeof(XYZZ<C>));
+  b += rt::Arena::pad((size_t)g.TB * sizeof(XYZZ<C>));
+  b += rt::Arena::pad((size_t)g.S * g.c * g.nseg * sizeof(XYZZ<C>));
   return b + 4096;
 }
 
-struct StageTimer;  // api.cu
-
-// Runs the whole pipeline on `st`.  d_scalars: n x 8 uint32 on the device.  Results are written to
-// d_out_xyzz / d_out_aff (device, either may be null).  *d_err (device word) is OR-ed with 1 when a
-// scalar is out of range.  `prof` (optional) brackets stages with events.
+// Runs the device pipeline on `st`.  d_scalars: n x 8 uint32 on the device.  On return (asynchronously)
+// *d_planes points at the S*c bit-plane sums, element (s*c + j) at index (s*c + j) * plane_stride, and
+// *d_err at a device word that is non-zero when a scalar was out of range.  `prof` brackets stages with events.
 template <class C, class Prof>
 inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_scalars, rt::Arena &arena,
-                   XYZZ<C> *d_out_xyzz, Affine<C> *d_out_aff, uint32_t **d_err_out, rt::stream_t st, Prof &prof) {
+                   const XYZZ<C> **d_planes, size_t *plane_stride, uint32_t **d_err_out, rt::stream_t st, Prof &prof) {
   int rc;
   if ((rc = arena.reserve(msm_workspace_bytes<C>(g)))) return rc;
   size_t max_entries = (size_t)g.n * g.W;
@@ -373,10 +367,12 @@ inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_
   uint32_t *scratch = arena.take<uint32_t>(scan_scratch_words(g.TB + 1));
   uint32_t *err = arena.take<uint32_t>(16);
   XYZZ<C> *partial = arena.take<XYZZ<C>>(max_tasks);
-  XYZZ<C> *seg_out = arena.take<XYZZ<C>>((size_t)g.S * g.nseg);
-  if (!counts || !offsets || !cursor || !ntasks || !task_off || !task_bucket || !entries || !scratch || !err || !partial || !seg_out)
+  XYZZ<C> *buckets = arena.take<XYZZ<C>>(g.TB);
+  XYZZ<C> *planes = arena.take<XYZZ<C>>((size_t)g.S * g.c * g.nseg);
+  if (!counts || !offsets || !cursor || !ntasks || !task_off || !task_bucket || !entries || !scratch || !err || !partial ||
+      !buckets || !planes)
     return rt::E_OOM;
-  if (d_err_out) *d_err_out = err;
+  *d_err_out = err; *d_planes = planes; *plane_stride = g.nseg;
 
   prof.begin(0, st);
   if ((rc = rt::dev_memset(counts, 0, (g.TB + 2) * sizeof(uint32_t), st))) return rc;
@@ -404,17 +400,14 @@ inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_
   prof.end(4, st);
 
   prof.begin(5, st);
-  if ((rc = rt::launch<64>(MsmSegmentBody<C>{g, task_off, partial, seg_out}, (size_t)g.S * g.nseg, st))) return rc;
+  if ((rc = rt::launch<128>(MsmBucketSumBody<C>{task_off, partial, buckets}, g.TB, st))) return rc;
+  if ((rc = rt::launch<128>(MsmBitPlaneBody<C>{g, buckets, planes}, (size_t)g.S * g.c * g.nseg, st))) return rc;
   for (uint32_t m = g.nseg; m > 1;) {
     uint32_t half = (m + 1) / 2;
-    if ((rc = rt::launch<64>(MsmTreeAddBody<C>{seg_out, g.nseg, m, half}, (size_t)g.S * (m - half), st))) return rc;
+    if ((rc = rt::launch<128>(MsmTreeAddBody<C>{planes, g.nseg, m, half}, (size_t)g.S * g.c * (m - half), st))) return rc;
     m = half;
   }
   prof.end(5, st);
-
-  prof.begin(6, st);
-  if ((rc = rt::launch<32>(MsmFinalBody<C>{g, seg_out, g.nseg, d_out_xyzz, d_out_aff}, 1, st))) return rc;
-  prof.end(6, st);
   return rt::OK;
 }
 

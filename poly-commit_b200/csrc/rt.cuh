@@ -44,6 +44,10 @@ inline int dev_memset(void *p, int v, size_t bytes, stream_t) { memset(p, v, byt
 inline int copy_h2d(void *d, const void *h, size_t bytes, stream_t) { memcpy(d, h, bytes); return OK; }
 inline int copy_d2h(void *h, const void *d, size_t bytes, stream_t) { memcpy(h, d, bytes); return OK; }
 inline int copy_d2d(void *d, const void *s, size_t bytes, stream_t) { memmove(d, s, bytes); return OK; }
+inline int copy_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width, size_t rows, stream_t) {
+  for (size_t r = 0; r < rows; r++) memcpy((char *)h + r * hpitch, (const char *)d + r * dpitch, width);
+  return OK;
+}
 inline int stream_sync(stream_t) { return OK; }
 inline int last_error() { return OK; }
 
@@ -77,6 +81,9 @@ inline int dev_memset(void *p, int v, size_t bytes, stream_t s) { return map_cud
 inline int copy_h2d(void *d, const void *h, size_t bytes, stream_t s) { return map_cuda(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s)); }
 inline int copy_d2h(void *h, const void *d, size_t bytes, stream_t s) { return map_cuda(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s)); }
 inline int copy_d2d(void *d, const void *s_, size_t bytes, stream_t s) { return map_cuda(cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDeviceToDevice, s)); }
+inline int copy_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, size_t width, size_t rows, stream_t s) {
+  return map_cuda(cudaMemcpy2DAsync(h, hpitch, d, dpitch, width, rows, cudaMemcpyDeviceToHost, s));
+}
 inline int stream_sync(stream_t s) { return map_cuda(cudaStreamSynchronize(s)); }
 inline int last_error() { return map_cuda(cudaGetLastError()); }
 
