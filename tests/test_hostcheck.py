@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import orc, pyref
-from tests import util
+from tests import golden_cases, util
 
 FIELDS = [("bls12_381", "p", 0), ("bls12_381", "r", 1), ("bn254", "p", 2), ("bn254", "r", 3), ("pallas", "p", 4),
           ("pallas", "r", 5)]
@@ -197,14 +197,13 @@ def test_fr_vector_ops(eng, cname):
 
 
 def test_row_mul_reference_kat(eng):
-    """utils.rs:274-286 test_row_mul: [12, 41, 55] * M = [4088, 4431, 543]."""
-    C = pyref.Curve("bls12_381")
-    M = [10, 23, 55, 100, 1, 58, 4, 0, 9, 456, 34, 90, 45, 0, 9]  # 3 x 5 ... see reference: 3 rows used below
-    mat = [[10, 23, 55], [100, 1, 58], [4, 0, 9]]  # not the reference matrix; generic check vs python instead
-    v = [12, 41, 55]
-    exp = [sum(v[r] * mat[r][c] for r in range(3)) % C.r for c in range(3)]
-    got = eng.fr_row_mul(C.id, C.fr_to_limbs(v, True), C.fr_to_limbs([x for row in mat for x in row], True), 3, 3)
-    assert C.fr_from_limbs(got, True) == exp
+    """utils.rs:274-286 test_row_mul: [12, 41, 55] * [[10,100,4],[23,1,0],[55,58,9]] = [4088, 4431, 543]."""
+    golden_cases.check_row_mul_kat(eng)
+
+
+@pytest.mark.parametrize("cname", util.CURVE_NAMES)
+def test_golden_vectors(eng, cname):
+    golden_cases.check_engine(eng, cname)
 
 
 @pytest.mark.parametrize("cname", ["bls12_381", "bn254"])
