@@ -53,7 +53,8 @@ enum {
 enum {
   PCGPU_SCALARS_MONT = 1u,   /* scalars are Montgomery Fr; F::into_bigint is fused into the digit pass */
   PCGPU_DEVICE_PTRS = 2u,    /* bulk array arguments are device pointers (results stay host pointers) */
-  PCGPU_SRS_PRECOMPUTE = 4u  /* srs_register: also store 2^(c*k)-multiples of the bases (window folding) */
+  PCGPU_SRS_PRECOMPUTE = 4u, /* srs_register: also store 2^(c*k)-multiples of the bases (window folding) */
+  PCGPU_NTT_INVERSE = 8u     /* pcgpu_ntt: ifft instead of fft */
 };
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -112,6 +113,13 @@ int pcgpu_fr_inner_product(pcgpu_ctx *ctx, int curve, const void *a, const void 
 /* out = v * M, M rows x cols row-major -- Matrix::row_mul, utils.rs:127-146 */
 int pcgpu_fr_row_mul(pcgpu_ctx *ctx, int curve, const void *v, const void *m, size_t rows, size_t cols, void *out,
                      uint32_t flags);
+
+/* ---- NTT ---------------------------------------------------------------------------------------- */
+/* EvaluationDomain::fft(coeffs) on the radix-2 domain of size 2^logn -- linear_codes/utils.rs:119-126 (reed_solomon):
+ * the n_in <= 2^logn input elements are zero-padded, out[j] = p(w^j) in natural order with
+ * w = root_of_unity^(2^(two_adicity - logn)).  PCGPU_NTT_INVERSE computes ifft (coefficients from evaluations,
+ * includes the 1/N factor).  1 <= logn <= 22.  out: 2^logn elements. */
+int pcgpu_ntt(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in, uint32_t logn, uint32_t flags, void *out);
 
 /* ---- KZG10 fused prover calls ------------------------------------------------------------------ */
 /* KZG10::commit -- kzg10/mod.rs:157-210.  coeffs: n Montgomery Fr (low degree first; trailing zeros allowed and

@@ -7,7 +7,7 @@ import numpy as np
 
 BLS12_381, BN254, PALLAS = 0, 1, 2
 CURVES = {"bls12_381": BLS12_381, "bn254": BN254, "pallas": PALLAS}
-SCALARS_MONT, DEVICE_PTRS, SRS_PRECOMPUTE = 1, 2, 4
+SCALARS_MONT, DEVICE_PTRS, SRS_PRECOMPUTE, NTT_INVERSE = 1, 2, 4, 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -61,6 +61,7 @@ def _load(path):
         "pcgpu_fr_inner_product": [_vp, ctypes.c_int, _vp, _vp, _sz, _vp, ctypes.c_uint32],
         "pcgpu_fr_row_mul": [_vp, ctypes.c_int, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint32],
         "pcgpu_selftest_field": [_vp, ctypes.c_int, ctypes.c_uint64, _sz, ctypes.POINTER(ctypes.c_uint64)],
+        "pcgpu_ntt": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
     }
@@ -243,6 +244,16 @@ class Engine:
         v, m = _u64(v), _u64(m)
         out = np.zeros((cols, 4), dtype=np.uint64)
         self._ck(self.lib.pcgpu_fr_row_mul(self.ctx, curve, _ptr(v), _ptr(m), rows, cols, _ptr(out), flags))
+        return out
+
+    def ntt(self, curve, coeffs, logn, n_in=None, inverse=False, flags=0, out=None):
+        """EvaluationDomain::fft (zero-padded, natural order) / ifft."""
+        coeffs = _u64(coeffs)
+        if n_in is None:
+            n_in = coeffs.size // 4
+        if out is None:
+            out = np.zeros((1 << logn, 4), dtype=np.uint64)
+        self._ck(self.lib.pcgpu_ntt(self.ctx, curve, _ptr(coeffs), n_in, logn, flags | (NTT_INVERSE if inverse else 0), _ptr(out)))
         return out
 
     # ---- KZG10 ----

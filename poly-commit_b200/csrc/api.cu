@@ -53,6 +53,7 @@ extern "C" void pcgpu_destroy(pcgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
 #endif
   ctx->prof.destroy();
+  for (NttPlan &p : ctx->ntt_plans) rt::dev_free(p.base);
   ctx->msm_arena.release();
   ctx->stage.release();
   rt::dev_free(ctx->d_slots);
@@ -227,3 +228,10 @@ extern "C" int pcgpu_selftest_field(pcgpu_ctx *ctx, int curve, uint64_t seed, si
 }
 
 extern "C" uint64_t pcgpu_launch_count(void) { return rt::launch_counter().load(); }
+
+extern "C" int pcgpu_ntt(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in, uint32_t logn, uint32_t flags, void *out) {
+  if (!ctx || !out || (n_in && !in)) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(curve, return ntt_impl<C>(ctx, in, n_in, logn, flags, out));
+}

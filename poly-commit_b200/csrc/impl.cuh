@@ -12,6 +12,7 @@
 #include "../../include/pcgpu.h"
 #include "frops.cuh"
 #include "host_ec.hpp"
+#include "ntt.cuh"
 #include <chrono>
 #include "msm.cuh"
 #include "srs.cuh"
@@ -67,6 +68,7 @@ struct pcgpu_ctx {
   rt::Arena msm_arena, stage;
   void *d_slots;    // 8 XYZZ result slots + 1 affine + err word, generously sized
   Prof prof;
+  std::vector<NttPlan> ntt_plans;  // twiddle tables, cached per (curve, logn, direction)
   std::mutex mu;
 };
 
@@ -431,6 +433,43 @@ int kzg_open_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, size_
 
 
 // ---------------------------------------------------------------------------------------------
+// NTT
+// ---------------------------------------------------------------------------------------------
+template <class C>
+int ntt_impl(pcgpu_ctx *ctx, const void *in, size_t n_in, uint32_t logn, uint32_t flags, void *out) {
+  using R = typename C::Fr;
+  if (!ntt_supported(logn) || logn > (uint32_t)R::TWO_ADICITY) return PCGPU_E_BADARG;
+  const size_t N = (size_t)1 << logn;
+  if (n_in > N) return PCGPU_E_LEN;
+  rt::stream_t st = ctx->stream;
+  int rc, inverse = (flags & PCGPU_NTT_INVERSE) ? 1 : 0;
+  const NttPlan *plan = nullptr;
+  for (const NttPlan &p : ctx->ntt_plans) if (p.curve == C::ID && p.logn == logn && p.inverse == inverse) plan = &p;
+  if (!plan) {
+    NttPlan p;
+    if ((rc = ntt_build_plan<R>(p, C::ID, logn, inverse, st))) return rc;
+    ctx->ntt_plans.push_back(p);
+    plan = &ctx->ntt_plans.back();
+  }
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  if ((rc = ctx->stage.reserve((dev ? 1 : 3) * rt::Arena::pad(N * 32) + 4096))) return rc;
+  uint32_t *tmp = ctx->stage.take<uint32_t>(N * 8);
+  const uint32_t *d_in = (const uint32_t *)in; uint32_t *d_out = (uint32_t *)out;
+  if (!dev) {
+    uint32_t *ti = ctx->stage.take<uint32_t>(N * 8); d_out = ctx->stage.take<uint32_t>(N * 8);
+    if (n_in && (rc = rt::copy_h2d(ti, in, n_in * 32, st))) return rc;
+    d_in = ti;
+  }
+  ctx->prof.begin(9, st);
+  if ((rc = ntt_run<R>(*plan, d_in, n_in, d_out, tmp, st))) return rc;
+  ctx->prof.end(9, st);
+  if (!dev && (rc = rt::copy_d2h(out, d_out, N * 32, st))) return rc;
+  rc = rt::stream_sync(st);
+  ctx->prof.collect();
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // device self-test of the field layer
 // ---------------------------------------------------------------------------------------------
 template <class P>
@@ -495,4 +534,5 @@ int selftest_field_impl(pcgpu_ctx *ctx, uint64_t seed, size_t n, uint64_t *misma
                                       size_t, uint32_t, void *, uint8_t *);                                                \
   EXT template int kzg_open_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const void *, const pcgpu_srs *, \
                                     const void *, size_t, uint32_t, void *, uint8_t *, void *); \
-  EXT template int selftest_field_impl<C>(pcgpu_ctx *, uint64_t, size_t, uint64_t *);
+  EXT template int selftest_field_impl<C>(pcgpu_ctx *, uint64_t, size_t, uint64_t *); \
+  EXT template int ntt_impl<C>(pcgpu_ctx *, const void *, size_t, uint32_t, uint32_t, void *);

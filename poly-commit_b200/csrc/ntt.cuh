@@ -1,0 +1,160 @@
+// Radix-2 number-theoretic transform over Fr, four-step decomposition.
+//
+// Replaces Radix2EvaluationDomain::{fft, ifft} (ark-poly 0.5.0, un-vendored) at its only call site in the
+// reference, linear_codes/utils.rs:112-127 (reed_solomon): the n_in input coefficients are zero-padded to
+// N = 2^logn and out[j] = p(w^j) in natural order, w = root_of_unity^(2^(TWO_ADICITY - logn))
+// (test_reed_solomon, linear_codes/utils.rs:303-331, pins exactly this).  ifft is the inverse map.
+//
+// N = N1 * N2.  Pass 1: N2 column transforms of length N1 (stride N2) with the step-2 twiddle
+// w_N^(k1 n2) fused into the store; pass 2: N1 row transforms of length N2 writing X[k1 + N1 k2].
+// Each length-M transform is one thread block: bit-reversed load into shared memory (limb-major so
+// unit-stride butterflies are bank-conflict free), log2(M) butterfly stages with __syncthreads, store.
+// Compute: (N/2) log2(N) + 2N Montgomery products; traffic: 2 reads + 2 writes of the vector
+// (algorithmic: 1 read + 1 write = 64 B/element).
+#pragma once
+#include "frops.cuh"
+#include "rt.cuh"
+
+namespace pcgpu {
+
+enum { NTT_MAX_LOG_BLOCK = 11, NTT_LO_BITS = 10 };
+
+template <class R>
+PCGPU_DEV Fp<R> fp_pow_u64(Fp<R> base, uint64_t e) {
+  Fp<R> acc = Fp<R>::one();
+  while (e) { if (e & 1) acc = fp_mul<R>(acc, base); base = fp_sqr<R>(base); e >>= 1; }
+  return acc;
+}
+
+struct NttPlan {
+  int curve; uint32_t logn; int inverse;
+  uint32_t m1, m2;          // N1 = 2^m1 (pass 1 length), N2 = 2^m2
+  uint32_t *tw1, *tw2;      // w_{N1}^j (j < N1/2), w_{N2}^j (j < N2/2)
+  uint32_t *lo, *hi;        // w_N^e = hi[e >> 10] * lo[e & 1023]
+  uint32_t *scale;          // N^-1 (inverse) else null
+  uint32_t *base;           // allocation
+};
+
+// roots[0] = w_N (or its inverse), roots[1] = 2^-logn
+template <class R>
+struct NttRootsBody {
+  uint32_t logn; int inverse; uint32_t *roots;
+  PCGPU_KERNEL_DEV void operator()(size_t) const {
+    Fp<R> w;
+#pragma unroll
+    for (int i = 0; i < R::N; i++) w.l[i] = R::root_of_unity(i);
+    for (uint32_t i = logn; i < (uint32_t)R::TWO_ADICITY; i++) w = fp_sqr<R>(w);
+    if (inverse) w = fp_inv<R>(w);
+    store_fr<R>(roots, 0, w);
+    Fp<R> two = fp_dbl<R>(Fp<R>::one());
+    Fp<R> half = fp_inv<R>(two), s = Fp<R>::one();
+    for (uint32_t i = 0; i < logn; i++) s = fp_mul<R>(s, half);
+    store_fr<R>(roots, 1, s);
+  }
+};
+
+// table[k] = (w^mult)^k for k < count
+template <class R>
+struct NttTableBody {
+  const uint32_t *roots; uint64_t mult; uint32_t *table;
+  PCGPU_KERNEL_DEV void operator()(size_t k) const {
+    Fp<R> w = load_fr<R>(roots, 0);
+    store_fr<R>(table, k, fp_pow_u64<R>(w, mult * (uint64_t)k));
+  }
+};
+
+PCGPU_DEV uint32_t bitrev32(uint32_t v, uint32_t bits) {
+  uint32_t r = 0;
+  for (uint32_t i = 0; i < bits; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+  return r;
+}
+
+template <class R>
+struct NttBlockBody {
+  const uint32_t *in; uint32_t *out;
+  uint32_t m;                               // transform length M = 2^m
+  uint64_t in_stride, in_batch_stride, out_stride, out_batch_stride;
+  uint64_t n_valid;                         // input elements with linear index >= n_valid read as zero
+  const uint32_t *tw;                       // w_M^j, j < M/2
+  const uint32_t *lo, *hi; int step2;       // step-2 twiddle w_N^(i * batch)
+  const uint32_t *scale;                    // optional final factor
+  PCGPU_KERNEL_DEV void operator()(size_t batch, uint32_t *smem) const {
+    const uint32_t M = 1u << m;
+    PCGPU_BLOCK_FOR(i, M) {
+      uint64_t idx = batch * in_batch_stride + (uint64_t)i * in_stride;
+      Fp<R> v = idx < n_valid ? load_fr<R>(in, idx) : Fp<R>::zero();
+      uint32_t r = bitrev32(i, m);
+#pragma unroll
+      for (int l = 0; l < 8; l++) smem[l * M + r] = v.l[l];
+    }
+    PCGPU_BLOCK_SYNC();
+    for (uint32_t s = 0; s < m; s++) {
+      const uint32_t half = 1u << s;
+      PCGPU_BLOCK_FOR(b, M / 2) {
+        uint32_t pos = b & (half - 1);
+        uint32_t i0 = ((b >> s) << (s + 1)) + pos, i1 = i0 + half;
+        Fp<R> a, t;
+#pragma unroll
+        for (int l = 0; l < 8; l++) { a.l[l] = smem[l * M + i0]; t.l[l] = smem[l * M + i1]; }
+        if (s) t = fp_mul<R>(t, load_fr<R>(tw, (size_t)pos << (m - 1 - s)));  // w_M^(pos * M / (2 half)); pos = 0 at s = 0
+        Fp<R> x = fp_add<R>(a, t), y = fp_sub<R>(a, t);
+#pragma unroll
+        for (int l = 0; l < 8; l++) { smem[l * M + i0] = x.l[l]; smem[l * M + i1] = y.l[l]; }
+      }
+      PCGPU_BLOCK_SYNC();
+    }
+    PCGPU_BLOCK_FOR(i, M) {
+      Fp<R> v;
+#pragma unroll
+      for (int l = 0; l < 8; l++) v.l[l] = smem[l * M + i];
+      if (step2) {
+        uint64_t e = (uint64_t)i * batch;
+        if (e) v = fp_mul<R>(v, fp_mul<R>(load_fr<R>(hi, e >> NTT_LO_BITS), load_fr<R>(lo, e & ((1u << NTT_LO_BITS) - 1))));
+      }
+      if (scale) v = fp_mul<R>(v, load_fr<R>(scale, 0));
+      store_fr<R>(out, batch * out_batch_stride + (uint64_t)i * out_stride, v);
+    }
+  }
+};
+
+inline void ntt_split(uint32_t logn, uint32_t *m1, uint32_t *m2) {
+  if (logn <= NTT_MAX_LOG_BLOCK) { *m1 = logn; *m2 = 0; }
+  else { *m1 = (logn + 1) / 2; *m2 = logn - *m1; }
+}
+inline bool ntt_supported(uint32_t logn) { return logn >= 1 && logn <= 2 * NTT_MAX_LOG_BLOCK; }
+
+template <class R>
+inline int ntt_build_plan(NttPlan &p, int curve, uint32_t logn, int inverse, rt::stream_t st) {
+  p.curve = curve; p.logn = logn; p.inverse = inverse;
+  ntt_split(logn, &p.m1, &p.m2);
+  size_t n1h = (size_t)1 << (p.m1 ? p.m1 - 1 : 0), n2h = p.m2 ? (size_t)1 << (p.m2 - 1) : 1;
+  size_t nlo = (size_t)1 << NTT_LO_BITS, nhi = logn > NTT_LO_BITS ? (size_t)1 << (logn - NTT_LO_BITS) : 1;
+  size_t words = 8 * (4 + n1h + n2h + nlo + nhi);
+  int rc = rt::dev_malloc((void **)&p.base, words * 4);
+  if (rc) return rc;
+  uint32_t *roots = p.base;
+  p.scale = inverse ? roots + 8 : nullptr;
+  p.tw1 = roots + 32; p.tw2 = p.tw1 + 8 * n1h; p.lo = p.tw2 + 8 * n2h; p.hi = p.lo + 8 * nlo;
+  if ((rc = rt::launch<32>(NttRootsBody<R>{logn, inverse, roots}, 1, st))) return rc;
+  if ((rc = rt::launch<128>(NttTableBody<R>{roots, (uint64_t)1 << (logn - p.m1), p.tw1}, n1h, st))) return rc;
+  if ((rc = rt::launch<128>(NttTableBody<R>{roots, (uint64_t)1 << (logn - p.m2), p.tw2}, n2h, st))) return rc;
+  if ((rc = rt::launch<128>(NttTableBody<R>{roots, 1, p.lo}, nlo, st))) return rc;
+  return rt::launch<128>(NttTableBody<R>{roots, (uint64_t)1 << NTT_LO_BITS, p.hi}, nhi, st);
+}
+
+// in: n_in elements (device), out: N elements (device), tmp: N elements (device; unused when m2 == 0)
+template <class R>
+inline int ntt_run(const NttPlan &p, const uint32_t *in, size_t n_in, uint32_t *out, uint32_t *tmp, rt::stream_t st) {
+  const uint64_t N1 = (uint64_t)1 << p.m1, N2 = (uint64_t)1 << p.m2;
+  if (p.m2 == 0) {
+    NttBlockBody<R> b{in, out, p.m1, 1, 0, 1, 0, n_in, p.tw1, p.lo, p.hi, 0, p.scale};
+    return rt::launch_blocks<256>(b, 1, (size_t)N1 * 32, st);
+  }
+  NttBlockBody<R> b1{in, tmp, p.m1, N2, 1, N2, 1, n_in, p.tw1, p.lo, p.hi, 1, nullptr};
+  int rc = rt::launch_blocks<256>(b1, N2, (size_t)N1 * 32, st);
+  if (rc) return rc;
+  NttBlockBody<R> b2{tmp, out, p.m2, 1, N2, N1, 1, N1 * N2, p.tw2, p.lo, p.hi, 0, p.scale};
+  return rt::launch_blocks<256>(b2, N1, (size_t)N2 * 32, st);
+}
+
+}  // namespace pcgpu

@@ -59,6 +59,18 @@ inline int launch(const Body &body, size_t n, stream_t) {
 template <class T> inline T atomic_add(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomic_or(T *p, T v) { T o = *p; *p = o | v; return o; }
 #define PCGPU_KERNEL_DEV inline
+// Block-cooperative bodies: body(block_id, shared_memory).  Work inside the body is written as
+// PCGPU_BLOCK_FOR loops separated by PCGPU_BLOCK_SYNC(); anything that must survive a sync lives in shared memory.
+#define PCGPU_BLOCK_FOR(i, n) for (uint32_t i = 0; i < (uint32_t)(n); i++)
+#define PCGPU_BLOCK_SYNC() do { } while (0)
+template <int BLOCK, class Body>
+inline int launch_blocks(const Body &body, size_t nblocks, size_t smem_bytes, stream_t) {
+  uint32_t *smem = (uint32_t *)::malloc(smem_bytes ? smem_bytes : 16);
+  if (!smem) return E_OOM;
+  for (size_t b = 0; b < nblocks; b++) body(b, smem);
+  ::free(smem);
+  return OK;
+}
 
 #else
 // ------------------------------------------------------------------ CUDA (the product)
@@ -98,6 +110,24 @@ inline int launch(const Body &body, size_t n, stream_t s) {
   if (n == 0) return OK;
   size_t grid = (n + BLOCK - 1) / BLOCK;
   run_kernel<Body, BLOCK><<<(unsigned)grid, BLOCK, 0, s>>>(body, n);
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  return last_error();
+}
+#define PCGPU_BLOCK_FOR(i, n) for (uint32_t i = threadIdx.x; i < (uint32_t)(n); i += blockDim.x)
+#define PCGPU_BLOCK_SYNC() __syncthreads()
+template <class Body, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) run_block_kernel(const Body body) {
+  extern __shared__ uint4 pcgpu_smem[];
+  body((size_t)blockIdx.x, reinterpret_cast<uint32_t *>(pcgpu_smem));
+}
+template <int BLOCK, class Body>
+inline int launch_blocks(const Body &body, size_t nblocks, size_t smem_bytes, stream_t s) {
+  if (nblocks == 0) return OK;
+  if (smem_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(run_block_kernel<Body, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return map_cuda(e);
+  }
+  run_block_kernel<Body, BLOCK><<<(unsigned)nblocks, BLOCK, smem_bytes, s>>>(body);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   return last_error();
 }

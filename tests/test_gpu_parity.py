@@ -15,7 +15,7 @@ from tests import util
 from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_fr_vector_ops,  # noqa: F401
                                   test_kzg_commit_open, test_msm_edge_scalars, test_msm_infinity_bases,
                                   test_msm_partial_and_sum, test_msm_precomputed_tables, test_msm_vs_oracle,
-                                  test_row_mul_reference_kat, test_golden_vectors)
+                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle)
 
 pytestmark = pytest.mark.gpu
 
@@ -144,3 +144,15 @@ def test_device_pointer_path(eng, pc, big):
     got = eng.kzg_commit(big["srs"], d.data_ptr(), n=n, flags=pc.DEVICE_PTRS)
     exp = eng.kzg_commit(big["srs"], p)
     assert (got[0] == exp[0]).all()
+
+
+@pytest.mark.parametrize("cname,logn", [("bls12_381", 20), ("bn254", 18), ("pallas", 21)])
+def test_ntt_large(eng, cname, logn):
+    """north_star size (2^20, BLS12-381 Fr): bit-exact vs the oracle's recursive NTT, and ifft(fft(x)) == x."""
+    C = pyref.Curve(cname)
+    n_in = (1 << logn) - 12345
+    x = util.rand_fr_fast(cname, n_in, seed=400 + logn)
+    got = eng.ntt(C.id, x, logn)
+    assert (got == orc.fr_ntt(C.id, x, logn)).all()
+    back = eng.ntt(C.id, got, logn, inverse=True)
+    assert (back[:n_in] == x).all() and not back[n_in:].any()

@@ -206,6 +206,18 @@ def test_golden_vectors(eng, cname):
     golden_cases.check_engine(eng, cname)
 
 
+@pytest.mark.parametrize("cname", util.CURVE_NAMES)
+@pytest.mark.parametrize("logn,n_in", [(1, 2), (3, 5), (6, 64), (10, 700), (11, 2048), (12, 3000), (13, 8192)])
+def test_ntt_vs_oracle(eng, cname, logn, n_in):
+    """fft semantics of linear_codes/utils.rs:119-126 (zero-padded, natural order) and ifft(fft(x)) == x."""
+    C = pyref.Curve(cname)
+    x = util.rand_fr(cname, n_in, seed=300 + logn, mont=True)
+    got = eng.ntt(C.id, x, logn)
+    assert (got == orc.fr_ntt(C.id, x, logn)).all()
+    back = eng.ntt(C.id, got, logn, inverse=True)
+    assert (back[:n_in] == x).all() and not back[n_in:].any()
+
+
 @pytest.mark.parametrize("cname", ["bls12_381", "bn254"])
 def test_kzg_commit_open(eng, pc, cname):
     """KZG10::commit / open dataflow (kzg10/mod.rs:157-310), non-hiding and hiding, vs the C oracle."""
