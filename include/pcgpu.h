@@ -54,7 +54,8 @@ enum {
   PCGPU_SCALARS_MONT = 1u,   /* scalars are Montgomery Fr; F::into_bigint is fused into the digit pass */
   PCGPU_DEVICE_PTRS = 2u,    /* bulk array arguments are device pointers (results stay host pointers) */
   PCGPU_SRS_PRECOMPUTE = 4u, /* srs_register: also store 2^(c*k)-multiples of the bases (window folding) */
-  PCGPU_NTT_INVERSE = 8u     /* pcgpu_ntt: ifft instead of fft */
+  PCGPU_NTT_INVERSE = 8u,    /* pcgpu_ntt: ifft instead of fft */
+  PCGPU_SRS_COMB = 16u       /* srs_register: build fixed-base comb tables for pcgpu_msm_batch (shared-base batches) */
 };
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -93,6 +94,14 @@ int pcgpu_msm_partial(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, 
  * partials as bytes and each adds them locally (NCCL has no reduction operator for curve points). */
 int pcgpu_g1_sum_xyzz(pcgpu_ctx *ctx, int curve, const void *xyzz, size_t count, void *out_xy, uint8_t *out_inf);
 
+/* `count` MSMs of length n over the SAME bases (the first n of `srs`): out[r] = sum_i scalars[r*n + i] * bases[i].
+ * HyraxPC::commit row loop, hyrax/mod.rs:233-242 (dim Pedersen commitments over one com_key; append h as base n and the
+ * row randomness as scalar n to get `pedersen_commit(row) + h * r` in the same pass).  With PCGPU_SRS_COMB tables the
+ * batch is a fixed-base comb (no buckets); otherwise the rows run through pcgpu_msm one by one.
+ * out_xy: count affine points; out_inf: count bytes. */
+int pcgpu_msm_batch(pcgpu_ctx *ctx, const pcgpu_srs *srs, const void *scalars, size_t n, size_t count, uint32_t flags,
+                    void *out_xy, uint8_t *out_inf);
+
 /* g.batch_mul(scalars): out[i] = scalars[i] * base -- KZG10::setup, kzg10/mod.rs:76, :82-86 (used to build synthetic
  * SRSs on the device).  base_xy: one affine point (host).  scalars: n canonical.  out_xy: n affine points, x||y only
  * (an identity result is written as x = y = 0).  With PCGPU_DEVICE_PTRS scalars and out_xy are device pointers. */
@@ -120,6 +129,24 @@ int pcgpu_fr_row_mul(pcgpu_ctx *ctx, int curve, const void *v, const void *m, si
  * w = root_of_unity^(2^(two_adicity - logn)).  PCGPU_NTT_INVERSE computes ifft (coefficients from evaluations,
  * includes the 1/N factor).  1 <= logn <= 22.  out: 2^logn elements. */
 int pcgpu_ntt(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in, uint32_t logn, uint32_t flags, void *out);
+
+/* ---- InnerProductArgPC::open halving loop, device-resident (ipa_pc/mod.rs:636-711) ------------------------- */
+typedef struct pcgpu_ipa pcgpu_ipa;
+/* Upload the committer key (n = d+1 affine points, n a power of two) and the combined polynomial's coefficients
+ * (n_coeffs <= n Montgomery Fr, zero-padded :636-641); build z = [1, point, point^2, ...] on the device (:643-648). */
+int pcgpu_ipa_begin(pcgpu_ctx *ctx, int curve, const void *comm_key_xy, size_t n, const void *coeffs, size_t n_coeffs,
+                    const void *point, uint32_t flags, pcgpu_ipa **out);
+/* One round, first half (:671-677): l = cm_commit(key_l, coeffs_r) + h' * <coeffs_r, z_l>,
+ * r = cm_commit(key_r, coeffs_l) + h' * <coeffs_l, z_r>, normalised.  h_prime_xy: affine h' (host). */
+int pcgpu_ipa_round_lr(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_prime_xy, void *out_l_xy, uint8_t *out_l_inf,
+                       void *out_r_xy, uint8_t *out_r_inf);
+/* One round, second half (:691-708): fold coeffs, z and the key with the round challenge (Montgomery Fr, and its
+ * inverse), then halve n. */
+int pcgpu_ipa_round_fold(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *challenge, const void *challenge_inv);
+/* Current size (1 when the loop is over). */
+size_t pcgpu_ipa_len(const pcgpu_ipa *st);
+/* final_comm_key = comm_key[0], c = coeffs[0] (:713-720); releases the state. */
+int pcgpu_ipa_finish(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_key_xy, void *out_c);
 
 /* ---- KZG10 fused prover calls ------------------------------------------------------------------ */
 /* KZG10::commit -- kzg10/mod.rs:157-210.  coeffs: n Montgomery Fr (low degree first; trailing zeros allowed and

@@ -88,6 +88,14 @@ def g1_sum(curve, xy, inf=None):
     return out, int(oinf[0])
 
 
+def g1_fold(curve, key_xy, chal_canonical):
+    key_xy, chal = _u64(key_xy), _u64(chal_canonical)
+    m = key_xy.size // (2 * FQ_LIMBS[curve]) // 2
+    out = np.zeros((m, 2 * FQ_LIMBS[curve]), dtype=np.uint64)
+    assert lib().orc_g1_fold(curve, _p(key_xy), ctypes.c_size_t(m), _p(chal), _p(out)) == 0
+    return out
+
+
 def msm(curve, bases, scalars, inf=None, n=None, naive=False, nthreads=0):
     """bases (m, 2*nq) Montgomery, scalars (n, 4) CANONICAL.  Returns (xy, inf_flag)."""
     bases, scalars = _u64(bases), _u64(scalars)

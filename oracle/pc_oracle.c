@@ -193,6 +193,17 @@ int orc_g1_sum(int curve, const uint64_t *xy, const uint8_t *inf, size_t n, uint
   return 0;
 }
 
+/* key_l[i] += chal * key_r[i]; normalize_batch  (ipa_pc/mod.rs:699-707).  key: 2m affine points, chal canonical;
+ * out: m affine points. */
+int orc_g1_fold(int curve, const uint64_t *key_xy, size_t m, const uint64_t *chal, uint64_t *out_xy) {
+#define BODY(P) { for (size_t i = 0; i < m; i++) { P##_aff l, r, o; P##_aff_load(&l, key_xy, NULL, i); P##_aff_load(&r, key_xy, NULL, m + i); \
+      if (P##_fq_is_zero(&l.x) && P##_fq_is_zero(&l.y)) l.inf = 1; if (P##_fq_is_zero(&r.x) && P##_fq_is_zero(&r.y)) r.inf = 1; \
+      P##_jac j; P##_jac_mul(&j, &r, chal, 4); P##_jac_add_aff(&j, &j, &l, 0); P##_jac_to_aff(&o, &j); P##_aff_store(&o, out_xy, NULL, i); } }
+  DISPATCH(curve, BODY(bls), BODY(bn), BODY(pal))
+#undef BODY
+  return 0;
+}
+
 /* VariableBaseMSM::msm_bigint restated at definition level (sum of double-and-add products) */
 int orc_msm_naive(int curve, const uint64_t *bases, const uint8_t *inf, const uint64_t *scalars, size_t n,
                   uint64_t *out_xy, uint8_t *out_inf) {

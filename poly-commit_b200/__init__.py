@@ -8,7 +8,7 @@ There is no CPU fallback: importing works anywhere, but creating an ``Engine`` r
 library is present AND an sm_100 device is usable.
 """
 from .binding import (Engine, Srs, PcgpuError, CURVES, BLS12_381, BN254, PALLAS, SCALARS_MONT, DEVICE_PTRS,
-                      SRS_PRECOMPUTE, NTT_INVERSE, library_path, fq_limbs)
+                      SRS_PRECOMPUTE, NTT_INVERSE, SRS_COMB, library_path, fq_limbs)
 
 __all__ = ["Engine", "Srs", "PcgpuError", "CURVES", "BLS12_381", "BN254", "PALLAS", "SCALARS_MONT", "DEVICE_PTRS",
-           "SRS_PRECOMPUTE", "NTT_INVERSE", "library_path", "fq_limbs"]
+           "SRS_PRECOMPUTE", "NTT_INVERSE", "SRS_COMB", "library_path", "fq_limbs"]

@@ -7,7 +7,7 @@ import numpy as np
 
 BLS12_381, BN254, PALLAS = 0, 1, 2
 CURVES = {"bls12_381": BLS12_381, "bn254": BN254, "pallas": PALLAS}
-SCALARS_MONT, DEVICE_PTRS, SRS_PRECOMPUTE, NTT_INVERSE = 1, 2, 4, 8
+SCALARS_MONT, DEVICE_PTRS, SRS_PRECOMPUTE, NTT_INVERSE, SRS_COMB = 1, 2, 4, 8, 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -41,6 +41,8 @@ def _load(path):
     lib.pcgpu_srs_len.restype = _sz
     lib.pcgpu_srs_len.argtypes = [_vp]
     lib.pcgpu_srs_curve.argtypes = [_vp]
+    lib.pcgpu_ipa_len.restype = _sz
+    lib.pcgpu_ipa_len.argtypes = [_vp]
     lib.pcgpu_launch_count.restype = ctypes.c_uint64
     lib.pcgpu_launch_count.argtypes = []
     sigs = {
@@ -52,6 +54,7 @@ def _load(path):
         "pcgpu_srs_register": [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_uint32, ctypes.POINTER(_vp)],
         "pcgpu_srs_release": [_vp, _vp],
         "pcgpu_msm": [_vp, _vp, _sz, _vp, _sz, ctypes.c_uint32, _vp, _vp],
+        "pcgpu_msm_batch": [_vp, _vp, _vp, _sz, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_msm_partial": [_vp, _vp, _sz, _vp, _sz, ctypes.c_uint32, _vp],
         "pcgpu_g1_sum_xyzz": [_vp, ctypes.c_int, _vp, _sz, _vp, _vp],
         "pcgpu_g1_fixed_base_mul": [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_uint32, _vp],
@@ -61,6 +64,10 @@ def _load(path):
         "pcgpu_fr_inner_product": [_vp, ctypes.c_int, _vp, _vp, _sz, _vp, ctypes.c_uint32],
         "pcgpu_fr_row_mul": [_vp, ctypes.c_int, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint32],
         "pcgpu_selftest_field": [_vp, ctypes.c_int, ctypes.c_uint64, _sz, ctypes.POINTER(ctypes.c_uint64)],
+        "pcgpu_ipa_begin": [_vp, ctypes.c_int, _vp, _sz, _vp, _sz, _vp, ctypes.c_uint32, ctypes.POINTER(_vp)],
+        "pcgpu_ipa_round_lr": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
+        "pcgpu_ipa_round_fold": [_vp, _vp, _vp, _vp],
+        "pcgpu_ipa_finish": [_vp, _vp, _vp, _vp],
         "pcgpu_ntt": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
@@ -177,6 +184,14 @@ class Engine:
         self._ck(self.lib.pcgpu_msm(self.ctx, srs.handle, base_offset, _ptr(scalars), n, flags, _ptr(out), _ptr(inf)))
         return out, int(inf[0])
 
+    def msm_batch(self, srs, scalars, n, count, flags=0):
+        """count MSMs of length n over the same bases -> ((count, 2*limbs) uint64, (count,) uint8 identity flags)."""
+        scalars = _u64(scalars)
+        out = np.zeros((count, 2 * fq_limbs(srs.curve)), dtype=np.uint64)
+        inf = np.zeros(count, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_msm_batch(self.ctx, srs.handle, _ptr(scalars), n, count, flags, _ptr(out), _ptr(inf)))
+        return out, inf
+
     def msm_partial(self, srs, scalars, n=None, base_offset=0, flags=0):
         scalars = _u64(scalars)
         if n is None:
@@ -255,6 +270,35 @@ class Engine:
             out = np.zeros((1 << logn, 4), dtype=np.uint64)
         self._ck(self.lib.pcgpu_ntt(self.ctx, curve, _ptr(coeffs), n_in, logn, flags | (NTT_INVERSE if inverse else 0), _ptr(out)))
         return out
+
+    # ---- IPA halving loop (device-resident state) ----
+    def ipa_begin(self, curve, comm_key_xy, coeffs, point, n=None, flags=0):
+        comm_key_xy, coeffs, point = _u64(comm_key_xy), _u64(coeffs), _u64(point)
+        if n is None:
+            n = comm_key_xy.size // (2 * fq_limbs(curve))
+        h = _vp()
+        self._ck(self.lib.pcgpu_ipa_begin(self.ctx, curve, _ptr(comm_key_xy), n, _ptr(coeffs), coeffs.size // 4, _ptr(point), flags,
+                                          ctypes.byref(h)))
+        return h
+
+    def ipa_round_lr(self, curve, state, h_prime_xy):
+        h_prime_xy = _u64(h_prime_xy)
+        nq = fq_limbs(curve)
+        l, r = np.zeros(2 * nq, dtype=np.uint64), np.zeros(2 * nq, dtype=np.uint64)
+        li, ri = np.zeros(1, dtype=np.uint8), np.zeros(1, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_ipa_round_lr(self.ctx, state, _ptr(h_prime_xy), _ptr(l), _ptr(li), _ptr(r), _ptr(ri)))
+        return l, r
+
+    def ipa_round_fold(self, state, challenge, challenge_inv):
+        self._ck(self.lib.pcgpu_ipa_round_fold(self.ctx, state, _ptr(_u64(challenge)), _ptr(_u64(challenge_inv))))
+
+    def ipa_len(self, state):
+        return int(self.lib.pcgpu_ipa_len(state))
+
+    def ipa_finish(self, curve, state):
+        key, c = np.zeros(2 * fq_limbs(curve), dtype=np.uint64), np.zeros(4, dtype=np.uint64)
+        self._ck(self.lib.pcgpu_ipa_finish(self.ctx, state, _ptr(key), _ptr(c)))
+        return key, c
 
     # ---- KZG10 ----
     def kzg_commit(self, powers_of_g, coeffs, n=None, powers_of_gamma_g=None, blind=None, flags=0):

@@ -98,7 +98,7 @@ extern "C" int pcgpu_srs_register(pcgpu_ctx *ctx, int curve, const void *bases_x
   SET_DEVICE(ctx);
   pcgpu_srs *srs = new (std::nothrow) pcgpu_srs();
   if (!srs) return PCGPU_E_OOM;
-  srs->curve = curve; srs->n = n; srs->d_tables = nullptr; srs->c = 0; srs->groups = 1;
+  srs->curve = curve; srs->n = n; srs->d_tables = nullptr; srs->c = 0; srs->groups = 1; srs->d_comb = nullptr; srs->comb_c = 0;
   int rc;
   switch (curve) {
     case PCGPU_BLS12_381: rc = srs_register_impl<Bls12381>(ctx, bases_xy, inf, n, flags, srs); break;
@@ -106,7 +106,7 @@ extern "C" int pcgpu_srs_register(pcgpu_ctx *ctx, int curve, const void *bases_x
     case PCGPU_PALLAS: rc = srs_register_impl<Pallas>(ctx, bases_xy, inf, n, flags, srs); break;
     default: rc = PCGPU_E_BADARG;
   }
-  if (rc) { rt::dev_free(srs->d_tables); delete srs; return rc; }
+  if (rc) { rt::dev_free(srs->d_tables); rt::dev_free(srs->d_comb); delete srs; return rc; }
   *out = srs;
   return PCGPU_OK;
 }
@@ -119,9 +119,9 @@ extern "C" void pcgpu_srs_release(pcgpu_ctx *ctx, pcgpu_srs *srs) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
 #endif
-    rt::dev_free(srs->d_tables);
+    rt::dev_free(srs->d_tables); rt::dev_free(srs->d_comb);
   } else {
-    rt::dev_free(srs->d_tables);
+    rt::dev_free(srs->d_tables); rt::dev_free(srs->d_comb);
   }
   delete srs;
 }
@@ -234,4 +234,65 @@ extern "C" int pcgpu_ntt(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in,
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return ntt_impl<C>(ctx, in, n_in, logn, flags, out));
+}
+
+extern "C" int pcgpu_msm_batch(pcgpu_ctx *ctx, const pcgpu_srs *srs, const void *scalars, size_t n, size_t count, uint32_t flags,
+                               void *out_xy, uint8_t *out_inf) {
+  if (!ctx || !srs || (n && count && !scalars) || (count && !out_xy)) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(srs->curve, return msm_batch_impl<C>(ctx, srs, scalars, n, count, flags, out_xy, out_inf));
+}
+
+extern "C" int pcgpu_ipa_begin(pcgpu_ctx *ctx, int curve, const void *comm_key_xy, size_t n, const void *coeffs, size_t n_coeffs,
+                               const void *point, uint32_t flags, pcgpu_ipa **out) {
+  if (!ctx || !out || !comm_key_xy || !point || n == 0 || (n & (n - 1)) || n_coeffs > n || (n_coeffs && !coeffs)) return PCGPU_E_BADARG;
+  *out = nullptr;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  pcgpu_ipa *st = new (std::nothrow) pcgpu_ipa();
+  if (!st) return PCGPU_E_OOM;
+  int rc;
+  switch (curve) {
+    case PCGPU_BLS12_381: rc = ipa_begin_impl<Bls12381>(ctx, comm_key_xy, n, coeffs, n_coeffs, point, flags, st); break;
+    case PCGPU_BN254: rc = ipa_begin_impl<Bn254>(ctx, comm_key_xy, n, coeffs, n_coeffs, point, flags, st); break;
+    case PCGPU_PALLAS: rc = ipa_begin_impl<Pallas>(ctx, comm_key_xy, n, coeffs, n_coeffs, point, flags, st); break;
+    default: rc = PCGPU_E_BADARG;
+  }
+  if (rc) { rt::dev_free(st->d_key); rt::dev_free(st->d_coeffs); delete st; return rc; }
+  *out = st;
+  return PCGPU_OK;
+}
+
+extern "C" int pcgpu_ipa_round_lr(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_prime_xy, void *out_l_xy, uint8_t *out_l_inf,
+                                  void *out_r_xy, uint8_t *out_r_inf) {
+  if (!ctx || !st || !h_prime_xy || !out_l_xy || !out_r_xy) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(st->curve, return ipa_round_lr_impl<C>(ctx, st, h_prime_xy, out_l_xy, out_l_inf, out_r_xy, out_r_inf));
+}
+
+extern "C" int pcgpu_ipa_round_fold(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *challenge, const void *challenge_inv) {
+  if (!ctx || !st || !challenge || !challenge_inv) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(st->curve, return ipa_round_fold_impl<C>(ctx, st, challenge, challenge_inv));
+}
+
+extern "C" size_t pcgpu_ipa_len(const pcgpu_ipa *st) { return st ? st->n : 0; }
+
+extern "C" int pcgpu_ipa_finish(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_key_xy, void *out_c) {
+  if (!ctx || !st) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  int rc;
+  switch (st->curve) {
+    case PCGPU_BLS12_381: rc = ipa_finish_impl<Bls12381>(ctx, st, out_final_key_xy, out_c); break;
+    case PCGPU_BN254: rc = ipa_finish_impl<Bn254>(ctx, st, out_final_key_xy, out_c); break;
+    case PCGPU_PALLAS: rc = ipa_finish_impl<Pallas>(ctx, st, out_final_key_xy, out_c); break;
+    default: rc = PCGPU_E_BADARG;
+  }
+  rt::dev_free(st->d_key); rt::dev_free(st->d_coeffs);
+  delete st;
+  return rc;
 }

@@ -132,6 +132,23 @@ template <class C> inline void to_affine(const HXYZZ<C> &p, void *out_xy, uint8_
   if (out_inf) *out_inf = 0;
 }
 
+// k * P for an affine P (x||y Montgomery limbs, identity = all zero) and a CANONICAL 256-bit scalar
+template <class C> inline HXYZZ<C> pmul_affine(const void *p_xy, const uint64_t *k) {
+  using Q = typename C::Fq;
+  HXYZZ<C> base;
+  memcpy(&base.x, p_xy, sizeof base.x); memcpy(&base.y, (const char *)p_xy + sizeof base.x, sizeof base.y);
+  if (base.x.is_zero() && base.y.is_zero()) return HXYZZ<C>::inf();
+  base.zz = HFp<Q>::one(); base.zzz = HFp<Q>::one();
+  HXYZZ<C> acc = HXYZZ<C>::inf();
+  for (int b = 255; b >= 0; b--) { acc = pdbl<C>(acc); if ((k[b >> 6] >> (b & 63)) & 1) acc = padd<C>(acc, base); }
+  return acc;
+}
+// Montgomery -> canonical for one Fr element on the host
+template <class R> inline void fr_from_mont_host(const void *in, uint64_t *out) {
+  HFp<R> a, one = HFp<R>::zero(); memcpy(a.l, in, sizeof a.l); one.l[0] = 1;
+  HFp<R> r = mul<R>(a, one); memcpy(out, r.l, sizeof r.l);
+}
+
 // Combination of the device's bit-plane sums T[s][j] = sum of the buckets of set s whose weight has bit j set:
 //   result = sum_s 2^(c s) * sum_j 2^j T[s][j]
 template <class C> inline HXYZZ<C> combine_bit_planes(const HXYZZ<C> *T, uint32_t S, uint32_t c) {

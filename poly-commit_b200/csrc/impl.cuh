@@ -13,6 +13,7 @@
 #include "frops.cuh"
 #include "host_ec.hpp"
 #include "ntt.cuh"
+#include "ipa.cuh"
 #include <chrono>
 #include "msm.cuh"
 #include "srs.cuh"
@@ -60,6 +61,8 @@ struct pcgpu_srs {
   uint32_t c;        // window bits the groups were built for (0: raw bases only)
   uint32_t groups;   // table groups (1: raw bases)
   void *d_tables;    // groups * n affine points
+  void *d_comb;      // fixed-base comb tables (PCGPU_SRS_COMB) or null
+  uint32_t comb_c;   // comb window bits
 };
 
 struct pcgpu_ctx {
@@ -117,6 +120,13 @@ int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, siz
       for (size_t i = 0; i < n; i++)
         if (inf[i] && (rc = rt::dev_memset((char *)srs->d_tables + psz * i, 0, psz, st))) return rc;
     if (groups > 1 && (rc = srs_build_groups<C>((Affine<C> *)srs->d_tables, n, c, groups, ctx->stage, st))) return rc;
+    if (flags & PCGPU_SRS_COMB) {
+      CombGeom cg; memset(&cg, 0, sizeof cg);
+      cg.n_bases = (uint32_t)n; cg.c = 8; cg.W = C::Fr::BITS / cg.c + 1; cg.NBk = 1u << (cg.c - 1);
+      if ((rc = rt::dev_malloc(&srs->d_comb, psz * n * cg.W * cg.NBk))) return rc;
+      srs->comb_c = cg.c;
+      if ((rc = rt::launch<64>(CombTableBody<C>{(const Affine<C> *)srs->d_tables, cg, (Affine<C> *)srs->d_comb}, n * cg.W, st))) return rc;
+    }
   }
   srs->c = c; srs->groups = groups;
   return rt::stream_sync(st);
@@ -202,6 +212,62 @@ int g1_sum_impl(pcgpu_ctx *, const void *xyzz, size_t count, void *out_xy, uint8
     acc = host::padd<C>(acc, p);
   }
   host::to_affine<C>(acc, out_xy, out_inf);
+  return PCGPU_OK;
+}
+
+// `count` MSMs over shared bases (hyrax/mod.rs:233-242)
+template <class C>
+int msm_batch_impl(pcgpu_ctx *ctx, const pcgpu_srs *srs, const void *scalars, size_t n, size_t count, uint32_t flags,
+                   void *out_xy, uint8_t *out_inf) {
+  if (n > srs->n) return PCGPU_E_LEN;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  const size_t psz = sizeof(Affine<C>);
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0, mont = (flags & PCGPU_SCALARS_MONT) != 0;
+  if (count == 0) return PCGPU_OK;
+  if (!srs->d_comb || n == 0) {  // no comb tables: run the rows through the single-MSM pipeline
+    for (size_t r = 0; r < count; r++) {
+      rc = msm_impl<C>(ctx, srs, 0, (const char *)scalars + r * n * 32, n, flags, (char *)out_xy + r * psz,
+                       out_inf ? out_inf + r : nullptr, nullptr);
+      if (rc) return rc;
+    }
+    return PCGPU_OK;
+  }
+  CombGeom g; memset(&g, 0, sizeof g);
+  g.n_bases = (uint32_t)srs->n; g.c = srs->comb_c; g.W = C::Fr::BITS / g.c + 1; g.NBk = 1u << (g.c - 1);
+  g.n = (uint32_t)n; g.count = (uint32_t)count;
+  g.seg_len = 64; if (count < 4096) { while (g.seg_len > 8 && count * ((n + g.seg_len - 1) / g.seg_len) < 65536) g.seg_len /= 2; }
+  g.segs = (uint32_t)((n + g.seg_len - 1) / g.seg_len);
+  g.scalar_bits = C::Fr::BITS; g.scalars_mont = mont ? 1 : 0;
+  size_t ntasks = count * g.segs;
+  size_t need = rt::Arena::pad(ntasks * sizeof(XYZZ<C>)) + rt::Arena::pad(count * psz) + (dev ? 0 : rt::Arena::pad(count * n * 32)) + 8192;
+  if ((rc = ctx->stage.reserve(need))) return rc;
+  uint32_t *d_err = ctx->stage.take<uint32_t>(16);
+  XYZZ<C> *partial = ctx->stage.take<XYZZ<C>>(ntasks);
+  Affine<C> *d_out = ctx->stage.take<Affine<C>>(count);
+  const uint32_t *d_s = (const uint32_t *)scalars;
+  if (!dev) {
+    uint32_t *ts = ctx->stage.take<uint32_t>(count * n * 8);
+    if ((rc = rt::copy_h2d(ts, scalars, count * n * 32, st))) return rc;
+    d_s = ts;
+  }
+  if ((rc = rt::dev_memset(d_err, 0, 64, st))) return rc;
+  ctx->prof.begin(10, st);
+  if ((rc = rt::launch<128>(CombAccumulateBody<C>{(const Affine<C> *)srs->d_comb, d_s, g, partial, d_err}, ntasks, st))) return rc;
+  if ((rc = rt::launch<64>(CombRowSumBody<C>{partial, g.segs, d_out}, count, st))) return rc;
+  ctx->prof.end(10, st);
+  std::vector<Affine<C>> h(count);
+  uint32_t herr = 0;
+  if ((rc = rt::copy_d2h(h.data(), d_out, count * psz, st))) return rc;
+  if ((rc = rt::copy_d2h(&herr, d_err, 4, st))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  ctx->prof.collect();
+  if (herr) return PCGPU_E_RANGE;
+  for (size_t r = 0; r < count; r++) {
+    bool inf = h[r].is_inf();
+    memcpy((char *)out_xy + r * psz, &h[r], psz);
+    if (out_inf) out_inf[r] = inf ? 1 : 0;
+  }
   return PCGPU_OK;
 }
 
@@ -433,6 +499,99 @@ int kzg_open_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, size_
 
 
 // ---------------------------------------------------------------------------------------------
+// IPA halving loop (device-resident)
+// ---------------------------------------------------------------------------------------------
+struct pcgpu_ipa {
+  int curve; size_t n0, n;
+  void *d_key;        // n0 affine points (folded in place)
+  uint32_t *d_coeffs, *d_z, *d_scr;  // n0 Fr each; scratch for inner products
+  pcgpu_srs view;     // non-owning SRS view over d_key for the MSM pipeline
+};
+
+template <class C>
+int ipa_begin_impl(pcgpu_ctx *ctx, const void *key_xy, size_t n, const void *coeffs, size_t n_coeffs, const void *point,
+                   uint32_t flags, pcgpu_ipa *st) {
+  using R = typename C::Fr;
+  rt::stream_t s = ctx->stream;
+  int rc;
+  bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  st->curve = C::ID; st->n0 = st->n = n;
+  st->d_key = nullptr; st->d_coeffs = nullptr;
+  if ((rc = rt::dev_malloc(&st->d_key, n * sizeof(Affine<C>)))) return rc;
+  if ((rc = rt::dev_malloc((void **)&st->d_coeffs, (2 * n + IP_THREADS + 16) * 32))) return rc;
+  st->d_z = st->d_coeffs + 8 * n; st->d_scr = st->d_z + 8 * n;
+  if ((rc = dev ? rt::copy_d2d(st->d_key, key_xy, n * sizeof(Affine<C>), s) : rt::copy_h2d(st->d_key, key_xy, n * sizeof(Affine<C>), s))) return rc;
+  if ((rc = rt::dev_memset(st->d_coeffs, 0, n * 32, s))) return rc;
+  if (n_coeffs && (rc = dev ? rt::copy_d2d(st->d_coeffs, coeffs, n_coeffs * 32, s) : rt::copy_h2d(st->d_coeffs, coeffs, n_coeffs * 32, s))) return rc;
+  uint32_t *d_pt = st->d_scr + 8 * IP_THREADS;
+  if ((rc = rt::copy_h2d(d_pt, point, 32, s))) return rc;
+  if ((rc = rt::launch<128>(FrPowersBody<R>{d_pt, st->d_z}, n, s))) return rc;
+  st->view.curve = C::ID; st->view.n = n; st->view.c = 0; st->view.groups = 1; st->view.d_tables = st->d_key;
+  st->view.d_comb = nullptr; st->view.comb_c = 0;
+  return rt::stream_sync(s);
+}
+
+template <class C>
+int ipa_round_lr_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_prime_xy, void *out_l_xy, uint8_t *out_l_inf,
+                      void *out_r_xy, uint8_t *out_r_inf) {
+  using R = typename C::Fr;
+  rt::stream_t s = ctx->stream;
+  int rc;
+  size_t m = st->n / 2;
+  if (m == 0) return PCGPU_E_BADARG;
+  const uint32_t *cl = st->d_coeffs, *cr = st->d_coeffs + 8 * m, *zl = st->d_z, *zr = st->d_z + 8 * m;
+  uint32_t *d_ip = st->d_scr + 8 * IP_THREADS + 8;
+  uint64_t ip_m[2][4], ip_c[2][4];
+  // <coeffs_r, z_l>, <coeffs_l, z_r>
+  if ((rc = fr_inner_product<R>(cr, zl, m, d_ip, st->d_scr, s))) return rc;
+  if ((rc = rt::copy_d2h(ip_m[0], d_ip, 32, s))) return rc;
+  if ((rc = rt::stream_sync(s))) return rc;
+  if ((rc = fr_inner_product<R>(cl, zr, m, d_ip, st->d_scr, s))) return rc;
+  if ((rc = rt::copy_d2h(ip_m[1], d_ip, 32, s))) return rc;
+  if ((rc = rt::stream_sync(s))) return rc;
+  host::HXYZZ<C> l, r;
+  if ((rc = msm_to_host<C>(ctx, &st->view, 0, cr, m, true, &l))) return rc;  // cm_commit(key_l, coeffs_r)
+  if ((rc = msm_to_host<C>(ctx, &st->view, m, cl, m, true, &r))) return rc;  // cm_commit(key_r, coeffs_l)
+  host::fr_from_mont_host<R>(ip_m[0], ip_c[0]);
+  host::fr_from_mont_host<R>(ip_m[1], ip_c[1]);
+  l = host::padd<C>(l, host::pmul_affine<C>(h_prime_xy, ip_c[0]));
+  r = host::padd<C>(r, host::pmul_affine<C>(h_prime_xy, ip_c[1]));
+  host::to_affine<C>(l, out_l_xy, out_l_inf);
+  host::to_affine<C>(r, out_r_xy, out_r_inf);
+  return PCGPU_OK;
+}
+
+template <class C>
+int ipa_round_fold_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *challenge, const void *challenge_inv) {
+  using R = typename C::Fr;
+  rt::stream_t s = ctx->stream;
+  int rc;
+  size_t m = st->n / 2;
+  if (m == 0) return PCGPU_E_BADARG;
+  uint32_t *d_ch = st->d_scr + 8 * IP_THREADS + 16, *d_chi = d_ch + 8;
+  if ((rc = rt::copy_h2d(d_ch, challenge, 32, s))) return rc;
+  if ((rc = rt::copy_h2d(d_chi, challenge_inv, 32, s))) return rc;
+  if ((rc = rt::launch<256>(FrAxpyBody<R>{st->d_coeffs, d_chi, st->d_coeffs + 8 * m}, m, s))) return rc;  // :691-693
+  if ((rc = rt::launch<256>(FrAxpyBody<R>{st->d_z, d_ch, st->d_z + 8 * m}, m, s))) return rc;              // :695-697
+  G1FoldBody<C> fb; fb.key = (Affine<C> *)st->d_key; fb.m = (uint32_t)m;
+  uint64_t canon[4];
+  host::fr_from_mont_host<R>(challenge, canon);
+  memcpy(fb.chal, canon, 32);
+  if ((rc = rt::launch<128>(fb, m, s))) return rc;                                                          // :699-707
+  st->n = m; st->view.n = m;
+  return rt::stream_sync(s);
+}
+
+template <class C>
+int ipa_finish_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_key_xy, void *out_c) {
+  rt::stream_t s = ctx->stream;
+  int rc;
+  if (out_final_key_xy && (rc = rt::copy_d2h(out_final_key_xy, st->d_key, sizeof(Affine<C>), s))) return rc;
+  if (out_c && (rc = rt::copy_d2h(out_c, st->d_coeffs, 32, s))) return rc;
+  return rt::stream_sync(s);
+}
+
+// ---------------------------------------------------------------------------------------------
 // NTT
 // ---------------------------------------------------------------------------------------------
 template <class C>
@@ -535,4 +694,9 @@ int selftest_field_impl(pcgpu_ctx *ctx, uint64_t seed, size_t n, uint64_t *misma
   EXT template int kzg_open_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const void *, const pcgpu_srs *, \
                                     const void *, size_t, uint32_t, void *, uint8_t *, void *); \
   EXT template int selftest_field_impl<C>(pcgpu_ctx *, uint64_t, size_t, uint64_t *); \
-  EXT template int ntt_impl<C>(pcgpu_ctx *, const void *, size_t, uint32_t, uint32_t, void *);
+  EXT template int ntt_impl<C>(pcgpu_ctx *, const void *, size_t, uint32_t, uint32_t, void *); \
+  EXT template int msm_batch_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, size_t, uint32_t, void *, uint8_t *); \
+  EXT template int ipa_begin_impl<C>(pcgpu_ctx *, const void *, size_t, const void *, size_t, const void *, uint32_t, pcgpu_ipa *); \
+  EXT template int ipa_round_lr_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, void *, uint8_t *, void *, uint8_t *); \
+  EXT template int ipa_round_fold_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, const void *); \
+  EXT template int ipa_finish_impl<C>(pcgpu_ctx *, pcgpu_ipa *, void *, void *);

@@ -72,4 +72,64 @@ struct FixedBaseMulBody {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Batched MSM over SHARED bases (HyraxPC::commit: one Pedersen commitment per matrix row, all rows over the
+// same com_key -- hyrax/mod.rs:233-242): fixed-base comb.  comb[(j*W + w)*NBk + d-1] = d * 2^(c w) * G_j for
+// d in 1..2^(c-1), so a row costs n*W mixed additions and no bucket work at all.  Signed digits halve the table.
+// ---------------------------------------------------------------------------------------------
+struct CombGeom {
+  uint32_t n_bases, c, W, NBk;  // NBk = 2^(c-1) table entries per (base, window)
+  uint32_t n, count;            // row length, number of rows
+  uint32_t segs, seg_len;       // each row is split into `segs` segments of `seg_len` scalars
+  uint32_t scalar_bits, scalars_mont;
+};
+
+template <class C>
+struct CombTableBody {
+  const Affine<C> *bases; CombGeom g; Affine<C> *table;
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    uint32_t j = (uint32_t)(t / g.W), w = (uint32_t)(t % g.W);
+    XYZZ<C> p = xyzz_from_affine<C>(load_affine<C>(bases + j));
+    for (uint32_t k = 0; k < w * g.c; k++) p = xyzz_dbl<C>(p);
+    XYZZ<C> acc = p;
+    Affine<C> *row = table + t * (size_t)g.NBk;
+    for (uint32_t d = 1; d <= g.NBk; d++) {
+      row[d - 1] = xyzz_to_affine<C>(acc);
+      xyzz_add<C>(acc, p);
+    }
+  }
+};
+
+template <class C>
+struct CombAccumulateBody {
+  const Affine<C> *table; const uint32_t *scalars; CombGeom g; XYZZ<C> *partial; uint32_t *err;
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    uint32_t row = (uint32_t)(t / g.segs), seg = (uint32_t)(t % g.segs);
+    uint32_t lo = seg * g.seg_len, hi = lo + g.seg_len < g.n ? lo + g.seg_len : g.n;
+    MsmGeom mg; mg.c = g.c; mg.W = g.W;
+    XYZZ<C> acc = XYZZ<C>::inf();
+    const Affine<C> *tab = table; const CombGeom gg = g;
+    for (uint32_t i = lo; i < hi; i++) {
+      uint32_t k[8];
+      load_scalar<C>(scalars, (size_t)row * g.n + i, g.scalars_mont != 0, k);
+      if (!scalar_in_range(k, g.scalar_bits)) { rt::atomic_or(err, 1u); continue; }
+      for_each_digit(k, mg, [&](uint32_t w, uint32_t mag, bool neg) {
+        Affine<C> a = load_affine<C>(tab + ((size_t)i * gg.W + w) * gg.NBk + (mag - 1));
+        xyzz_madd<C>(acc, a, neg);
+      });
+    }
+    store_xyzz<C>(partial + t, acc);
+  }
+};
+
+template <class C>
+struct CombRowSumBody {
+  const XYZZ<C> *partial; uint32_t segs; Affine<C> *out;
+  PCGPU_KERNEL_DEV void operator()(size_t row) const {
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (uint32_t s = 0; s < segs; s++) { XYZZ<C> p = load_xyzz<C>(partial + row * segs + s); xyzz_add<C>(acc, p); }
+    out[row] = xyzz_to_affine<C>(acc);
+  }
+};
+
 }  // namespace pcgpu

@@ -15,7 +15,7 @@ from tests import util
 from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_fr_vector_ops,  # noqa: F401
                                   test_kzg_commit_open, test_msm_edge_scalars, test_msm_infinity_bases,
                                   test_msm_partial_and_sum, test_msm_precomputed_tables, test_msm_vs_oracle,
-                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle)
+                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds)
 
 pytestmark = pytest.mark.gpu
 
@@ -156,3 +156,74 @@ def test_ntt_large(eng, cname, logn):
     assert (got == orc.fr_ntt(C.id, x, logn)).all()
     back = eng.ntt(C.id, got, logn, inverse=True)
     assert (back[:n_in] == x).all() and not back[n_in:].any()
+
+
+def test_cfg4_hyrax_commit_rows(eng, pc):
+    """BASELINE.json cfg4: Hyrax, 22 variables, BN254 -- 2^11 Pedersen row commitments over one com_key (+ h * r_i)
+    (hyrax/mod.rs:233-242).  Row randomness is an INPUT (the reference draws it from thread_rng, :237-238, so parity is
+    asserted at pedersen_commit level).  Checks: sampled rows vs one oracle MSM each; the sum of all row commitments vs
+    the oracle MSM of the column sums (linearity over the whole matrix)."""
+    cname = "bn254"
+    C = pyref.Curve(cname)
+    dim = 1 << 11
+    bases = gpu_srs(eng, cname, dim + 1, seed=30)                 # com_key || h  (synthetic generators k_i * G)
+    mat = util.rand_fr_fast(cname, dim * (dim + 1), seed=31).reshape(dim, dim + 1, 4)   # evaluations || r_i
+    srs = eng.srs_register(C.id, bases, flags=pc.SRS_COMB)
+    got, inf = eng.msm_batch(srs, mat, dim + 1, dim, flags=pc.SCALARS_MONT)
+    assert not inf.any()
+    for r in (0, 1, 777, dim - 1):
+        exp = orc.msm(C.id, bases, orc.field_unop("orc_fr_from_mont", C.id, mat[r]))
+        assert (got[r] == exp[0]).all(), r
+    ones = np.tile(util.fr_const(cname, 1), (dim, 1))
+    colsum = eng.fr_row_mul(C.id, ones, mat.reshape(-1, 4), dim, dim + 1)
+    exp = orc.msm(C.id, bases, orc.field_unop("orc_fr_from_mont", C.id, colsum))
+    tot = orc.g1_sum(C.id, got)
+    assert (tot[0] == exp[0]).all()
+    # Hyrax open's matrix-vector product (hyrax/mod.rs:347 -> utils.rs:127-146) at full size, sampled columns vs oracle
+    l = util.rand_fr_fast(cname, dim, seed=32)
+    lt = eng.fr_row_mul(C.id, l, mat.reshape(-1, 4), dim, dim + 1)
+    for cidx in (0, 5, dim):
+        col = np.ascontiguousarray(mat[:, cidx, :])
+        assert (lt[cidx] == orc.fr_inner_product(C.id, l, col)).all()
+
+
+def test_cfg3_ipa_open_2p18_pallas(eng, pc):
+    """BASELINE.json cfg3: InnerProductArgPC open, degree 2^18 - 1, Pallas: the whole 18-round loop on the device;
+    parity through (i) round-1 l and r against the oracle directly, (ii) the closed forms of the loop:
+    c = sum_i coeffs[i] * prod_j inv_j^{b_j(i)},  final_comm_key = sum_i (prod_j chal_j^{b_j(i)}) key[i]."""
+    from poly_commit_b200 import ipa_pc
+    cname = "pallas"
+    C = pyref.Curve(cname)
+    logn = 18
+    n = 1 << logn
+    key = gpu_srs(eng, cname, n, seed=40)
+    h_prime = util.random_points(cname, 1, seed=41)[0]
+    coeffs = util.rand_fr_fast(cname, n, seed=42)
+    point = util.rand_fr(cname, 1, seed=43, mont=True)[0]
+    got = ipa_pc.open_rounds(eng, C.id, key, coeffs, point, h_prime, 0xabcdef)
+    assert len(got["l_vec"]) == logn
+    # (i) first round against the oracle
+    m = n // 2
+    z_int = C.fr_from_limbs(point, True)[0]
+    co_int = C.fr_from_limbs(coeffs, True)
+    zp = [1] * n
+    for i in range(1, n):
+        zp[i] = zp[i - 1] * z_int % C.r
+    def cm(keypart, sc_ints, ip):
+        msm, inf = orc.msm(C.id, keypart, C.fr_to_limbs(sc_ints, False))
+        hp, hinf = orc.g1_mul(C.id, h_prime, C.fr_to_limbs([ip], False))
+        return orc.g1_sum(C.id, np.stack([msm, hp]), inf=np.array([inf, hinf], dtype=np.uint8))[0]
+    l0 = cm(key[:m], co_int[m:], sum(a * b for a, b in zip(co_int[m:], zp[:m])) % C.r)
+    r0 = cm(key[m:], co_int[:m], sum(a * b for a, b in zip(co_int[:m], zp[m:])) % C.r)
+    assert (got["l_vec"][0] == l0).all() and (got["r_vec"][0] == r0).all()
+    # (ii) closed forms
+    ch = got["challenges"]
+    inv = [pow(c, -1, C.r) for c in ch]
+    s_ch, s_inv = [1], [1]
+    for j in range(logn - 1, -1, -1):          # last round pairs neighbours (lowest bit), first round the top bit
+        s_ch = s_ch + [x * ch[j] % C.r for x in s_ch]
+        s_inv = s_inv + [x * inv[j] % C.r for x in s_inv]
+    c_exp = sum(a * b for a, b in zip(co_int, s_inv)) % C.r
+    assert C.fr_from_limbs(got["c"], True)[0] == c_exp
+    fk = orc.msm(C.id, key, C.fr_to_limbs(s_ch, False))
+    assert (got["final_comm_key"] == fk[0]).all()

@@ -142,6 +142,28 @@ def test_msm_precomputed_tables(eng, pc):
     assert (got[0] == exp[0]).all()
 
 
+@pytest.mark.parametrize("cname", ["bn254", "bls12_381"])
+def test_msm_batch_shared_bases(eng, pc, cname):
+    """HyraxPC::commit row loop (hyrax/mod.rs:233-242): dim Pedersen commitments over one com_key (+ h * r_i),
+    comb tables and the no-table path, against one oracle MSM per row."""
+    C = pyref.Curve(cname)
+    dim = 9
+    bases = util.random_points(cname, dim + 1, seed=50)       # com_key || h
+    rows = util.rand_fr(cname, dim * (dim + 1), seed=51, mont=True).reshape(dim, dim + 1, 4)
+    rows[2] = 0                                                # an all-zero row commits to the identity
+    rows[3, :, :] = 0; rows[3, 0] = util.fr_const(cname, 1)    # = G_0
+    canon = orc.field_unop("orc_fr_from_mont", C.id, rows.reshape(-1, 4)).reshape(dim, dim + 1, 4)
+    exp = [orc.msm(C.id, bases, canon[r]) for r in range(dim)]
+    for flags in (pc.SRS_COMB, 0):
+        srs = eng.srs_register(C.id, bases, flags=flags)
+        got, inf = eng.msm_batch(srs, rows, dim + 1, dim, flags=pc.SCALARS_MONT)
+        for r in range(dim):
+            assert inf[r] == exp[r][1] and (got[r] == exp[r][0]).all(), (flags, r)
+        got2, _ = eng.msm_batch(srs, canon, dim + 1, dim)
+        assert (got2 == got).all()
+    assert inf[2] == 1
+
+
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
 def test_msm_partial_and_sum(eng, cname):
     """index-range sharding (SURVEY 8e partitioning B): partial XYZZ sums add up to the whole MSM."""
@@ -204,6 +226,52 @@ def test_row_mul_reference_kat(eng):
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
 def test_golden_vectors(eng, cname):
     golden_cases.check_engine(eng, cname)
+
+
+def oracle_ipa_rounds(cname, comm_key, coeffs, point, h_prime, round_challenge):
+    """InnerProductArgPC::open's halving loop (ipa_pc/mod.rs:665-711) restated over the C oracle's primitives."""
+    from poly_commit_b200 import ipa_pc
+    C = pyref.Curve(cname)
+    n = comm_key.shape[0]
+    co = np.zeros((n, 4), dtype=np.uint64); co[: coeffs.shape[0]] = coeffs
+    z_int = C.fr_from_limbs(point, True)[0]
+    z = C.fr_to_limbs([pow(z_int, i, C.r) for i in range(n)], True)
+    key = comm_key.copy()
+    l_vec, r_vec = [], []
+    while n > 1:
+        m = n // 2
+        def cm(keypart, sc, ip):
+            msm, inf = orc.msm(C.id, keypart, orc.field_unop("orc_fr_from_mont", C.id, sc))
+            hp, hinf = orc.g1_mul(C.id, h_prime, orc.field_unop("orc_fr_from_mont", C.id, ip.reshape(1, 4)))
+            return orc.g1_sum(C.id, np.stack([msm, hp]), inf=np.array([inf, hinf], dtype=np.uint8))[0]
+        l = cm(key[:m], co[m:n], orc.fr_inner_product(C.id, co[m:n], z[:m]))
+        r = cm(key[m:n], co[:m], orc.fr_inner_product(C.id, co[:m], z[m:n]))
+        l_vec.append(l); r_vec.append(r)
+        data = int(round_challenge).to_bytes(32, "little") + l.tobytes() + r.tobytes()
+        round_challenge = ipa_pc.compute_random_oracle_challenge(C.id, data)
+        inv = pow(round_challenge, -1, C.r)
+        co[:m] = orc.fr_axpy(C.id, co[:m], C.fr_to_limbs([inv], True)[0], co[m:n])
+        z[:m] = orc.fr_axpy(C.id, z[:m], C.fr_to_limbs([round_challenge], True)[0], z[m:n])
+        key[:m] = orc.g1_fold(C.id, key[:n], C.fr_to_limbs([round_challenge], False))
+        n = m
+    return dict(l_vec=l_vec, r_vec=r_vec, final_comm_key=key[0], c=co[0])
+
+
+@pytest.mark.parametrize("cname,n", [("pallas", 64), ("bls12_381", 16), ("bn254", 32)])
+def test_ipa_open_rounds(eng, pc, cname, n):
+    """cfg3's dataflow (Pallas; the reference instantiates IPA on Jubjub only): every l, r, the final key and c."""
+    from poly_commit_b200 import ipa_pc
+    C = pyref.Curve(cname)
+    key = util.random_points(cname, n, seed=70)
+    h_prime = util.random_points(cname, 1, seed=71)[0]
+    coeffs = util.rand_fr(cname, n - 3, seed=72, mont=True)     # fewer than d+1 coefficients: zero padded (:636-641)
+    point = util.rand_fr(cname, 1, seed=73, mont=True)[0]
+    got = ipa_pc.open_rounds(eng, C.id, key, coeffs, point, h_prime, 0x1234567)
+    exp = oracle_ipa_rounds(cname, key, coeffs, point, h_prime, 0x1234567)
+    assert len(got["l_vec"]) == n.bit_length() - 1
+    for a, b in zip(got["l_vec"] + got["r_vec"], exp["l_vec"] + exp["r_vec"]):
+        assert (a == b).all()
+    assert (got["final_comm_key"] == exp["final_comm_key"]).all() and (got["c"] == exp["c"]).all()
 
 
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
