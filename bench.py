@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 LOG_DEG = 20
 CURVE = "bls12_381"
 ALGO_BYTES_PER_SCALAR_MULT = 128  # 96 B affine base + 32 B scalar
+# dram__bytes_read.sum + dram__bytes_write.sum of one MsmAccumulateBody<Bls12381> launch, from the committed
+# ncu --set full capture profiles/r01_ncu_accumulate_bls12_381_2p20.txt (3.272687 GB + 52.435456 MB)
+NCU_TRAFFIC_BYTES = {20: 3272687000 + 52435456}
 
 
 def parse():
@@ -41,6 +44,7 @@ def parse():
     ap.add_argument("--impl", default="pcgpu", choices=["pcgpu", "reference"])
     ap.add_argument("--log-deg", type=int, default=LOG_DEG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3, help="polynomials in flight per GPU (one context + stream each)")
     return ap.parse_args()
 
 
@@ -55,7 +59,8 @@ def measured_peaks():
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,"
+         "timestamp")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -63,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -73,6 +78,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """start of the timed region: only samples taken after this moment are reported"""
+        import datetime
+        self.t_mark = datetime.datetime.now()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -81,10 +91,21 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        import datetime
+        rows = []
+        for r in self.rows:
+            if len(r) < 10:
+                continue
+            try:
+                ts = datetime.datetime.strptime(r[9], "%Y/%m/%d %H:%M:%S.%f")
+            except Exception:
+                continue
+            if getattr(self, "t_mark", None) is None or ts >= self.t_mark:
+                rows.append(r)
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 9 for k in range(4) if r[5 + k].lower().startswith("active")})
+        reasons = sorted({names[k] for r in rows for k in range(4) if r[5 + k].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -212,19 +233,40 @@ def main():
     host_polys = [torch.from_numpy(util.rand_fr_fast(CURVE, n, 100 + rank * n_polys + i).view(np.int64)).pin_memory() for i in range(n_polys)]
     dev_polys = [h.cuda() for h in host_polys]
     z = util.rand_fr(CURVE, 1, seed=4, mont=True)[0]
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    # `inflight` independent polynomials are processed concurrently, each on its own context (own stream + workspace),
+    # sharing the read-only SRS tables: the latency-bound tails of one MSM overlap the multiply-bound phase of another.
+    import threading
+    inflight = max(1, args.inflight)
+    engines = [eng] + [pc.Engine(local_rank) for _ in range(inflight - 1)]
 
-    def step_dev(i):
+    def step_dev(i, e=None):
+        e = e or eng
         d = dev_polys[i % n_polys]
-        c = eng.kzg_commit(srs, d.data_ptr(), n=n, flags=pc.DEVICE_PTRS)
-        w = eng.kzg_open(srs, d.data_ptr(), z, n=n, flags=pc.DEVICE_PTRS)
+        c = e.kzg_commit(srs, d.data_ptr(), n=n, flags=pc.DEVICE_PTRS)
+        w = e.kzg_open(srs, d.data_ptr(), z, n=n, flags=pc.DEVICE_PTRS)
         return c, w
 
-    def step_host(i):
+    def step_host(i, e=None):
+        e = e or eng
         h = host_polys[i % n_polys].numpy().view(np.uint64)
-        c = eng.kzg_commit(srs, h, n=n)
-        w = eng.kzg_open(srs, h, z, n=n)
+        c = e.kzg_commit(srs, h, n=n)
+        w = e.kzg_open(srs, h, z, n=n)
         return c, w
+
+    def run_steps(fn, k):
+        """k steps spread over the in-flight contexts (thread j takes steps j, j+inflight, ...)."""
+        if inflight == 1:
+            for i in range(k):
+                fn(i)
+            return
+        def work(j):
+            for i in range(j, k, inflight):
+                fn(i, engines[j])
+        ts = [threading.Thread(target=work, args=(j,)) for j in range(inflight)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
 
     def barrier():
         if world > 1:
@@ -234,34 +276,44 @@ def main():
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the library's calls are synchronous (each ends with a sync of its own stream), so events recorded on the
+        # current stream before the first call and after the last one bracket all the work of all contexts
         e0.record()
-        for i in range(k):
-            fn(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_steps(fn, k)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = max(e0.elapsed_time(e1), wall_ms)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
-    for i in range(warmup):
-        step_dev(i)
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    eng.profile_enable(True)
+    sampler.start()                      # started before the warm-up so nvidia-smi is already streaming samples
+    run_steps(step_dev, warmup * inflight)
+    sampler.mark()
     l0 = eng.launch_count()
     ms_dev = timed(step_dev, steps)
     launches = eng.launch_count() - l0
-    acc_ms, acc_cnt = eng.profile_get(4)
-    stage_ms = {name: eng.profile_get(s)[0] / max(steps, 1) for s, name in
-                enumerate(["digits_count", "scan", "scatter", "tasks", "bucket_accumulate", "bucket_reduce", "final", "fr_division"])}
-    eng.profile_enable(False)
     clocks = sampler.stop()
-    for i in range(min(warmup, 2)):
-        step_host(i)
+    eng.profile_enable(False)
+    run_steps(step_host, 2 * inflight)
     ms_host = timed(step_host, steps)
+    # kernel-level timings: a separate pass with ONE polynomial in flight, CUDA events around every stage on the
+    # launching stream (with several contexts in flight the per-stage times would include the other context's kernels)
+    eng.profile_enable(True)
+    prof_steps = min(steps, 8)
+    for i in range(prof_steps):
+        step_dev(i)
+    acc_ms, acc_cnt = eng.profile_get(4)
+    stage_ms = {name: eng.profile_get(s)[0] / max(prof_steps, 1) for s, name in
+                enumerate(["digits_count", "scan", "scatter", "tasks", "bucket_accumulate", "bucket_reduce", "final_host", "fr_division"])}
+    eng.profile_enable(False)
 
     if rank != 0:
         return
@@ -275,7 +327,7 @@ def main():
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32-limb Montgomery (Fq 381-bit x12, Fr 255-bit x8)",
         "data": "synthetic",
-        "config": {"workload": workload, "parallelism": f"poly-sharded x{world}, SRS replicated",
+        "config": {"workload": workload, "parallelism": f"poly-sharded x{world}, SRS replicated, {inflight} polynomials in flight per GPU",
                    "l2": "per-step working set (window-folded SRS tables 1.6 GB gather + 34 MB coefficients, rotating "
                          "polynomials) exceeds the 126 MB L2; no explicit flush"},
         "msm_scalar_mults_per_s": 2 * n * polys / (ms_dev / 1e3),
@@ -285,7 +337,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "run_kernel<MsmAccumulateBody<Bls12381>>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC_BYTES.get(log_deg), "peak_source": peak_src,
                      "launch_ms": acc_ms / max(acc_cnt, 1),
                      "note": "MSM is INT32-multiply bound (~3.4k IMAD.WIDE per 128 algorithmic bytes); the HBM fraction "
                              "is reported because north_star asks for it"},

