@@ -54,7 +54,7 @@ PCGPU_DEV XYZZ<C> xyzz_dbl_affine(const Affine<C> &a) {
   Fp<Q> S = fp_mul<Q>(a.x, V);
   Fp<Q> M = fp_mul3<Q>(fp_sqr<Q>(a.x));
   r.x = fp_sub<Q>(fp_sqr<Q>(M), fp_dbl<Q>(S));
-  r.y = fp_sub<Q>(fp_mul<Q>(M, fp_sub<Q>(S, r.x)), fp_mul<Q>(W, a.y));
+  r.y = fp_mul2<Q>(M, fp_sub<Q>(S, r.x), W, fp_neg<Q>(a.y));
   r.zz = V; r.zzz = W;
   return r;
 }
@@ -71,7 +71,7 @@ PCGPU_DEV XYZZ<C> xyzz_dbl(const XYZZ<C> &p) {
   Fp<Q> S = fp_mul<Q>(p.x, V);
   Fp<Q> M = fp_mul3<Q>(fp_sqr<Q>(p.x));
   r.x = fp_sub<Q>(fp_sqr<Q>(M), fp_dbl<Q>(S));
-  r.y = fp_sub<Q>(fp_mul<Q>(M, fp_sub<Q>(S, r.x)), fp_mul<Q>(W, p.y));
+  r.y = fp_mul2<Q>(M, fp_sub<Q>(S, r.x), W, fp_neg<Q>(p.y));
   r.zz = fp_mul<Q>(V, p.zz);
   r.zzz = fp_mul<Q>(W, p.zzz);
   return r;
@@ -98,7 +98,7 @@ PCGPU_DEV void xyzz_madd(XYZZ<C> &p, const Affine<C> &a_in, bool neg) {
   Fp<Q> PPP = fp_mul<Q>(Pd, PP);
   Fp<Q> Qv = fp_mul<Q>(p.x, PP);
   Fp<Q> x3 = fp_sub<Q>(fp_sub<Q>(fp_sqr<Q>(R), PPP), fp_dbl<Q>(Qv));
-  Fp<Q> y3 = fp_sub<Q>(fp_mul<Q>(R, fp_sub<Q>(Qv, x3)), fp_mul<Q>(p.y, PPP));
+  Fp<Q> y3 = fp_mul2<Q>(R, fp_sub<Q>(Qv, x3), fp_neg<Q>(p.y), PPP);
   p.x = x3; p.y = y3;
   p.zz = fp_mul<Q>(p.zz, PP);
   p.zzz = fp_mul<Q>(p.zzz, PPP);
@@ -124,7 +124,7 @@ PCGPU_DEV void xyzz_add(XYZZ<C> &p, const XYZZ<C> &q) {
   Fp<Q> PPP = fp_mul<Q>(Pd, PP);
   Fp<Q> Qv = fp_mul<Q>(U1, PP);
   Fp<Q> x3 = fp_sub<Q>(fp_sub<Q>(fp_sqr<Q>(R), PPP), fp_dbl<Q>(Qv));
-  Fp<Q> y3 = fp_sub<Q>(fp_mul<Q>(R, fp_sub<Q>(Qv, x3)), fp_mul<Q>(S1, PPP));
+  Fp<Q> y3 = fp_mul2<Q>(R, fp_sub<Q>(Qv, x3), fp_neg<Q>(S1), PPP);
   p.x = x3; p.y = y3;
   p.zz = fp_mul<Q>(fp_mul<Q>(p.zz, q.zz), PP);
   p.zzz = fp_mul<Q>(fp_mul<Q>(p.zzz, q.zzz), PPP);

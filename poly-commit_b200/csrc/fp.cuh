@@ -274,10 +274,103 @@ PCGPU_DEV Fp<P> mont_mul(const Fp<P> &a, const Fp<P> &b) {
   return r;
 }
 
+// ---- sum of two products with ONE Montgomery reduction:  a*b + c*d  (mod p, Montgomery form) ----
+// Same row structure as mont_row with a second pair of product chains per row; T stays below 3p
+// (3p < 2^(32N) for every field here), so the result needs two conditional subtractions.  Saves one
+// reduction phase (N^2/2 wide multiplies) wherever a formula has the shape x*y - z*w.
+template <class P, bool FIRST>
+PCGPU_DEV void mont_row2(uint32_t *X, uint32_t *Y, const uint32_t *a, uint32_t bi, const uint32_t *c, uint32_t di) {
+  constexpr int N = P::N;
+  if (FIRST) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      X[j] = mul_lo(a[j], bi); X[j + 1] = mul_hi(a[j], bi);
+      Y[j] = mul_lo(a[j + 1], bi); Y[j + 1] = mul_hi(a[j + 1], bi);
+    }
+  } else {
+    X[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+      Y[j] = madc_lo_cc(a[j + 1], bi, Y[j + 2]);
+      Y[j + 1] = madc_hi_cc(a[j + 1], bi, Y[j + 3]);
+    }
+    Y[N - 2] = madc_lo_cc(a[N - 1], bi, 0u);
+    Y[N - 1] = madc_hi(a[N - 1], bi, 0u);
+    X[0] = mad_lo_cc(a[0], bi, X[0]);
+    X[1] = madc_hi_cc(a[0], bi, X[1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      X[j] = madc_lo_cc(a[j], bi, X[j]);
+      X[j + 1] = madc_hi_cc(a[j], bi, X[j + 1]);
+    }
+    Y[N - 1] = addc(Y[N - 1], 0u);
+  }
+  // second product c * di
+  Y[0] = mad_lo_cc(c[1], di, Y[0]);
+  Y[1] = madc_hi_cc(c[1], di, Y[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    Y[j] = madc_lo_cc(c[j + 1], di, Y[j]);
+    Y[j + 1] = madc_hi_cc(c[j + 1], di, Y[j + 1]);
+  }
+  X[0] = mad_lo_cc(c[0], di, X[0]);
+  X[1] = madc_hi_cc(c[0], di, X[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    X[j] = madc_lo_cc(c[j], di, X[j]);
+    X[j + 1] = madc_hi_cc(c[j], di, X[j + 1]);
+  }
+  Y[N - 1] = addc(Y[N - 1], 0u);
+  // reduction row
+  uint32_t m = X[0] * P::M0;
+  Y[0] = mad_lo_cc(P::mod(1), m, Y[0]);
+  Y[1] = madc_hi_cc(P::mod(1), m, Y[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    Y[j] = madc_lo_cc(P::mod(j + 1), m, Y[j]);
+    Y[j + 1] = madc_hi_cc(P::mod(j + 1), m, Y[j + 1]);
+  }
+  X[0] = mad_lo_cc(P::mod(0), m, X[0]);
+  X[1] = madc_hi_cc(P::mod(0), m, X[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    X[j] = madc_lo_cc(P::mod(j), m, X[j]);
+    X[j + 1] = madc_hi_cc(P::mod(j), m, X[j + 1]);
+  }
+  Y[N - 1] = addc(Y[N - 1], 0u);
+}
+
+template <class P>
+PCGPU_HD constexpr bool mont_mul2_supported() { return 3ull * ((unsigned long long)P::mod(P::N - 1) + 1) <= (1ull << 32); }
+
+template <class P>
+PCGPU_DEV Fp<P> mont_mul2(const Fp<P> &a, const Fp<P> &b, const Fp<P> &c, const Fp<P> &d) {
+  constexpr int N = P::N;
+  static_assert(mont_mul2_supported<P>(), "sum-of-products reduction needs 3p < 2^(32N) (not true for BLS12-381 Fr)");
+  uint32_t X[N], Y[N];
+  mont_row2<P, true>(X, Y, a.l, b.l[0], c.l, d.l[0]);
+  mont_row2<P, false>(Y, X, a.l, b.l[1], c.l, d.l[1]);
+#pragma unroll
+  for (int i = 2; i < N; i += 2) {
+    mont_row2<P, false>(X, Y, a.l, b.l[i], c.l, d.l[i]);
+    mont_row2<P, false>(Y, X, a.l, b.l[i + 1], c.l, d.l[i + 1]);
+  }
+  Fp<P> r;
+  r.l[0] = add_cc(X[0], Y[1]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(X[i], Y[i + 1]);
+  r.l[N - 1] = addc(X[N - 1], 0u);
+  fp_reduce_once<P>(r.l);
+  fp_reduce_once<P>(r.l);
+  return r;
+}
+
 #ifdef PCGPU_USE_REF_MUL
 template <class P> PCGPU_DEV Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) { return mont_mul_ref<P>(a, b); }
+template <class P> PCGPU_DEV Fp<P> fp_mul2(const Fp<P> &a, const Fp<P> &b, const Fp<P> &c, const Fp<P> &d) { return fp_add<P>(mont_mul_ref<P>(a, b), mont_mul_ref<P>(c, d)); }
 #else
 template <class P> PCGPU_DEV Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) { return mont_mul<P>(a, b); }
+template <class P> PCGPU_DEV Fp<P> fp_mul2(const Fp<P> &a, const Fp<P> &b, const Fp<P> &c, const Fp<P> &d) { return mont_mul2<P>(a, b, c, d); }
 #endif
 template <class P> PCGPU_DEV Fp<P> fp_sqr(const Fp<P> &a) { return fp_mul<P>(a, a); }
 

@@ -56,24 +56,26 @@ struct FrAxpyBody {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Division by (X - z) as a three-level scan of the affine maps  t -> p_i + z * t.
-//   level 1: chunks of DIV_K coefficients  (thread per chunk)  -> local Horner value
-//   level 2: groups of DIV_G chunks        (thread per group)
-//   level 3: one thread walks the groups
-// then the carries are pushed back down and every chunk replays its recurrence writing q.
+// Division by (X - z) as a multi-level scan of the affine maps  t -> p_i + z * t.
+//   level 0: chunks of DIV_K coefficients (thread per chunk) -> local Horner value
+//   level l: nodes of DIV_F children each, folded with the factor z^(span of a child)
+//   the top level (<= DIV_F nodes) is walked by one thread; carries are then pushed back down level by
+//   level and every chunk replays its recurrence writing q.
 // q[i-1] = p[i] + z*q[i]; carry into a chunk = q[hi-1] with q[n-1] := 0; remainder = p(z).
 // ---------------------------------------------------------------------------------------------
-enum { DIV_K = 32, DIV_G = 64 };
+enum { DIV_K = 32, DIV_F = 32, DIV_MAX_LEVELS = 8 };
 
 template <class R>
-struct DivPowersBody {  // zp[0] = z^DIV_K, zp[1] = z^(DIV_K*DIV_G)
-  const uint32_t *z; uint32_t *zp;
+struct DivPowersBody {  // zp[0] = z^DIV_K, zp[l] = zp[l-1]^DIV_F
+  const uint32_t *z; uint32_t *zp; uint32_t levels;
   PCGPU_KERNEL_DEV void operator()(size_t) const {
     Fp<R> a = load_fr<R>(z, 0);
     for (int k = DIV_K; k > 1; k >>= 1) a = fp_sqr<R>(a);
     store_fr<R>(zp, 0, a);
-    for (int k = DIV_G; k > 1; k >>= 1) a = fp_sqr<R>(a);
-    store_fr<R>(zp, 1, a);
+    for (uint32_t l = 1; l < levels; l++) {
+      for (int k = DIV_F; k > 1; k >>= 1) a = fp_sqr<R>(a);
+      store_fr<R>(zp, l, a);
+    }
   }
 };
 
@@ -88,43 +90,32 @@ struct DivChunkLocalBody {
   }
 };
 
-// group local value: fold chunk locals from the top chunk of the group down
+// parent local value: fold the children's locals from the top child down (factor = z^(span of one child))
 template <class R>
-struct DivGroupLocalBody {
-  const uint32_t *local; size_t nchunks; const uint32_t *zp; uint32_t *glocal;
+struct DivFoldBody {
+  const uint32_t *child; size_t nchild; const uint32_t *factor; uint32_t *parent;
   PCGPU_KERNEL_DEV void operator()(size_t g) const {
-    size_t lo = g * DIV_G, hi = lo + DIV_G < nchunks ? lo + DIV_G : nchunks;
-    Fp<R> zk = load_fr<R>(zp, 0), acc = Fp<R>::zero();
-    for (size_t c = hi; c-- > lo;) acc = fp_add<R>(fp_mul<R>(acc, zk), load_fr<R>(local, c));
-    store_fr<R>(glocal, g, acc);
+    size_t lo = g * DIV_F, hi = lo + DIV_F < nchild ? lo + DIV_F : nchild;
+    Fp<R> f = load_fr<R>(factor, 0), acc = Fp<R>::zero();
+    for (size_t c = hi; c-- > lo;) acc = fp_add<R>(fp_mul<R>(acc, f), load_fr<R>(child, c));
+    store_fr<R>(parent, g, acc);
   }
 };
 
-// carries into groups (gcarry[g] = value entering group g from above); rem = value leaving group 0
+// carries into the children of node g (carry[c] = value entering child c from above); with parent_carry == null the
+// node is the (single) root whose incoming carry is zero and whose outgoing value is the remainder
 template <class R>
-struct DivGroupCarryBody {
-  const uint32_t *glocal; size_t ngroups; const uint32_t *zp; uint32_t *gcarry; uint32_t *rem;
-  PCGPU_KERNEL_DEV void operator()(size_t) const {
-    Fp<R> zg = load_fr<R>(zp, 1), t = Fp<R>::zero();
-    for (size_t g = ngroups; g-- > 0;) {
-      store_fr<R>(gcarry, g, t);
-      t = fp_add<R>(fp_mul<R>(t, zg), load_fr<R>(glocal, g));
-    }
-    store_fr<R>(rem, 0, t);
-  }
-};
-
-// carries into chunks
-template <class R>
-struct DivChunkCarryBody {
-  const uint32_t *local; size_t nchunks; const uint32_t *zp; const uint32_t *gcarry; uint32_t *ccarry;
+struct DivCarryBody {
+  const uint32_t *child; size_t nchild; const uint32_t *factor; const uint32_t *parent_carry; uint32_t *carry; uint32_t *rem;
   PCGPU_KERNEL_DEV void operator()(size_t g) const {
-    size_t lo = g * DIV_G, hi = lo + DIV_G < nchunks ? lo + DIV_G : nchunks;
-    Fp<R> zk = load_fr<R>(zp, 0), t = load_fr<R>(gcarry, g);
+    size_t lo = g * DIV_F, hi = lo + DIV_F < nchild ? lo + DIV_F : nchild;
+    if (!parent_carry) { lo = 0; hi = nchild; }
+    Fp<R> f = load_fr<R>(factor, 0), t = parent_carry ? load_fr<R>(parent_carry, g) : Fp<R>::zero();
     for (size_t c = hi; c-- > lo;) {
-      store_fr<R>(ccarry, c, t);
-      t = fp_add<R>(fp_mul<R>(t, zk), load_fr<R>(local, c));
+      store_fr<R>(carry, c, t);
+      t = fp_add<R>(fp_mul<R>(t, f), load_fr<R>(child, c));
     }
+    if (rem) store_fr<R>(rem, 0, t);
   }
 };
 
@@ -142,31 +133,40 @@ struct DivChunkWriteBody {
 };
 
 inline size_t div_scratch_words(size_t n) {
-  size_t nchunks = (n + DIV_K - 1) / DIV_K, ngroups = (nchunks + DIV_G - 1) / DIV_G;
-  return 8 * (2 * nchunks + 2 * ngroups + 4);
+  size_t cnt = (n + DIV_K - 1) / DIV_K, tot = 0;
+  for (int l = 0; l < DIV_MAX_LEVELS; l++) { tot += 2 * cnt; if (cnt <= DIV_F) break; cnt = (cnt + DIV_F - 1) / DIV_F; }
+  return 8 * (tot + DIV_MAX_LEVELS + 4);
 }
 
-// p: n coefficients, q: n-1 coefficients (n >= 1), rem: 1 element (may alias scratch), z: 1 element; all device.
+// p: n coefficients, q: n-1 coefficients (n >= 1), rem: 1 element, z: 1 element; all device.
 template <class R>
 inline int fr_div_linear(const uint32_t *p, size_t n, const uint32_t *z, uint32_t *q, uint32_t *rem,
                          uint32_t *scratch, rt::stream_t st) {
   if (n == 0) return rt::dev_memset(rem, 0, 32, st);
-  size_t nchunks = (n + DIV_K - 1) / DIV_K, ngroups = (nchunks + DIV_G - 1) / DIV_G;
-  uint32_t *zp = scratch, *local = zp + 16, *ccarry = local + 8 * nchunks, *glocal = ccarry + 8 * nchunks,
-           *gcarry = glocal + 8 * ngroups;
+  size_t cnt[DIV_MAX_LEVELS]; uint32_t *local[DIV_MAX_LEVELS], *carry[DIV_MAX_LEVELS];
+  uint32_t *zp = scratch, *cur = scratch + 8 * DIV_MAX_LEVELS;
+  int levels = 0;
+  for (size_t c = (n + DIV_K - 1) / DIV_K;; c = (c + DIV_F - 1) / DIV_F) {
+    cnt[levels] = c; local[levels] = cur; cur += 8 * c; carry[levels] = cur; cur += 8 * c;
+    levels++;
+    if (c <= DIV_F || levels == DIV_MAX_LEVELS) break;
+  }
   int rc;
-  if ((rc = rt::launch<32>(DivPowersBody<R>{z, zp}, 1, st))) return rc;
-  if ((rc = rt::launch<128>(DivChunkLocalBody<R>{p, n, z, local}, nchunks, st))) return rc;
-  if ((rc = rt::launch<64>(DivGroupLocalBody<R>{local, nchunks, zp, glocal}, ngroups, st))) return rc;
-  if ((rc = rt::launch<32>(DivGroupCarryBody<R>{glocal, ngroups, zp, gcarry, rem}, 1, st))) return rc;
-  if ((rc = rt::launch<64>(DivChunkCarryBody<R>{local, nchunks, zp, gcarry, ccarry}, ngroups, st))) return rc;
-  return rt::launch<128>(DivChunkWriteBody<R>{p, n, z, ccarry, q}, nchunks, st);
+  if ((rc = rt::launch<32>(DivPowersBody<R>{z, zp, (uint32_t)levels}, 1, st))) return rc;
+  if ((rc = rt::launch<128>(DivChunkLocalBody<R>{p, n, z, local[0]}, cnt[0], st))) return rc;
+  for (int l = 1; l < levels; l++)
+    if ((rc = rt::launch<64>(DivFoldBody<R>{local[l - 1], cnt[l - 1], zp + 8 * (l - 1), local[l]}, cnt[l], st))) return rc;
+  // root: one thread walks the top level (<= DIV_F nodes unless DIV_MAX_LEVELS was hit)
+  if ((rc = rt::launch<32>(DivCarryBody<R>{local[levels - 1], cnt[levels - 1], zp + 8 * (levels - 1), nullptr, carry[levels - 1], rem}, 1, st))) return rc;
+  for (int l = levels - 1; l >= 1; l--)
+    if ((rc = rt::launch<64>(DivCarryBody<R>{local[l - 1], cnt[l - 1], zp + 8 * (l - 1), carry[l], carry[l - 1], nullptr}, cnt[l], st))) return rc;
+  return rt::launch<128>(DivChunkWriteBody<R>{p, n, z, carry[0], q}, cnt[0], st);
 }
 
 // ---------------------------------------------------------------------------------------------
-// inner product: per-thread strided partial sums, then a single-thread fold of the partials
+// inner product: strided per-thread partial sums (coalesced), then block-level shared-memory trees
 // ---------------------------------------------------------------------------------------------
-enum { IP_THREADS = 4096 };
+enum { IP_THREADS = 65536, IP_BLOCK = 256 };
 template <class R>
 struct IpPartialBody {
   const uint32_t *a; const uint32_t *b; size_t n; uint32_t *partial;
@@ -176,23 +176,45 @@ struct IpPartialBody {
     store_fr<R>(partial, t, acc);
   }
 };
+// block b sums in[b*IP_BLOCK .. +IP_BLOCK) (count m) into out[b]
 template <class R>
-struct FrTreeAddBody {
-  uint32_t *a; uint32_t m; uint32_t half;
-  PCGPU_KERNEL_DEV void operator()(size_t i) const {
-    store_fr<R>(a, i, fp_add<R>(load_fr<R>(a, i), load_fr<R>(a, i + half)));
+struct FrBlockSumBody {
+  const uint32_t *in; size_t m; uint32_t *out;
+  PCGPU_KERNEL_DEV void operator()(size_t b, uint32_t *smem) const {
+    PCGPU_BLOCK_FOR(i, IP_BLOCK) {
+      size_t idx = b * IP_BLOCK + i;
+      Fp<R> v = idx < m ? load_fr<R>(in, idx) : Fp<R>::zero();
+#pragma unroll
+      for (int l = 0; l < 8; l++) smem[l * IP_BLOCK + i] = v.l[l];
+    }
+    PCGPU_BLOCK_SYNC();
+    for (uint32_t half = IP_BLOCK / 2; half >= 1; half >>= 1) {
+      PCGPU_BLOCK_FOR(i, half) {
+        Fp<R> x, y;
+#pragma unroll
+        for (int l = 0; l < 8; l++) { x.l[l] = smem[l * IP_BLOCK + i]; y.l[l] = smem[l * IP_BLOCK + i + half]; }
+        x = fp_add<R>(x, y);
+#pragma unroll
+        for (int l = 0; l < 8; l++) smem[l * IP_BLOCK + i] = x.l[l];
+      }
+      PCGPU_BLOCK_SYNC();
+    }
+    PCGPU_BLOCK_FOR(i, 1) {
+      Fp<R> v;
+#pragma unroll
+      for (int l = 0; l < 8; l++) v.l[l] = smem[l * IP_BLOCK];
+      store_fr<R>(out, b, v);
+    }
   }
 };
+// scratch: (IP_THREADS + IP_THREADS / IP_BLOCK) elements
 template <class R>
 inline int fr_inner_product(const uint32_t *a, const uint32_t *b, size_t n, uint32_t *out, uint32_t *scratch, rt::stream_t st) {
   int rc;
+  uint32_t *lvl1 = scratch + 8 * IP_THREADS;
   if ((rc = rt::launch<128>(IpPartialBody<R>{a, b, n, scratch}, IP_THREADS, st))) return rc;
-  for (uint32_t m = IP_THREADS; m > 1;) {
-    uint32_t half = (m + 1) / 2;
-    if ((rc = rt::launch<128>(FrTreeAddBody<R>{scratch, m, half}, m - half, st))) return rc;
-    m = half;
-  }
-  return rt::copy_d2d(out, scratch, 32, st);
+  if ((rc = rt::launch_blocks<IP_BLOCK>(FrBlockSumBody<R>{scratch, IP_THREADS, lvl1}, IP_THREADS / IP_BLOCK, IP_BLOCK * 32, st))) return rc;
+  return rt::launch_blocks<IP_BLOCK>(FrBlockSumBody<R>{lvl1, IP_THREADS / IP_BLOCK, out}, 1, IP_BLOCK * 32, st);
 }
 
 // out[c] = sum_r v[r] * M[r*cols + c]   (thread per column; coalesced across columns)

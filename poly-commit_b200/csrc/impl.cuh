@@ -378,8 +378,8 @@ int fr_ip_impl(pcgpu_ctx *ctx, const void *a, const void *b, size_t n, void *out
   rt::stream_t st = ctx->stream;
   int rc;
   bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
-  if ((rc = ctx->stage.reserve((dev ? 0 : 2 * rt::Arena::pad(n * 32 + 32)) + rt::Arena::pad(IP_THREADS * 32) + 8192))) return rc;
-  uint32_t *scratch = ctx->stage.take<uint32_t>(IP_THREADS * 8), *d_out = ctx->stage.take<uint32_t>(8);
+  if ((rc = ctx->stage.reserve((dev ? 0 : 2 * rt::Arena::pad(n * 32 + 32)) + rt::Arena::pad((IP_THREADS + IP_THREADS / IP_BLOCK + 8) * 32) + 8192))) return rc;
+  uint32_t *scratch = ctx->stage.take<uint32_t>((IP_THREADS + IP_THREADS / IP_BLOCK + 8) * 8), *d_out = ctx->stage.take<uint32_t>(8);
   const uint32_t *d_a = (const uint32_t *)a, *d_b = (const uint32_t *)b;
   if (!dev) {
     uint32_t *ta = ctx->stage.take<uint32_t>(n * 8 + 8), *tb = ctx->stage.take<uint32_t>(n * 8 + 8);
@@ -518,12 +518,12 @@ int ipa_begin_impl(pcgpu_ctx *ctx, const void *key_xy, size_t n, const void *coe
   st->curve = C::ID; st->n0 = st->n = n;
   st->d_key = nullptr; st->d_coeffs = nullptr;
   if ((rc = rt::dev_malloc(&st->d_key, n * sizeof(Affine<C>)))) return rc;
-  if ((rc = rt::dev_malloc((void **)&st->d_coeffs, (2 * n + IP_THREADS + 16) * 32))) return rc;
+  if ((rc = rt::dev_malloc((void **)&st->d_coeffs, (2 * n + IP_THREADS + IP_THREADS / IP_BLOCK + 32) * 32))) return rc;
   st->d_z = st->d_coeffs + 8 * n; st->d_scr = st->d_z + 8 * n;
   if ((rc = dev ? rt::copy_d2d(st->d_key, key_xy, n * sizeof(Affine<C>), s) : rt::copy_h2d(st->d_key, key_xy, n * sizeof(Affine<C>), s))) return rc;
   if ((rc = rt::dev_memset(st->d_coeffs, 0, n * 32, s))) return rc;
   if (n_coeffs && (rc = dev ? rt::copy_d2d(st->d_coeffs, coeffs, n_coeffs * 32, s) : rt::copy_h2d(st->d_coeffs, coeffs, n_coeffs * 32, s))) return rc;
-  uint32_t *d_pt = st->d_scr + 8 * IP_THREADS;
+  uint32_t *d_pt = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 4);
   if ((rc = rt::copy_h2d(d_pt, point, 32, s))) return rc;
   if ((rc = rt::launch<128>(FrPowersBody<R>{d_pt, st->d_z}, n, s))) return rc;
   st->view.curve = C::ID; st->view.n = n; st->view.c = 0; st->view.groups = 1; st->view.d_tables = st->d_key;
@@ -540,7 +540,7 @@ int ipa_round_lr_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_prime_xy, voi
   size_t m = st->n / 2;
   if (m == 0) return PCGPU_E_BADARG;
   const uint32_t *cl = st->d_coeffs, *cr = st->d_coeffs + 8 * m, *zl = st->d_z, *zr = st->d_z + 8 * m;
-  uint32_t *d_ip = st->d_scr + 8 * IP_THREADS + 8;
+  uint32_t *d_ip = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 6);
   uint64_t ip_m[2][4], ip_c[2][4];
   // <coeffs_r, z_l>, <coeffs_l, z_r>
   if ((rc = fr_inner_product<R>(cr, zl, m, d_ip, st->d_scr, s))) return rc;
@@ -568,7 +568,7 @@ int ipa_round_fold_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *challenge, co
   int rc;
   size_t m = st->n / 2;
   if (m == 0) return PCGPU_E_BADARG;
-  uint32_t *d_ch = st->d_scr + 8 * IP_THREADS + 16, *d_chi = d_ch + 8;
+  uint32_t *d_ch = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 8), *d_chi = d_ch + 8;
   if ((rc = rt::copy_h2d(d_ch, challenge, 32, s))) return rc;
   if ((rc = rt::copy_h2d(d_chi, challenge_inv, 32, s))) return rc;
   if ((rc = rt::launch<256>(FrAxpyBody<R>{st->d_coeffs, d_chi, st->d_coeffs + 8 * m}, m, s))) return rc;  // :691-693
