@@ -229,22 +229,31 @@ struct MsmAccumulateBody {
   const uint32_t *task_bucket;  // per task
   const uint32_t *entries;
   XYZZ<C> *partial;             // per task
-  PCGPU_KERNEL_DEV void operator()(size_t t) const {
-    if (t >= task_off[g.TB]) return;
-    uint32_t b = task_bucket[t];
-    uint32_t j = (uint32_t)t - task_off[b];
-    uint32_t lo = offsets[b] + j * g.L;
-    uint32_t end = offsets[b + 1];
-    uint32_t hi = lo + g.L < end ? lo + g.L : end;
-    XYZZ<C> acc = XYZZ<C>::inf();
-    for (uint32_t e = lo; e < hi; e++) {
-      uint32_t v = entries[e];
-      uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
-      size_t idx = (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK);
-      Affine<C> a = load_affine<C>(tables + idx);
-      xyzz_madd<C>(acc, a, (v & ENTRY_SIGN) != 0);
+  uint32_t *queue;              // global task counter (zeroed before the launch)
+  // Persistent: every warp keeps claiming 32 consecutive tasks until the queue is empty.  A bucket with cnt entries
+  // and T = ceil(cnt / L) tasks is split EVENLY (task j covers [cnt*j/T, cnt*(j+1)/T)), so the lanes of a warp --
+  // neighbouring tasks, mostly of the same bucket -- run chains of equal length.
+  PCGPU_KERNEL_DEV void operator()(size_t) const {
+    const uint32_t total = task_off[g.TB];
+    for (;;) {
+      uint32_t t = rt::next_task(queue);
+      if (t - (t & 31u) >= total) break;   // the whole warp is past the end
+      if (t >= total) continue;
+      uint32_t b = task_bucket[t];
+      uint32_t t0 = task_off[b], T = task_off[b + 1] - t0, j = t - t0;
+      uint32_t base = offsets[b], cnt = offsets[b + 1] - base;
+      uint32_t lo = base + (uint32_t)(((uint64_t)cnt * j) / T);
+      uint32_t hi = base + (uint32_t)(((uint64_t)cnt * (j + 1)) / T);
+      XYZZ<C> acc = XYZZ<C>::inf();
+      for (uint32_t e = lo; e < hi; e++) {
+        uint32_t v = entries[e];
+        uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
+        size_t idx = (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK);
+        Affine<C> a = load_affine<C>(tables + idx);
+        xyzz_madd<C>(acc, a, (v & ENTRY_SIGN) != 0);
+      }
+      store_xyzz<C>(partial + t, acc);
     }
-    store_xyzz<C>(partial + t, acc);
   }
 };
 
@@ -323,7 +332,8 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
   g.S = (g.W + g.G - 1) / g.G;
   g.NB = 1u << (c - 1);
   g.TB = g.S * g.NB;
-  g.L = 64;
+  g.L = 32;
+  if (const char *e = getenv("PCGPU_MSM_L")) { int v = atoi(e); if (v >= 4 && v <= 4096) g.L = (uint32_t)v; }  // tuning knob
   g.seg_len = 16;
   g.nseg = (g.NB + g.seg_len - 1) / g.seg_len;
   g.scalar_bits = scalar_bits; g.scalars_mont = mont ? 1 : 0;
@@ -365,7 +375,7 @@ inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_
   uint32_t *task_bucket = arena.take<uint32_t>(max_tasks);
   uint32_t *entries = arena.take<uint32_t>(max_entries + 1);
   uint32_t *scratch = arena.take<uint32_t>(scan_scratch_words(g.TB + 1));
-  uint32_t *err = arena.take<uint32_t>(16);
+  uint32_t *err = arena.take<uint32_t>(16);  // err[0]: scalar out of range; err[8]: accumulate task queue
   XYZZ<C> *partial = arena.take<XYZZ<C>>(max_tasks);
   XYZZ<C> *buckets = arena.take<XYZZ<C>>(g.TB);
   XYZZ<C> *planes = arena.take<XYZZ<C>>((size_t)g.S * g.c * g.nseg);
@@ -396,7 +406,7 @@ inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_
   prof.end(3, st);
 
   prof.begin(4, st);
-  if ((rc = rt::launch<128>(MsmAccumulateBody<C>{tables, g, offsets, task_off, task_bucket, entries, partial}, max_tasks, st))) return rc;
+  if ((rc = rt::launch_persistent<128>(MsmAccumulateBody<C>{tables, g, offsets, task_off, task_bucket, entries, partial, err + 8}, st))) return rc;
   prof.end(4, st);
 
   prof.begin(5, st);

@@ -59,6 +59,10 @@ inline int launch(const Body &body, size_t n, stream_t) {
 template <class T> inline T atomic_add(T *p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomic_or(T *p, T v) { T o = *p; *p = o | v; return o; }
 #define PCGPU_KERNEL_DEV inline
+// Persistent bodies pull work from a global counter: next_task() returns this lane's next task index.
+inline uint32_t next_task(uint32_t *counter) { return atomic_add(counter, 1u); }
+template <int BLOCK, class Body>
+inline int launch_persistent(const Body &body, stream_t) { body(0); return OK; }
 // Block-cooperative bodies: body(block_id, shared_memory).  Work inside the body is written as
 // PCGPU_BLOCK_FOR loops separated by PCGPU_BLOCK_SYNC(); anything that must survive a sync lives in shared memory.
 #define PCGPU_BLOCK_FOR(i, n) for (uint32_t i = 0; i < (uint32_t)(n); i++)
@@ -128,6 +132,33 @@ inline int launch_blocks(const Body &body, size_t nblocks, size_t smem_bytes, st
     if (e != cudaSuccess) return map_cuda(e);
   }
   run_block_kernel<Body, BLOCK><<<(unsigned)nblocks, BLOCK, smem_bytes, s>>>(body);
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  return last_error();
+}
+// Persistent kernels: one resident wave of threads (SM count x occupancy), each warp repeatedly claims 32
+// consecutive tasks from a global counter -- no wave quantisation, no tail of half-empty blocks.
+__device__ __forceinline__ uint32_t next_task(uint32_t *counter) {
+  uint32_t lane = threadIdx.x & 31, base = 0;
+  if (lane == 0) base = atomicAdd(counter, 32u);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  return base + lane;
+}
+template <class Body, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) run_persistent_kernel(const Body body) {
+  body((size_t)blockIdx.x * BLOCK + threadIdx.x);
+}
+template <int BLOCK, class Body>
+inline int launch_persistent(const Body &body, stream_t s) {
+  static int grid = 0;  // per kernel instantiation
+  if (grid == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_persistent_kernel<Body, BLOCK>, BLOCK, 0);
+    if (e != cudaSuccess) return map_cuda(e);
+    grid = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  run_persistent_kernel<Body, BLOCK><<<grid, BLOCK, 0, s>>>(body);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   return last_error();
 }
