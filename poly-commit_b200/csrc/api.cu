@@ -54,6 +54,7 @@ extern "C" void pcgpu_destroy(pcgpu_ctx *ctx) {
 #endif
   ctx->prof.destroy();
   for (NttPlan &p : ctx->ntt_plans) rt::dev_free(p.base);
+  for (int k = 0; k < 3; k++) rt::dev_free(ctx->d_pow2[k]);
   ctx->msm_arena.release();
   ctx->stage.release();
   rt::dev_free(ctx->d_slots);

@@ -71,6 +71,7 @@ struct pcgpu_ctx {
   rt::Arena msm_arena, stage;
   void *d_slots;    // 8 XYZZ result slots + 1 affine + err word, generously sized
   Prof prof;
+  uint32_t *d_pow2[3] = {nullptr, nullptr, nullptr};  // fp_inv_gcd tables (Fq), per curve
   std::vector<NttPlan> ntt_plans;  // twiddle tables, cached per (curve, logn, direction)
   std::mutex mu;
 };
@@ -150,8 +151,25 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
   if (srs->groups > 1 && n >= SRS_PRECOMPUTE_MIN_N) { c = srs->c; groups = srs->groups; }
   else { c = msm_pick_c(n); groups = 1; }
   MsmGeom g = msm_geometry(n, c, groups, C::Fr::BITS, mont, srs->n, base_offset);
+  int rc;
+  // batched-affine rounds while buckets hold >= 64 points and a round still gives every thread >= 16 additions
+  {
+    size_t Tmax = 0;
+    if ((rc = rt::resident_threads<128, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
+    size_t entries = (size_t)g.n * g.W, avg = entries / g.TB;
+    uint32_t R = 0;
+    while (R < 8 && (avg >> R) >= 64 && (entries >> (R + 1)) >= 16 * Tmax) R++;
+    if (const char *e = getenv("PCGPU_MSM_AFFINE_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= 12) R = (uint32_t)v; }
+    g.affine_rounds = R;
+  }
+  if (g.affine_rounds && !ctx->d_pow2[C::ID]) {
+    using QP = typename C::Fq;
+    if ((rc = rt::dev_malloc((void **)&ctx->d_pow2[C::ID], (size_t)(64 * QP::N + 1) * QP::N * 4))) return rc;
+    if ((rc = rt::launch<32>(Pow2TableBody<QP>{ctx->d_pow2[C::ID]}, 1, st))) return rc;
+  }
   const XYZZ<C> *d_planes = nullptr; size_t stride = 0; uint32_t *d_err = nullptr;
-  int rc = msm_run<C>((const Affine<C> *)srs->d_tables, g, d_scalars, ctx->msm_arena, &d_planes, &stride, &d_err, st, ctx->prof);
+  rc = msm_run<C>((const Affine<C> *)srs->d_tables, g, d_scalars, ctx->msm_arena, &d_planes, &stride, &d_err, st, ctx->prof,
+                  ctx->d_pow2[C::ID]);
   if (rc) return rc;
   size_t np = (size_t)g.S * g.c;
   std::vector<host::HXYZZ<C>> planes(np);

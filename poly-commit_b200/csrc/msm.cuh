@@ -42,6 +42,7 @@ struct MsmGeom {
   uint32_t scalars_mont; // 1: scalars are Montgomery Fr (convert in the digit pass)
   uint64_t table_stride; // points per table group
   uint64_t base_off;     // first base used inside each group
+  uint32_t affine_rounds; // batched-affine pairwise rounds before the XYZZ task kernel
 };
 
 enum : uint32_t { ENTRY_SIGN = 0x80000000u, ENTRY_GROUP_SHIFT = 26, ENTRY_IDX_MASK = (1u << 26) - 1 };
@@ -230,6 +231,7 @@ struct MsmAccumulateBody {
   const uint32_t *entries;
   XYZZ<C> *partial;             // per task
   uint32_t *queue;              // global task counter (zeroed before the launch)
+  const Affine<C> *pts;         // non-null after batched-affine rounds: entry e IS the point pts[e]
   // Persistent: every warp keeps claiming 32 consecutive tasks until the queue is empty.  A bucket with cnt entries
   // and T = ceil(cnt / L) tasks is split EVENLY (task j covers [cnt*j/T, cnt*(j+1)/T)), so the lanes of a warp --
   // neighbouring tasks, mostly of the same bucket -- run chains of equal length.
@@ -245,12 +247,16 @@ struct MsmAccumulateBody {
       uint32_t lo = base + (uint32_t)(((uint64_t)cnt * j) / T);
       uint32_t hi = base + (uint32_t)(((uint64_t)cnt * (j + 1)) / T);
       XYZZ<C> acc = XYZZ<C>::inf();
-      for (uint32_t e = lo; e < hi; e++) {
-        uint32_t v = entries[e];
-        uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
-        size_t idx = (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK);
-        Affine<C> a = load_affine<C>(tables + idx);
-        xyzz_madd<C>(acc, a, (v & ENTRY_SIGN) != 0);
+      if (pts) {
+        for (uint32_t e = lo; e < hi; e++) { Affine<C> a = load_affine<C>(pts + e); xyzz_madd<C>(acc, a, false); }
+      } else {
+        for (uint32_t e = lo; e < hi; e++) {
+          uint32_t v = entries[e];
+          uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
+          size_t idx = (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK);
+          Affine<C> a = load_affine<C>(tables + idx);
+          xyzz_madd<C>(acc, a, (v & ENTRY_SIGN) != 0);
+        }
       }
       store_xyzz<C>(partial + t, acc);
     }
@@ -303,6 +309,10 @@ struct MsmTreeAddBody {
   }
 };
 
+}  // namespace pcgpu
+#include "msm_affine.cuh"
+namespace pcgpu {
+
 // ---------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------
@@ -338,6 +348,7 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
   g.nseg = (g.NB + g.seg_len - 1) / g.seg_len;
   g.scalar_bits = scalar_bits; g.scalars_mont = mont ? 1 : 0;
   g.table_stride = table_stride; g.base_off = base_off;
+  g.affine_rounds = 0;
   return g;
 }
 
@@ -354,6 +365,13 @@ inline size_t msm_workspace_bytes(const MsmGeom &g) {
   b += rt::Arena::pad(max_tasks * sizeof(XYZZ<C>));
   b += rt::Arena::pad((size_t)g.TB * sizeof(XYZZ<C>));
   b += rt::Arena::pad((size_t)g.S * g.c * g.nseg * sizeof(XYZZ<C>));
+  if (g.affine_rounds) {
+    size_t bound0 = max_entries / 2 + g.TB + 1, bound1 = bound0 / 2 + g.TB + 1;
+    b += 3 * rt::Arena::pad((g.TB + 2) * sizeof(uint32_t));
+    b += rt::Arena::pad(bound0 * sizeof(uint32_t));
+    b += rt::Arena::pad((bound0 + (1u << 20)) * sizeof(Fp<typename C::Fq>));
+    b += rt::Arena::pad(bound0 * sizeof(Affine<C>)) + rt::Arena::pad(bound1 * sizeof(Affine<C>));
+  }
   return b + 4096;
 }
 
@@ -362,7 +380,8 @@ inline size_t msm_workspace_bytes(const MsmGeom &g) {
 // *d_err at a device word that is non-zero when a scalar was out of range.  `prof` brackets stages with events.
 template <class C, class Prof>
 inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_scalars, rt::Arena &arena,
-                   const XYZZ<C> **d_planes, size_t *plane_stride, uint32_t **d_err_out, rt::stream_t st, Prof &prof) {
+                   const XYZZ<C> **d_planes, size_t *plane_stride, uint32_t **d_err_out, rt::stream_t st, Prof &prof,
+                   const uint32_t *pow2 = nullptr) {
   int rc;
   if ((rc = arena.reserve(msm_workspace_bytes<C>(g)))) return rc;
   size_t max_entries = (size_t)g.n * g.W;
@@ -399,6 +418,41 @@ inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_
   if ((rc = rt::launch<256>(MsmScatterBody<C>{d_scalars, g, cursor, entries}, g.n, st))) return rc;
   prof.end(2, st);
 
+  // ---- batched-affine pairwise rounds (msm_affine.cuh): halve every bucket g.affine_rounds times ----
+  const Affine<C> *pts = nullptr;
+  if (g.affine_rounds && pow2) {
+    using QF = Fp<typename C::Fq>;
+    size_t bound0 = max_entries / 2 + g.TB + 1, bound1 = bound0 / 2 + g.TB + 1;
+    uint32_t *offA = arena.take<uint32_t>(g.TB + 2), *offB = arena.take<uint32_t>(g.TB + 2), *cnt = arena.take<uint32_t>(g.TB + 2);
+    uint32_t *src = arena.take<uint32_t>(bound0);
+    uint32_t *prefix = (uint32_t *)arena.take<QF>(bound0 + (1u << 20));
+    Affine<C> *ptsA = arena.take<Affine<C>>(bound0), *ptsB = arena.take<Affine<C>>(bound1);
+    if (!offA || !offB || !cnt || !src || !prefix || !ptsA || !ptsB) return rt::E_OOM;
+    size_t Tmax = 0;
+    if ((rc = rt::resident_threads<128, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
+    if (Tmax > (1u << 20)) Tmax = 1u << 20;
+    prof.begin(11, st);
+    const uint32_t *off_in = offsets;
+    size_t bound = max_entries;
+    for (uint32_t r = 0; r < g.affine_rounds; r++) {
+      uint32_t *off_out = (r & 1) ? offB : offA;
+      Affine<C> *out = (r & 1) ? ptsB : ptsA;
+      const Affine<C> *in = (r & 1) ? ptsA : ptsB;
+      bound = bound / 2 + g.TB + 1;
+      if ((rc = rt::launch<256>(PairCountBody{off_in, cnt}, g.TB, st))) return rc;
+      if ((rc = exclusive_scan_u32(cnt, g.TB, off_out, scratch, st))) return rc;
+      if ((rc = rt::launch<256>(PairPlanBody{off_in, off_out, g.TB, src}, bound, st))) return rc;
+      uint32_t T = (uint32_t)Tmax;
+      if (r == 0) rc = rt::launch<128>(MsmAffinePairBody<C, true>{tables, g, entries, nullptr, src, off_out, T, prefix, pow2, out}, T, st);
+      else rc = rt::launch<128>(MsmAffinePairBody<C, false>{tables, g, entries, in, src, off_out, T, prefix, pow2, out}, T, st);
+      if (rc) return rc;
+      off_in = off_out;
+      pts = out;
+    }
+    prof.end(11, st);
+    offsets = const_cast<uint32_t *>(off_in);
+  }
+
   prof.begin(3, st);
   if ((rc = rt::launch<256>(TaskCountBody{offsets, g.L, ntasks}, g.TB, st))) return rc;
   if ((rc = exclusive_scan_u32(ntasks, g.TB, task_off, scratch, st))) return rc;
@@ -406,7 +460,7 @@ inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_
   prof.end(3, st);
 
   prof.begin(4, st);
-  if ((rc = rt::launch_persistent<128>(MsmAccumulateBody<C>{tables, g, offsets, task_off, task_bucket, entries, partial, err + 8}, st))) return rc;
+  if ((rc = rt::launch_persistent<128>(MsmAccumulateBody<C>{tables, g, offsets, task_off, task_bucket, entries, partial, err + 8, pts}, st))) return rc;
   prof.end(4, st);
 
   prof.begin(5, st);

@@ -63,6 +63,8 @@ template <class T> inline T atomic_or(T *p, T v) { T o = *p; *p = o | v; return 
 inline uint32_t next_task(uint32_t *counter) { return atomic_add(counter, 1u); }
 template <int BLOCK, class Body>
 inline int launch_persistent(const Body &body, stream_t) { body(0); return OK; }
+// threads of one resident wave of `Body` (host emulation: a small number so multi-iteration paths are exercised)
+template <int BLOCK, class Body> inline int resident_threads(size_t *out) { *out = 48; return OK; }
 // Block-cooperative bodies: body(block_id, shared_memory).  Work inside the body is written as
 // PCGPU_BLOCK_FOR loops separated by PCGPU_BLOCK_SYNC(); anything that must survive a sync lives in shared memory.
 #define PCGPU_BLOCK_FOR(i, n) for (uint32_t i = 0; i < (uint32_t)(n); i++)
@@ -146,6 +148,20 @@ __device__ __forceinline__ uint32_t next_task(uint32_t *counter) {
 template <class Body, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) run_persistent_kernel(const Body body) {
   body((size_t)blockIdx.x * BLOCK + threadIdx.x);
+}
+template <int BLOCK, class Body>
+inline int resident_threads(size_t *out) {
+  static size_t cached = 0;
+  if (!cached) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_kernel<Body, BLOCK>, BLOCK, 0);
+    if (e != cudaSuccess) return map_cuda(e);
+    cached = (size_t)sms * (per_sm > 0 ? per_sm : 1) * BLOCK;
+  }
+  *out = cached;
+  return OK;
 }
 template <int BLOCK, class Body>
 inline int launch_persistent(const Body &body, stream_t s) {

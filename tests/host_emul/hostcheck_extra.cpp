@@ -2,8 +2,16 @@
 // carry flags) so tests can compare the production limb schedule against the 64-bit reference
 // multiplier and the Python big-integer oracle.
 #include <stddef.h>
+#include <vector>
 #include "../../poly-commit_b200/csrc/ec.cuh"
 using namespace pcgpu;
+
+template <class P>
+static const uint32_t *pow2_table() {
+  static std::vector<uint32_t> t;
+  if (t.empty()) { t.resize((64 * P::N + 1) * P::N); Pow2TableBody<P>{t.data()}(0); }
+  return t.data();
+}
 
 template <class P>
 static void mul_many(const uint32_t *a, const uint32_t *b, uint32_t *out, size_t n, int which) {
@@ -17,6 +25,7 @@ static void mul_many(const uint32_t *a, const uint32_t *b, uint32_t *out, size_t
       case 3: r = fp_sub<P>(x, y); break;
       case 4: r = fp_neg<P>(x); break;
       case 5: r = fp_inv<P>(x); break;
+      case 8: r = fp_inv_gcd<P>(x, pow2_table<P>()); break;
       case 6: if constexpr (mont_mul2_supported<P>()) r = mont_mul2<P>(x, y, y, fp_neg<P>(x)); else r = Fp<P>::zero(); break;  // x*y + y*(-x) = 0
       case 7: if constexpr (mont_mul2_supported<P>()) r = mont_mul2<P>(x, y, fp_add<P>(x, y), fp_sub<P>(y, x));
               else r = fp_add<P>(mont_mul<P>(x, y), mont_mul<P>(fp_add<P>(x, y), fp_sub<P>(y, x)));

@@ -59,6 +59,13 @@ def test_field_schedule_vs_bigint(hostcheck_path, cname, which, fid):
     lib.hostcheck_field_op(fid, 5, A[:k].ctypes.data_as(vp), B[:k].ctypes.data_as(vp), out.ctypes.data_as(vp), ctypes.c_size_t(k))
     exp = _tol([(pow(a * Rinv % mod, -1, mod) * R % mod) if a else 0 for a in va[:k]], n64)
     assert (out == exp).all()
+    # binary-GCD (almost Montgomery) inverse == Fermat inverse, on edge values and random ones
+    k2 = 120
+    sel = list(range(len(edge))) + list(range(len(va) - k2, len(va)))
+    A2 = np.ascontiguousarray(A[sel]); out = np.zeros_like(A2)
+    lib.hostcheck_field_op(fid, 8, A2.ctypes.data_as(vp), A2.ctypes.data_as(vp), out.ctypes.data_as(vp), ctypes.c_size_t(len(sel)))
+    exp = _tol([(pow(va[i] * Rinv % mod, -1, mod) * R % mod) if va[i] else 0 for i in sel], n64)
+    assert (out == exp).all()
 
 
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
@@ -113,6 +120,34 @@ def test_msm_edge_scalars(eng, pc):
     with pytest.raises(pc.PcgpuError) as ei:
         eng.msm(srs, np.concatenate([sc, sc]))
     assert ei.value.code == -4
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 3, 5])
+def test_msm_batched_affine_rounds(eng, pc, rounds, monkeypatch):
+    """msm_affine.cuh: forced batched-affine pairwise rounds (Montgomery batch inversion with the binary-GCD inverse)
+    must give the same point, including the exceptional pairs: P + P, P + (-P), identity operands, odd bucket sizes."""
+    monkeypatch.setenv("PCGPU_MSM_AFFINE_ROUNDS", str(rounds))
+    for cname, n in (("bls12_381", 300), ("bn254", 77), ("pallas", 130)):
+        C = pyref.Curve(cname)
+        pts = util.random_points(cname, n, seed=90 + rounds)
+        neg = C.points_to_limbs([C.neg(p) for p in C.points_from_limbs(pts[:3])])[0]
+        bases = np.concatenate([pts, pts[:5], neg])                 # repeated and negated bases
+        inf = np.zeros(bases.shape[0], dtype=np.uint8); inf[7] = 1; inf[8] = 1
+        sc = util.rand_fr(cname, bases.shape[0], seed=91 + rounds, mont=False)
+        sc[n:n + 5] = sc[:5]                                        # same scalar on the repeated base -> P + P in a bucket
+        sc[n + 5:] = sc[:3]                                         # same scalar on the negated base -> P + (-P)
+        sc[20:40] = sc[20]                                          # a crowded bucket in every window
+        srs = eng.srs_register(C.id, bases, inf=inf)
+        got = eng.msm(srs, sc)
+        exp = orc.msm(C.id, bases, sc, inf=inf)
+        assert got[1] == exp[1] and (got[0] == exp[0]).all(), (cname, rounds)
+    # window-folded tables + rounds
+    C = pyref.Curve("bn254")
+    bases = util.random_points("bn254", 4200, seed=95)
+    sc = util.rand_fr("bn254", 4200, seed=96, mont=False)
+    srs = eng.srs_register(C.id, bases, flags=pc.SRS_PRECOMPUTE)
+    got = eng.msm(srs, sc); exp = orc.msm(C.id, bases, sc)
+    assert (got[0] == exp[0]).all()
 
 
 def test_msm_infinity_bases(eng):
