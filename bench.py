@@ -313,6 +313,7 @@ def main():
     acc_ms, acc_cnt = eng.profile_get(4)
     stage_ms = {name: eng.profile_get(s)[0] / max(prof_steps, 1) for s, name in
                 enumerate(["digits_count", "scan", "scatter", "tasks", "bucket_accumulate", "bucket_reduce", "final_host", "fr_division"])}
+    stage_ms["affine_pair_rounds"] = eng.profile_get(11)[0] / max(prof_steps, 1)
     eng.profile_enable(False)
 
     if rank != 0:

@@ -419,6 +419,30 @@ PCGPU_DEV uint32_t funnel_l1(uint32_t lo, uint32_t hi) {
 #endif
 }
 
+PCGPU_DEV uint32_t ctz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return (uint32_t)(__ffs((int)x) - 1);
+#else
+  return (uint32_t)__builtin_ctz(x);
+#endif
+}
+PCGPU_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {   // (hi:lo >> sh) low word, 0 < sh < 32
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return (lo >> sh) | (hi << (32 - sh));
+#endif
+}
+PCGPU_DEV uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) {   // (hi:lo << sh) high word, 0 < sh < 32
+#ifdef __CUDA_ARCH__
+  return __funnelshift_l(lo, hi, sh);
+#else
+  return (hi << sh) | (lo >> (32 - sh));
+#endif
+}
+
+// Both u and v are kept odd: every iteration is one subtraction followed by the removal of ALL trailing zero bits
+// (several Kaliski halving steps at once), about 0.7 * bits(p) iterations.
 template <class P>
 PCGPU_DEV Fp<P> fp_inv_gcd(const Fp<P> &a, const uint32_t *pow2) {
   constexpr int N = P::N;
@@ -428,48 +452,61 @@ PCGPU_DEV Fp<P> fp_inv_gcd(const Fp<P> &a, const uint32_t *pow2) {
   for (int i = 0; i < N; i++) { u[i] = P::mod(i); v[i] = a.l[i]; r[i] = 0; s[i] = 0; }
   s[0] = 1;
   uint32_t k = 0;
+  // make v odd (r = 0, so its doublings are no-ops)
+  while (!(v[0] & 1u)) {
+    uint32_t sh = v[0] ? ctz32(v[0]) : 31u;
+    if (sh > 31u) sh = 31u;
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) v[i] = funnel_r(v[i], v[i + 1], sh);
+    v[N - 1] >>= sh;
+    k += sh;
+  }
   for (;;) {
-    uint32_t nz = 0;
+    // gt = u > v  (borrow of v - u);  eq when u == v
+    uint32_t t = sub_cc(v[0], u[0]), diff = t;
 #pragma unroll
-    for (int i = 0; i < N; i++) nz |= v[i];
-    if (!nz) break;
-    // gt = u > v  (borrow of v - u)
-    uint32_t t = sub_cc(v[0], u[0]);
-#pragma unroll
-    for (int i = 1; i < N; i++) t = subc_cc(v[i], u[i]);
-    (void)t;
+    for (int i = 1; i < N; i++) { t = subc_cc(v[i], u[i]); diff |= t; }
     const bool gt = subc(0u, 0u) != 0;
-    const bool ue = !(u[0] & 1u), ve = !(v[0] & 1u);
-    const bool mod_u = ue || (!ve && gt);          // halve u (A) or u = (u - v)/2 (C); otherwise the same on v (B, D)
-    const uint32_t oddm = (!ue && !ve) ? 0xffffffffu : 0u;
-    uint32_t X[N], Y[N], Pp[N], Qq[N];
+    if (diff == 0) {                         // u == v == 1: last step (v = 0; s += r; r *= 2)
+      r[0] = add_cc(r[0], r[0]);             // only r is used afterwards: r <- 2r
+#pragma unroll
+      for (int i = 1; i < N - 1; i++) r[i] = addc_cc(r[i], r[i]);
+      r[N - 1] = addc(r[N - 1], r[N - 1]);
+      k++;
+      break;
+    }
+    uint32_t X[N], Y[N], Pp[N], Qq[N];       // X = the larger of (u, v); (Pp, Qq) = (r, s) in the matching order
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      X[i] = mod_u ? u[i] : v[i]; Y[i] = mod_u ? v[i] : u[i];
-      Pp[i] = mod_u ? r[i] : s[i]; Qq[i] = mod_u ? s[i] : r[i];
+      X[i] = gt ? u[i] : v[i]; Y[i] = gt ? v[i] : u[i];
+      Pp[i] = gt ? r[i] : s[i]; Qq[i] = gt ? s[i] : r[i];
     }
-    // X = (X - (odd ? Y : 0)) >> 1
-    X[0] = sub_cc(X[0], Y[0] & oddm);
+    X[0] = sub_cc(X[0], Y[0]);
 #pragma unroll
-    for (int i = 1; i < N - 1; i++) X[i] = subc_cc(X[i], Y[i] & oddm);
-    X[N - 1] = subc(X[N - 1], Y[N - 1] & oddm);
+    for (int i = 1; i < N - 1; i++) X[i] = subc_cc(X[i], Y[i]);
+    X[N - 1] = subc(X[N - 1], Y[N - 1]);
+    Pp[0] = add_cc(Pp[0], Qq[0]);
 #pragma unroll
-    for (int i = 0; i < N - 1; i++) X[i] = funnel_r1(X[i], X[i + 1]);
-    X[N - 1] >>= 1;
-    // P += (odd ? Q : 0);  Q <<= 1        (r, s stay below 2p < 2^(32N))
-    Pp[0] = add_cc(Pp[0], Qq[0] & oddm);
+    for (int i = 1; i < N - 1; i++) Pp[i] = addc_cc(Pp[i], Qq[i]);
+    Pp[N - 1] = addc(Pp[N - 1], Qq[N - 1]);
+    // X >>= tz, Qq <<= tz, k += tz   (X is even and non-zero)
+    do {
+      uint32_t sh = X[0] ? ctz32(X[0]) : 31u;
+      if (sh > 31u) sh = 31u;
+      if (sh == 0) break;
 #pragma unroll
-    for (int i = 1; i < N - 1; i++) Pp[i] = addc_cc(Pp[i], Qq[i] & oddm);
-    Pp[N - 1] = addc(Pp[N - 1], Qq[N - 1] & oddm);
+      for (int i = 0; i < N - 1; i++) X[i] = funnel_r(X[i], X[i + 1], sh);
+      X[N - 1] >>= sh;
 #pragma unroll
-    for (int i = N - 1; i > 0; i--) Qq[i] = funnel_l1(Qq[i - 1], Qq[i]);
-    Qq[0] <<= 1;
+      for (int i = N - 1; i > 0; i--) Qq[i] = funnel_l(Qq[i - 1], Qq[i], sh);
+      Qq[0] <<= sh;
+      k += sh;
+    } while (!(X[0] & 1u));
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      u[i] = mod_u ? X[i] : u[i]; v[i] = mod_u ? v[i] : X[i];
-      r[i] = mod_u ? Pp[i] : Qq[i]; s[i] = mod_u ? Qq[i] : Pp[i];
+      u[i] = gt ? X[i] : u[i]; v[i] = gt ? v[i] : X[i];
+      r[i] = gt ? Pp[i] : Qq[i]; s[i] = gt ? Qq[i] : Pp[i];
     }
-    k++;
   }
   // x = p - (r mod p) = a^-1 * 2^k
   fp_reduce_once<P>(r);
@@ -478,9 +515,9 @@ PCGPU_DEV Fp<P> fp_inv_gcd(const Fp<P> &a, const uint32_t *pow2) {
 #pragma unroll
   for (int i = 1; i < N - 1; i++) x.l[i] = subc_cc(P::mod(i), r[i]);
   x.l[N - 1] = subc(P::mod(N - 1), r[N - 1]);
-  fp_reduce_once<P>(x.l);  // r == 0 cannot occur for a != 0, but keep the value canonical
+  fp_reduce_once<P>(x.l);
   Fp<P> corr;
-  const uint32_t idx = 2u * 32u * N - k;   // e = 2 * (32N) - k
+  const uint32_t idx = 2u * 32u * N - k;   // multiply by 2^(2*32N - k) * R  (Montgomery product removes one R)
 #pragma unroll
   for (int i = 0; i < N; i++) corr.l[i] = pow2[(size_t)idx * N + i];
   return fp_mul<P>(x, corr);
