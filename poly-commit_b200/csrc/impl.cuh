@@ -158,7 +158,7 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
     if ((rc = rt::resident_threads<128, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
     size_t entries = (size_t)g.n * g.W, avg = entries / g.TB;
     uint32_t R = 0;
-    while (R < 8 && (avg >> R) >= 64 && (entries >> (R + 1)) >= 16 * Tmax) R++;
+    while (R < 8 && (avg >> R) >= 128 && (entries >> (R + 1)) >= 16 * Tmax) R++;
     if (const char *e = getenv("PCGPU_MSM_AFFINE_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= 12) R = (uint32_t)v; }
     g.affine_rounds = R;
   }
