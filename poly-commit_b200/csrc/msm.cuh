@@ -431,6 +431,7 @@ inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_
     size_t Tmax = 0;
     if ((rc = rt::resident_threads<128, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
     if (Tmax > (1u << 20)) Tmax = 1u << 20;
+    if (const char *e = getenv("PCGPU_MSM_AFFINE_TDIV")) { int v = atoi(e); if (v >= 1 && v <= 16) Tmax = (Tmax / v + 127) / 128 * 128; }  // tuning knob
     prof.begin(11, st);
     const uint32_t *off_in = offsets;
     size_t bound = max_entries;

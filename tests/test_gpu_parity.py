@@ -227,3 +227,40 @@ def test_cfg3_ipa_open_2p18_pallas(eng, pc):
     assert C.fr_from_limbs(got["c"], True)[0] == c_exp
     fk = orc.msm(C.id, key, C.fr_to_limbs(s_ch, False))
     assert (got["final_comm_key"] == fk[0]).all()
+
+
+def test_cpp_host_mirror(tmp_path):
+    """poly-commit_b200/host/pcgpu.hpp (C++ mirror of kzg10::KZG10::{commit, open}, Powers, Error) driven by the compiled
+    tests/cpp/host_mirror_test -- the shape of kzg10/mod.rs:546-575 end_to_end_test_template -- against the oracle."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "host_mirror_test")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "tests", "cpp")])
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    n = 5000
+    powers = util.synthetic_srs(cname, 512, seed=3)
+    powers = np.concatenate([powers] + [util.random_points(cname, n - 512, seed=4)])
+    gammas = util.random_points(cname, 6, seed=5)
+    coeffs = util.rand_fr(cname, n - 7, seed=6, mont=True)
+    blind = util.rand_fr(cname, 3, seed=7, mont=True)
+    z = util.rand_fr(cname, 1, seed=8, mont=True)[0]
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(np.array([C.id, n, n - 7, 6, 3], dtype=np.uint32).tobytes())
+        for a in (powers, coeffs, z, gammas, blind):
+            f.write(np.ascontiguousarray(a, dtype=np.uint64).tobytes())
+    subprocess.check_call([exe, str(fin), str(fout)])
+    raw = open(fout, "rb").read()
+    pts = np.frombuffer(raw[: 4 * 96], dtype=np.uint64).reshape(4, 12)
+    rv = np.frombuffer(raw[4 * 96: 4 * 96 + 32], dtype=np.uint64)
+    kind = int(np.frombuffer(raw[4 * 96 + 32:], dtype=np.uint32)[0])
+    rc, c0, _ = orc.kzg_commit(C.id, powers, coeffs)
+    rc, w0, _, _ = orc.kzg_open(C.id, powers, coeffs, z)
+    rc, c1, _ = orc.kzg_commit(C.id, powers, coeffs, gammas, blind)
+    rc, w1, _, erv = orc.kzg_open(C.id, powers, coeffs, z, gammas, blind)
+    assert (pts[0] == c0).all() and (pts[1] == w0).all() and (pts[2] == c1).all() and (pts[3] == w1).all()
+    assert (rv == erv).all()
+    assert kind == 0  # Error::TooManyCoefficients
