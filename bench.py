@@ -322,6 +322,13 @@ def main():
     value = polys / (ms_dev / 1e3)
     e2e = polys / (ms_host / 1e3)
     peak, peak_src = measured_peaks()
+    # compute roofline that actually binds the MSM: wide integer multiply-adds per second (measured live on this GPU)
+    imad_peak = eng.measure_imad_peak()
+    # multiply count of one 2^log_deg MSM: entries = n * W windows, 3 affine rounds at 6.2 modmuls, the rest XYZZ at 9.5,
+    # 288 wide multiplies per 12-limb Montgomery product
+    msm_entries = n * 16
+    wide_per_msm = (msm_entries * (7.0 / 8.0) * 6.2 + msm_entries * (1.0 / 8.0) * 9.5) * 288
+    msm_kernel_ms = (stage_ms["affine_pair_rounds"] + stage_ms["bucket_accumulate"]) / 2
     achieved = (n * ALGO_BYTES_PER_SCALAR_MULT / 1e9) / (acc_ms / max(acc_cnt, 1) / 1e3) if acc_cnt else None
     line = {
         "metric": "MarlinKZG10/BLS12-381 commit+open polys/s at deg 2^20", "value": value, "unit": "polys/s",
@@ -340,6 +347,10 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "run_kernel<MsmAccumulateBody<Bls12381>>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC_BYTES.get(log_deg), "peak_source": peak_src,
                      "launch_ms": acc_ms / max(acc_cnt, 1),
+                     "compute_roofline": {"bound": "int32 multiply pipe (IMAD.WIDE.U32)", "peak_wide_mul_per_s": imad_peak,
+                                          "achieved_wide_mul_per_s": wide_per_msm / (msm_kernel_ms / 1e3) if msm_kernel_ms else None,
+                                          "frac": (wide_per_msm / (msm_kernel_ms / 1e3) / imad_peak) if (msm_kernel_ms and imad_peak) else None,
+                                          "kernels": "MsmAffinePairBody x3 rounds + MsmAccumulateBody, per MSM"},
                      "note": "MSM is INT32-multiply bound (~3.4k IMAD.WIDE per 128 algorithmic bytes); the HBM fraction "
                              "is reported because north_star asks for it"},
     }

@@ -167,6 +167,11 @@ int pcgpu_kzg_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coe
 /* Device self-test of the field layer: n pseudo-random pairs per field (Fq and Fr of `curve`), production
  * multiplier (carry-chained mad.lo/mad.hi schedule) against the plain 64-bit-accumulate multiplier compiled into
  * the same kernel, plus a*a^-1 == 1 on a few elements.  *mismatches receives the number of disagreeing results. */
+/* Measures the chip's sustained 32x32+64 -> 64-bit integer multiply-add rate (IMAD.WIDE.U32, the instruction every field
+ * multiplication is made of) with a register-resident dependent-chain kernel at full occupancy; *ops_per_s receives
+ * multiply-adds per second.  bench.py divides the MSM kernels' multiply counts by it (the compute roofline that actually
+ * binds them; the HBM roofline north_star asks for is reported next to it). */
+int pcgpu_measure_imad_peak(pcgpu_ctx *ctx, double *ops_per_s);
 /* Kernels launched by this library in the calling process so far (bench.py's gpu_launches). */
 uint64_t pcgpu_launch_count(void);
 int pcgpu_selftest_field(pcgpu_ctx *ctx, int curve, uint64_t seed, size_t n, uint64_t *mismatches);

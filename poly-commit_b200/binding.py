@@ -63,6 +63,7 @@ def _load(path):
         "pcgpu_fr_div_linear": [_vp, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, ctypes.c_uint32],
         "pcgpu_fr_inner_product": [_vp, ctypes.c_int, _vp, _vp, _sz, _vp, ctypes.c_uint32],
         "pcgpu_fr_row_mul": [_vp, ctypes.c_int, _vp, _vp, _sz, _sz, _vp, ctypes.c_uint32],
+        "pcgpu_measure_imad_peak": [_vp, ctypes.POINTER(ctypes.c_double)],
         "pcgpu_selftest_field": [_vp, ctypes.c_int, ctypes.c_uint64, _sz, ctypes.POINTER(ctypes.c_uint64)],
         "pcgpu_ipa_begin": [_vp, ctypes.c_int, _vp, _sz, _vp, _sz, _vp, ctypes.c_uint32, ctypes.POINTER(_vp)],
         "pcgpu_ipa_round_lr": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -157,6 +158,11 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.pcgpu_launch_count())
+
+    def measure_imad_peak(self):
+        v = ctypes.c_double()
+        self._ck(self.lib.pcgpu_measure_imad_peak(self.ctx, ctypes.byref(v)))
+        return v.value
 
     def selftest_field(self, curve, seed=1, n=4096):
         bad = ctypes.c_uint64()

@@ -297,3 +297,10 @@ extern "C" int pcgpu_ipa_finish(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_k
   delete st;
   return rc;
 }
+
+extern "C" int pcgpu_measure_imad_peak(pcgpu_ctx *ctx, double *ops_per_s) {
+  if (!ctx || !ops_per_s) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  return measure_imad_peak_impl(ctx, ops_per_s);
+}

@@ -696,6 +696,47 @@ int selftest_field_impl(pcgpu_ctx *ctx, uint64_t seed, size_t n, uint64_t *misma
   return PCGPU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// IMAD.WIDE peak microbenchmark
+// ---------------------------------------------------------------------------------------------
+struct ImadPeakBody {
+  uint64_t *sink; uint32_t iters;
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    uint64_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
+    uint32_t x = (uint32_t)t * 2654435761u + 12345u, y = (uint32_t)t ^ 0x9e3779b9u;
+    for (uint32_t i = 0; i < iters; i++) {   // 8 independent 64-bit accumulators: (uint64)x*y + acc = one IMAD.WIDE.U32 each
+      a0 += (uint64_t)x * y; a1 += (uint64_t)x * (y + 1); a2 += (uint64_t)(x + 1) * y; a3 += (uint64_t)(x + 2) * y;
+      a4 += (uint64_t)x * (y + 3); a5 += (uint64_t)(x + 3) * y; a6 += (uint64_t)(x + 4) * (y + 1); a7 += (uint64_t)(x + 5) * y;
+      x += (uint32_t)a0; y ^= (uint32_t)a7;
+    }
+    sink[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  }
+};
+
+inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
+#ifdef PCGPU_EMUL
+  (void)ctx; *ops_per_s = 0; return PCGPU_OK;
+#else
+  rt::stream_t st = ctx->stream;
+  int rc;
+  const size_t threads = 148 * 2048;   // full occupancy on B200
+  const uint32_t iters = 4096;
+  if ((rc = ctx->stage.reserve(threads * 8 + 4096))) return rc;
+  uint64_t *sink = ctx->stage.take<uint64_t>(threads);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  if ((rc = rt::launch<256>(ImadPeakBody{sink, 64}, threads, st))) return rc;   // warm-up
+  cudaEventRecord(e0, st);
+  if ((rc = rt::launch<256>(ImadPeakBody{sink, iters}, threads, st))) return rc;
+  cudaEventRecord(e1, st);
+  if ((rc = rt::stream_sync(st))) return rc;
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ops_per_s = (double)threads * iters * 8.0 / (ms * 1e-3);
+  return PCGPU_OK;
+#endif
+}
+
 // Explicit instantiation list: `PCGPU_INSTANTIATE(Curve, extern)` declares, `PCGPU_INSTANTIATE(Curve, )` defines.
 #define PCGPU_INSTANTIATE(C, EXT)                                                                                          \
   EXT template int srs_register_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, pcgpu_srs *);        \

@@ -264,3 +264,27 @@ def test_cpp_host_mirror(tmp_path):
     assert (pts[0] == c0).all() and (pts[1] == w0).all() and (pts[2] == c1).all() and (pts[3] == w1).all()
     assert (rv == erv).all()
     assert kind == 0  # Error::TooManyCoefficients
+
+
+def test_cfg5_shape_2p22(eng, pc):
+    """BASELINE.json cfg5's per-polynomial shape (degree 2^22, BLS12-381; the 64-polynomial batch is 64 such commits
+    spread over the GPUs, poly_assignment): one commit against the oracle directly, plus linearity between two
+    polynomials:  commit(p0 + f*p1) == commit(p0) + f*commit(p1)."""
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    n = (1 << 22) + 1
+    bases = gpu_srs(eng, cname, n, seed=50)
+    srs = eng.srs_register(C.id, bases, flags=pc.SRS_PRECOMPUTE)
+    p0 = util.rand_fr_fast(cname, n, seed=500)
+    p1 = util.rand_fr_fast(cname, n, seed=501)
+    c0 = eng.kzg_commit(srs, p0)
+    c1 = eng.kzg_commit(srs, p1)
+    rc, e0, _ = orc.kzg_commit(C.id, bases, p0)
+    assert rc == 0 and (c0[0] == e0).all()
+    f = util.rand_fr(cname, 1, seed=502, mont=True)[0]
+    comb = eng.fr_axpy(C.id, p0, f, p1)
+    cc = eng.kzg_commit(srs, comb)
+    fc1, _ = orc.g1_mul(C.id, c1[0], orc.field_unop("orc_fr_from_mont", C.id, f.reshape(1, 4)))
+    exp, _ = orc.g1_sum(C.id, np.stack([c0[0], fc1]))
+    assert (cc[0] == exp).all()
+    srs.release()
