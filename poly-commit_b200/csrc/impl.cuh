@@ -702,14 +702,24 @@ int selftest_field_impl(pcgpu_ctx *ctx, uint64_t seed, size_t n, uint64_t *misma
 struct ImadPeakBody {
   uint64_t *sink; uint32_t iters;
   PCGPU_KERNEL_DEV void operator()(size_t t) const {
-    uint64_t a0 = t, a1 = t + 1, a2 = t + 2, a3 = t + 3, a4 = t + 4, a5 = t + 5, a6 = t + 6, a7 = t + 7;
-    uint32_t x = (uint32_t)t * 2654435761u + 12345u, y = (uint32_t)t ^ 0x9e3779b9u;
-    for (uint32_t i = 0; i < iters; i++) {   // 8 independent 64-bit accumulators: (uint64)x*y + acc = one IMAD.WIDE.U32 each
-      a0 += (uint64_t)x * y; a1 += (uint64_t)x * (y + 1); a2 += (uint64_t)(x + 1) * y; a3 += (uint64_t)(x + 2) * y;
-      a4 += (uint64_t)x * (y + 3); a5 += (uint64_t)(x + 3) * y; a6 += (uint64_t)(x + 4) * (y + 1); a7 += (uint64_t)(x + 5) * y;
-      x += (uint32_t)a0; y ^= (uint32_t)a7;
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { lo[j] = (uint32_t)t * 8u + j + 1u; hi[j] = (uint32_t)t ^ (0x9e3779b9u * (j + 1)); }
+    const uint32_t y = (uint32_t)t | 0x80000001u;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        // (hi:lo)[j] += hi[j+3] * y -- the same mad.lo.cc / madc.hi pair the field multiplier is made of; ptxas fuses each
+        // pair into one IMAD.WIDE.U32 with 64-bit accumulate.  8 independent chains per thread.
+        uint32_t x = hi[(j + 3) & 7];
+        lo[j] = mad_lo_cc(x, y, lo[j]);
+        hi[j] = madc_hi(x, y, hi[j]);
+      }
     }
-    sink[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    uint64_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc ^= ((uint64_t)hi[j] << 32) | lo[j];
+    sink[t] = acc;
   }
 };
 

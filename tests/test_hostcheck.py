@@ -200,6 +200,29 @@ def test_msm_batch_shared_bases(eng, pc, cname):
     assert inf[2] == 1
 
 
+def test_hyrax_host_mirror(eng, pc):
+    """hyrax.commit / open_row_mul (mirror of hyrax/mod.rs:230-242, :347) vs the oracle, 4 variables -> dim 4."""
+    from poly_commit_b200 import hyrax
+    cname = "bn254"
+    C = pyref.Curve(cname)
+    dim = 4
+    gens = util.random_points(cname, dim + 1, seed=60)
+    ck = hyrax.CommitterKey(eng, C.id, gens[:dim], gens[dim])
+    evals = util.rand_fr(cname, dim * dim, seed=61, mont=True)
+    rnd = util.rand_fr(cname, dim, seed=62, mont=True)
+    row_coms, inf, mat = hyrax.commit(ck, evals, rnd)
+    assert (mat[1, 2] == evals[2 * dim + 1]).all()            # flat_to_matrix_column_major: row[r][c] = flat[c*n + r]
+    for r in range(dim):
+        sc = np.concatenate([mat[r], rnd[r:r + 1]])
+        exp = orc.msm(C.id, gens, orc.field_unop("orc_fr_from_mont", C.id, sc))
+        assert (row_coms[r] == exp[0]).all()
+    l = util.rand_fr(cname, dim, seed=63, mont=True)
+    lt = hyrax.open_row_mul(ck, mat, l)
+    assert (lt == orc.fr_row_mul(C.id, l, mat.reshape(-1, 4), dim, dim)).all()
+    pc0 = hyrax.pedersen_commit(ck, mat[0])
+    assert (pc0[0] == orc.msm(C.id, gens[:dim], orc.field_unop("orc_fr_from_mont", C.id, mat[0]))[0]).all()
+
+
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
 def test_msm_partial_and_sum(eng, cname):
     """index-range sharding (SURVEY 8e partitioning B): partial XYZZ sums add up to the whole MSM."""
