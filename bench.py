@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="pcgpu", choices=["pcgpu", "reference"])
     ap.add_argument("--log-deg", type=int, default=LOG_DEG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=3, help="polynomials in flight per GPU (one context + stream each)")
+    ap.add_argument("--inflight", type=int, default=4, help="polynomials in flight per GPU (one context + stream each)")
     return ap.parse_args()
 
 

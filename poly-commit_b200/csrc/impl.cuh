@@ -155,7 +155,7 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
   // batched-affine rounds while buckets hold >= 64 points and a round still gives every thread >= 16 additions
   {
     size_t Tmax = 0;
-    if ((rc = rt::resident_threads<128, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
+    if ((rc = rt::resident_threads_occ<128, PAIR_MIN_BLOCKS, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
     size_t entries = (size_t)g.n * g.W, avg = entries / g.TB;
     uint32_t R = 0;
     while (R < 8 && (avg >> R) >= 128 && (entries >> (R + 1)) >= 16 * Tmax) R++;

@@ -375,6 +375,11 @@ inline size_t msm_workspace_bytes(const MsmGeom &g) {
   return b + 4096;
 }
 
+#ifndef PCGPU_PAIR_MIN_BLOCKS
+#define PCGPU_PAIR_MIN_BLOCKS 4
+#endif
+enum { PAIR_MIN_BLOCKS = PCGPU_PAIR_MIN_BLOCKS };  // resident blocks per SM requested for the affine pair kernel
+
 // Runs the device pipeline on `st`.  d_scalars: n x 8 uint32 on the device.  On return (asynchronously)
 // *d_planes points at the S*c bit-plane sums, element (s*c + j) at index (s*c + j) * plane_stride, and
 // *d_err at a device word that is non-zero when a scalar was out of range.  `prof` brackets stages with events.
@@ -429,7 +434,7 @@ inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_
     Affine<C> *ptsA = arena.take<Affine<C>>(bound0), *ptsB = arena.take<Affine<C>>(bound1);
     if (!offA || !offB || !cnt || !src || !prefix || !ptsA || !ptsB) return rt::E_OOM;
     size_t Tmax = 0;
-    if ((rc = rt::resident_threads<128, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
+    if ((rc = rt::resident_threads_occ<128, PAIR_MIN_BLOCKS, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
     if (Tmax > (1u << 20)) Tmax = 1u << 20;
     if (const char *e = getenv("PCGPU_MSM_AFFINE_TDIV")) { int v = atoi(e); if (v >= 1 && v <= 16) Tmax = (Tmax / v + 127) / 128 * 128; }  // tuning knob
     prof.begin(11, st);
@@ -444,8 +449,8 @@ inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_
       if ((rc = exclusive_scan_u32(cnt, g.TB, off_out, scratch, st))) return rc;
       if ((rc = rt::launch<256>(PairPlanBody{off_in, off_out, g.TB, src}, bound, st))) return rc;
       uint32_t T = (uint32_t)Tmax;
-      if (r == 0) rc = rt::launch<128>(MsmAffinePairBody<C, true>{tables, g, entries, nullptr, src, off_out, T, prefix, pow2, out}, T, st);
-      else rc = rt::launch<128>(MsmAffinePairBody<C, false>{tables, g, entries, in, src, off_out, T, prefix, pow2, out}, T, st);
+      if (r == 0) rc = rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, true>{tables, g, entries, nullptr, src, off_out, T, prefix, pow2, out}, T, st);
+      else rc = rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, false>{tables, g, entries, in, src, off_out, T, prefix, pow2, out}, T, st);
       if (rc) return rc;
       off_in = off_out;
       pts = out;

@@ -65,6 +65,8 @@ template <int BLOCK, class Body>
 inline int launch_persistent(const Body &body, stream_t) { body(0); return OK; }
 // threads of one resident wave of `Body` (host emulation: a small number so multi-iteration paths are exercised)
 template <int BLOCK, class Body> inline int resident_threads(size_t *out) { *out = 48; return OK; }
+template <int BLOCK, int MINB, class Body> inline int launch_occ(const Body &body, size_t n, stream_t s) { return launch<BLOCK>(body, n, s); }
+template <int BLOCK, int MINB, class Body> inline int resident_threads_occ(size_t *out) { *out = 48; return OK; }
 // Block-cooperative bodies: body(block_id, shared_memory).  Work inside the body is written as
 // PCGPU_BLOCK_FOR loops separated by PCGPU_BLOCK_SYNC(); anything that must survive a sync lives in shared memory.
 #define PCGPU_BLOCK_FOR(i, n) for (uint32_t i = 0; i < (uint32_t)(n); i++)
@@ -118,6 +120,34 @@ inline int launch(const Body &body, size_t n, stream_t s) {
   run_kernel<Body, BLOCK><<<(unsigned)grid, BLOCK, 0, s>>>(body, n);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   return last_error();
+}
+// same, with a minimum number of resident blocks per SM (caps registers; for latency-bound bodies that want more warps)
+template <class Body, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) run_kernel_occ(const Body body, size_t n) {
+  size_t tid = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (tid < n) body(tid);
+}
+template <int BLOCK, int MINB, class Body>
+inline int launch_occ(const Body &body, size_t n, stream_t s) {
+  if (n == 0) return OK;
+  size_t grid = (n + BLOCK - 1) / BLOCK;
+  run_kernel_occ<Body, BLOCK, MINB><<<(unsigned)grid, BLOCK, 0, s>>>(body, n);
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  return last_error();
+}
+template <int BLOCK, int MINB, class Body>
+inline int resident_threads_occ(size_t *out) {
+  static size_t cached = 0;
+  if (!cached) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_kernel_occ<Body, BLOCK, MINB>, BLOCK, 0);
+    if (e != cudaSuccess) return map_cuda(e);
+    cached = (size_t)sms * (per_sm > 0 ? per_sm : 1) * BLOCK;
+  }
+  *out = cached;
+  return OK;
 }
 #define PCGPU_BLOCK_FOR(i, n) for (uint32_t i = threadIdx.x; i < (uint32_t)(n); i += blockDim.x)
 #define PCGPU_BLOCK_SYNC() __syncthreads()
