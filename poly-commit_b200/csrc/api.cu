@@ -99,7 +99,7 @@ extern "C" int pcgpu_srs_register(pcgpu_ctx *ctx, int curve, const void *bases_x
   SET_DEVICE(ctx);
   pcgpu_srs *srs = new (std::nothrow) pcgpu_srs();
   if (!srs) return PCGPU_E_OOM;
-  srs->curve = curve; srs->n = n; srs->d_tables = nullptr; srs->c = 0; srs->groups = 1; srs->d_comb = nullptr; srs->comb_c = 0;
+  srs->curve = curve; srs->n = n; srs->d_tables = nullptr; srs->d_folded = nullptr; srs->c = 0; srs->groups = 1; srs->d_comb = nullptr; srs->comb_c = 0;
   int rc;
   switch (curve) {
     case PCGPU_BLS12_381: rc = srs_register_impl<Bls12381>(ctx, bases_xy, inf, n, flags, srs); break;
@@ -107,7 +107,7 @@ extern "C" int pcgpu_srs_register(pcgpu_ctx *ctx, int curve, const void *bases_x
     case PCGPU_PALLAS: rc = srs_register_impl<Pallas>(ctx, bases_xy, inf, n, flags, srs); break;
     default: rc = PCGPU_E_BADARG;
   }
-  if (rc) { rt::dev_free(srs->d_tables); rt::dev_free(srs->d_comb); delete srs; return rc; }
+  if (rc) { rt::dev_free(srs->d_tables); rt::dev_free(srs->d_folded); rt::dev_free(srs->d_comb); delete srs; return rc; }
   *out = srs;
   return PCGPU_OK;
 }
@@ -120,9 +120,9 @@ extern "C" void pcgpu_srs_release(pcgpu_ctx *ctx, pcgpu_srs *srs) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
 #endif
-    rt::dev_free(srs->d_tables); rt::dev_free(srs->d_comb);
+    rt::dev_free(srs->d_tables); rt::dev_free(srs->d_folded); rt::dev_free(srs->d_comb);
   } else {
-    rt::dev_free(srs->d_tables); rt::dev_free(srs->d_comb);
+    rt::dev_free(srs->d_tables); rt::dev_free(srs->d_folded); rt::dev_free(srs->d_comb);
   }
   delete srs;
 }

@@ -60,7 +60,8 @@ struct pcgpu_srs {
   size_t n;          // bases per table group
   uint32_t c;        // window bits the groups were built for (0: raw bases only)
   uint32_t groups;   // table groups (1: raw bases)
-  void *d_tables;    // groups * n affine points
+  void *d_tables;    // the n raw bases, packed x||y
+  void *d_folded;    // window-folded tables: groups * n records in the aligned layout (PCGPU_SRS_PRECOMPUTE) or null
   void *d_comb;      // fixed-base comb tables (PCGPU_SRS_COMB) or null
   uint32_t comb_c;   // comb window bits
 };
@@ -110,8 +111,9 @@ int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, siz
     c = srs_precompute_window(n);
     groups = C::Fr::BITS / c + 1;
   }
-  int rc = rt::dev_malloc(&srs->d_tables, psz * (n ? n : 1) * groups);
+  int rc = rt::dev_malloc(&srs->d_tables, psz * (n ? n : 1));
   if (rc) return rc;
+  if (groups > 1 && (rc = rt::dev_malloc(&srs->d_folded, (size_t)aligned_pt_words<C>() * 4 * n * groups))) return rc;
   rt::stream_t st = ctx->stream;
   if (n) {
     if (flags & PCGPU_DEVICE_PTRS) rc = rt::copy_d2d(srs->d_tables, bases, psz * n, st);
@@ -120,7 +122,7 @@ int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, siz
     if (inf && !(flags & PCGPU_DEVICE_PTRS))
       for (size_t i = 0; i < n; i++)
         if (inf[i] && (rc = rt::dev_memset((char *)srs->d_tables + psz * i, 0, psz, st))) return rc;
-    if (groups > 1 && (rc = srs_build_groups<C>((Affine<C> *)srs->d_tables, n, c, groups, ctx->stage, st))) return rc;
+    if (groups > 1 && (rc = srs_build_groups<C>((const Affine<C> *)srs->d_tables, (uint32_t *)srs->d_folded, n, c, groups, st))) return rc;
     if (flags & PCGPU_SRS_COMB) {
       CombGeom cg; memset(&cg, 0, sizeof cg);
       cg.n_bases = (uint32_t)n; cg.c = 8; cg.W = C::Fr::BITS / cg.c + 1; cg.NBk = 1u << (cg.c - 1);
@@ -148,9 +150,14 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
   *out = host::HXYZZ<C>::inf();
   if (n == 0) return PCGPU_OK;
   uint32_t c, groups;
-  if (srs->groups > 1 && n >= SRS_PRECOMPUTE_MIN_N) { c = srs->c; groups = srs->groups; }
-  else { c = msm_pick_c(n); groups = 1; }
+  const uint32_t *tables = (const uint32_t *)srs->d_tables;
+  uint32_t pt_words = 2 * C::Fq::N, y_words = C::Fq::N;
+  if (srs->groups > 1 && n >= SRS_PRECOMPUTE_MIN_N) {
+    c = srs->c; groups = srs->groups;
+    tables = (const uint32_t *)srs->d_folded; pt_words = aligned_pt_words<C>(); y_words = aligned_y_words<C>();
+  } else { c = msm_pick_c(n); groups = 1; }
   MsmGeom g = msm_geometry(n, c, groups, C::Fr::BITS, mont, srs->n, base_offset);
+  g.pt_words = pt_words; g.y_words = y_words;
   int rc;
   // batched-affine rounds while buckets hold >= 64 points and a round still gives every thread >= 16 additions
   {
@@ -168,7 +175,7 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
     if ((rc = rt::launch<32>(Pow2TableBody<QP>{ctx->d_pow2[C::ID]}, 1, st))) return rc;
   }
   const XYZZ<C> *d_planes = nullptr; size_t stride = 0; uint32_t *d_err = nullptr;
-  rc = msm_run<C>((const Affine<C> *)srs->d_tables, g, d_scalars, ctx->msm_arena, &d_planes, &stride, &d_err, st, ctx->prof,
+  rc = msm_run<C>(tables, g, d_scalars, ctx->msm_arena, &d_planes, &stride, &d_err, st, ctx->prof,
                   ctx->d_pow2[C::ID]);
   if (rc) return rc;
   size_t np = (size_t)g.S * g.c;
@@ -544,7 +551,7 @@ int ipa_begin_impl(pcgpu_ctx *ctx, const void *key_xy, size_t n, const void *coe
   uint32_t *d_pt = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 4);
   if ((rc = rt::copy_h2d(d_pt, point, 32, s))) return rc;
   if ((rc = rt::launch<128>(FrPowersBody<R>{d_pt, st->d_z}, n, s))) return rc;
-  st->view.curve = C::ID; st->view.n = n; st->view.c = 0; st->view.groups = 1; st->view.d_tables = st->d_key;
+  st->view.curve = C::ID; st->view.n = n; st->view.c = 0; st->view.groups = 1; st->view.d_tables = st->d_key; st->view.d_folded = nullptr;
   st->view.d_comb = nullptr; st->view.comb_c = 0;
   return rt::stream_sync(s);
 }

@@ -43,6 +43,8 @@ struct MsmGeom {
   uint64_t table_stride; // points per table group
   uint64_t base_off;     // first base used inside each group
   uint32_t affine_rounds; // batched-affine pairwise rounds before the XYZZ task kernel
+  uint32_t pt_words;      // table record stride in 32-bit words (2N raw; 32 for 128-byte aligned BLS12-381 records)
+  uint32_t y_words;       // offset of y inside a record, in words (N raw; 16 in the aligned BLS12-381 layout)
 };
 
 enum : uint32_t { ENTRY_SIGN = 0x80000000u, ENTRY_GROUP_SHIFT = 26, ENTRY_IDX_MASK = (1u << 26) - 1 };
@@ -202,6 +204,38 @@ PCGPU_DEV Affine<C> load_affine(const Affine<C> *p) {
   return a;
 }
 
+// Table records: x at word 0, y at word g.y_words, record stride g.pt_words.  The window-folded BLS12-381 tables use
+// 128-byte records (x in the first 64-byte half, y in the second) so that an x-only read is ONE aligned 64-byte DRAM
+// access and a full read two; raw base arrays keep the ABI's packed x||y.
+template <class C>
+PCGPU_DEV const uint32_t *table_record(const uint32_t *tables, size_t idx, const MsmGeom &g) { return tables + idx * g.pt_words; }
+template <class C>
+PCGPU_DEV Affine<C> load_table_point(const uint32_t *tables, size_t idx, const MsmGeom &g) {
+  constexpr int N = C::Fq::N;
+  const uint32_t *rec = tables + idx * g.pt_words;
+  const u32x4 *qx = reinterpret_cast<const u32x4 *>(rec), *qy = reinterpret_cast<const u32x4 *>(rec + g.y_words);
+  Affine<C> a;
+#pragma unroll
+  for (int j = 0; j < N / 4; j++) {
+    u32x4 v = qx[j]; a.x.l[4 * j] = v.x; a.x.l[4 * j + 1] = v.y; a.x.l[4 * j + 2] = v.z; a.x.l[4 * j + 3] = v.w;
+    u32x4 w = qy[j]; a.y.l[4 * j] = w.x; a.y.l[4 * j + 1] = w.y; a.y.l[4 * j + 2] = w.z; a.y.l[4 * j + 3] = w.w;
+  }
+  return a;
+}
+template <class C>
+PCGPU_DEV void store_table_point(uint32_t *tables, size_t idx, uint32_t pt_words, uint32_t y_words, const Affine<C> &a) {
+  constexpr int N = C::Fq::N;
+  uint32_t *rec = tables + idx * pt_words;
+  u32x4 *qx = reinterpret_cast<u32x4 *>(rec), *qy = reinterpret_cast<u32x4 *>(rec + y_words);
+#pragma unroll
+  for (int j = 0; j < N / 4; j++) {
+    u32x4 v; v.x = a.x.l[4 * j]; v.y = a.x.l[4 * j + 1]; v.z = a.x.l[4 * j + 2]; v.w = a.x.l[4 * j + 3]; qx[j] = v;
+    u32x4 w; w.x = a.y.l[4 * j]; w.y = a.y.l[4 * j + 1]; w.z = a.y.l[4 * j + 2]; w.w = a.y.l[4 * j + 3]; qy[j] = w;
+  }
+}
+template <class C> constexpr uint32_t aligned_pt_words() { return C::Fq::N == 12 ? 32u : 2u * C::Fq::N; }
+template <class C> constexpr uint32_t aligned_y_words() { return C::Fq::N == 12 ? 16u : (uint32_t)C::Fq::N; }
+
 template <class C>
 PCGPU_DEV void store_xyzz(XYZZ<C> *dst, const XYZZ<C> &p) {
   constexpr int N = C::Fq::N;
@@ -224,7 +258,7 @@ PCGPU_DEV XYZZ<C> load_xyzz(const XYZZ<C> *src) {
 
 template <class C>
 struct MsmAccumulateBody {
-  const Affine<C> *tables; MsmGeom g;
+  const uint32_t *tables; MsmGeom g;
   const uint32_t *offsets;      // TB+1 bucket offsets into entries
   const uint32_t *task_off;     // TB+1
   const uint32_t *task_bucket;  // per task
@@ -254,7 +288,7 @@ struct MsmAccumulateBody {
           uint32_t v = entries[e];
           uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
           size_t idx = (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK);
-          Affine<C> a = load_affine<C>(tables + idx);
+          Affine<C> a = load_table_point<C>(tables, idx, g);
           xyzz_madd<C>(acc, a, (v & ENTRY_SIGN) != 0);
         }
       }
@@ -349,6 +383,7 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
   g.scalar_bits = scalar_bits; g.scalars_mont = mont ? 1 : 0;
   g.table_stride = table_stride; g.base_off = base_off;
   g.affine_rounds = 0;
+  g.pt_words = 0; g.y_words = 0;  // set by the caller (table_layout)
   return g;
 }
 
@@ -384,7 +419,7 @@ enum { PAIR_MIN_BLOCKS = PCGPU_PAIR_MIN_BLOCKS };  // resident blocks per SM req
 // *d_planes points at the S*c bit-plane sums, element (s*c + j) at index (s*c + j) * plane_stride, and
 // *d_err at a device word that is non-zero when a scalar was out of range.  `prof` brackets stages with events.
 template <class C, class Prof>
-inline int msm_run(const Affine<C> *tables, const MsmGeom &g, const uint32_t *d_scalars, rt::Arena &arena,
+inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_scalars, rt::Arena &arena,
                    const XYZZ<C> **d_planes, size_t *plane_stride, uint32_t **d_err_out, rt::stream_t st, Prof &prof,
                    const uint32_t *pow2 = nullptr) {
   int rc;

@@ -72,7 +72,7 @@ PCGPU_DEV uint32_t pair_classify(const Affine<C> &P, const Affine<C> &Qp, bool s
 
 template <class C, bool FROM_TABLES>
 struct MsmAffinePairBody {
-  const Affine<C> *tables; MsmGeom g; const uint32_t *entries;  // round 0: operands are (table group, base, sign) entries
+  const uint32_t *tables; MsmGeom g; const uint32_t *entries;  // round 0: operands are (table group, base, sign) entries
   const Affine<C> *pts_in;                                      // later rounds: operands are affine points
   const uint32_t *src; const uint32_t *off_out;                 // plan; total outputs = off_out[g.TB]
   uint32_t T;                                                   // threads in this launch
@@ -85,7 +85,7 @@ struct MsmAffinePairBody {
     if (FROM_TABLES) {
       uint32_t v = entries[idx];
       uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
-      Affine<C> a = load_affine<C>(tables + ((size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK)));
+      Affine<C> a = load_table_point<C>(tables, (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK), g);
       if (!a.is_inf()) a.y = fp_cneg<Q>(a.y, (v & ENTRY_SIGN) != 0);
       return a;
     }
@@ -97,7 +97,7 @@ struct MsmAffinePairBody {
     if (FROM_TABLES) {
       uint32_t v = entries[idx];
       uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
-      return load_fq<Q>(reinterpret_cast<const uint32_t *>(tables + ((size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK))));
+      return load_fq<Q>(table_record<C>(tables, (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK), g));
     }
     return load_fq<Q>(reinterpret_cast<const uint32_t *>(pts_in + idx));
   }

@@ -23,22 +23,23 @@ inline uint32_t srs_precompute_window(size_t n) {
 }
 
 template <class C>
-struct SrsGroupsBody {
-  Affine<C> *tables; size_t n; uint32_t c; uint32_t groups;
+struct SrsGroupsBody {   // raw bases (packed x||y) -> all W groups in the aligned table layout (group 0 = the bases themselves)
+  const Affine<C> *raw; uint32_t *folded; size_t n; uint32_t c; uint32_t groups; uint32_t pt_words, y_words;
   PCGPU_KERNEL_DEV void operator()(size_t i) const {
-    Affine<C> a = load_affine<C>(tables + i);
+    Affine<C> a = load_affine<C>(raw + i);
+    store_table_point<C>(folded, i, pt_words, y_words, a);
     for (uint32_t k = 1; k < groups; k++) {
       XYZZ<C> p = xyzz_dbl_affine<C>(a);
       for (uint32_t j = 1; j < c; j++) p = xyzz_dbl<C>(p);
       a = xyzz_to_affine<C>(p);
-      tables[(size_t)k * n + i] = a;
+      store_table_point<C>(folded, (size_t)k * n + i, pt_words, y_words, a);
     }
   }
 };
 
 template <class C>
-inline int srs_build_groups(Affine<C> *tables, size_t n, uint32_t c, uint32_t groups, rt::Arena &, rt::stream_t st) {
-  return rt::launch<128>(SrsGroupsBody<C>{tables, n, c, groups}, n, st);
+inline int srs_build_groups(const Affine<C> *raw, uint32_t *folded, size_t n, uint32_t c, uint32_t groups, rt::stream_t st) {
+  return rt::launch<128>(SrsGroupsBody<C>{raw, folded, n, c, groups, aligned_pt_words<C>(), aligned_y_words<C>()}, n, st);
 }
 
 // out[i] = k_i * P for canonical scalars k_i (thread per scalar, 4-bit fixed window over a table of
