@@ -65,7 +65,8 @@ const char *pcgpu_strerror(int code);
 /* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL restores the context's own stream. */
 int pcgpu_set_stream(pcgpu_ctx *ctx, void *cuda_stream);
 /* Per-stage device timings (CUDA events on the launching stream).  stage: 0 digits/count, 1 scan,
- * 2 scatter, 3 tasks, 4 bucket accumulate, 5 bucket reduce, 6 final, 7 fr division, 8 fr axpy.
+ * 2 scatter, 3 tasks, 4 bucket accumulate (XYZZ), 5 bucket reduce, 6 final (host tail, wall clock), 7 fr division,
+ * 8 fr axpy, 9 ntt, 10 comb batch, 11 affine pair rounds (all), 12 affine pair round 0 kernel alone.
  * enable=1 starts recording; get returns accumulated milliseconds and launch count since enable. */
 int pcgpu_profile_enable(pcgpu_ctx *ctx, int enable);
 int pcgpu_profile_get(pcgpu_ctx *ctx, int stage, double *ms, uint64_t *count);

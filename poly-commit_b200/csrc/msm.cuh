@@ -484,9 +484,11 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
       if ((rc = exclusive_scan_u32(cnt, g.TB, off_out, scratch, st))) return rc;
       if ((rc = rt::launch<256>(PairPlanBody{off_in, off_out, g.TB, src}, bound, st))) return rc;
       uint32_t T = (uint32_t)Tmax;
+      if (r == 0) prof.begin(12, st);
       if (r == 0) rc = rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, true>{tables, g, entries, nullptr, src, off_out, T, prefix, pow2, out}, T, st);
       else rc = rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, false>{tables, g, entries, in, src, off_out, T, prefix, pow2, out}, T, st);
       if (rc) return rc;
+      if (r == 0) prof.end(12, st);
       off_in = off_out;
       pts = out;
     }

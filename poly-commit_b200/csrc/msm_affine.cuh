@@ -36,13 +36,30 @@ struct PairPlanBody {    // src[o] = index of the first operand of output slot o
   }
 };
 
+// read-only (non-coherent) loads: the operands of a pair round are never written by it, which lets the compiler hoist
+// the gathers of several iterations above the prefix stores
+PCGPU_DEV u32x4 ldg4(const u32x4 *p) {
+#ifdef __CUDA_ARCH__
+  uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+  u32x4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+  return *p;
+#endif
+}
+PCGPU_DEV uint32_t ldg1(const uint32_t *p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
 template <class Q>
 PCGPU_DEV Fp<Q> load_fq(const uint32_t *p) {
   constexpr int N = Q::N;
   const u32x4 *q = reinterpret_cast<const u32x4 *>(p);
   Fp<Q> r;
 #pragma unroll
-  for (int j = 0; j < N / 4; j++) { u32x4 v = q[j]; r.l[4 * j] = v.x; r.l[4 * j + 1] = v.y; r.l[4 * j + 2] = v.z; r.l[4 * j + 3] = v.w; }
+  for (int j = 0; j < N / 4; j++) { u32x4 v = ldg4(q + j); r.l[4 * j] = v.x; r.l[4 * j + 1] = v.y; r.l[4 * j + 2] = v.z; r.l[4 * j + 3] = v.w; }
   return r;
 }
 template <class Q>
@@ -83,7 +100,7 @@ struct MsmAffinePairBody {
   PCGPU_DEV Affine<C> operand(uint32_t idx) const {
     using Q = typename C::Fq;
     if (FROM_TABLES) {
-      uint32_t v = entries[idx];
+      uint32_t v = ldg1(entries + idx);
       uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
       Affine<C> a = load_table_point<C>(tables, (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK), g);
       if (!a.is_inf()) a.y = fp_cneg<Q>(a.y, (v & ENTRY_SIGN) != 0);
@@ -95,11 +112,23 @@ struct MsmAffinePairBody {
   PCGPU_DEV Fp<typename C::Fq> operand_x(uint32_t idx) const {
     using Q = typename C::Fq;
     if (FROM_TABLES) {
-      uint32_t v = entries[idx];
+      uint32_t v = ldg1(entries + idx);
       uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
       return load_fq<Q>(table_record<C>(tables, (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK), g));
     }
     return load_fq<Q>(reinterpret_cast<const uint32_t *>(pts_in + idx));
+  }
+
+  // denominator of slot `sv` given the two x coordinates (the exceptional cases re-read the full points; rare)
+  PCGPU_DEV Fp<typename C::Fq> denominator(uint32_t sv, const Fp<typename C::Fq> &x1, const Fp<typename C::Fq> &x2) const {
+    using Q = typename C::Fq;
+    if (sv & PAIR_SINGLE) return Fp<Q>::one();
+    if (x1 != x2 && !x1.is_zero() && !x2.is_zero()) return fp_sub<Q>(x2, x1);
+    uint32_t i0 = sv & ~PAIR_SINGLE;
+    Affine<C> P = operand(i0), Qp = operand(i0 + 1);
+    Fp<Q> d;
+    pair_classify<C>(P, Qp, false, d);
+    return d;
   }
 
   PCGPU_KERNEL_DEV void operator()(size_t t) const {
@@ -107,30 +136,37 @@ struct MsmAffinePairBody {
     constexpr int N = Q::N;
     if (t >= T) return;
     const uint32_t total = off_out[g.TB];
-    const uint32_t K = (total + T - 1) / T;
     // ---- pass 1: running product of the denominators, prefix products to memory ----
+    // (two slots per trip so that four x-coordinate gathers are in flight before the first multiplication needs one)
+    const uint32_t kmax = (uint32_t)t < total ? (total - (uint32_t)t + T - 1) / T : 0u;   // slots k*T + t < total
     Fp<Q> acc = Fp<Q>::one();
-    for (uint32_t k = 0; k < K; k++) {
-      uint32_t o = k * T + (uint32_t)t;
-      if (o >= total) break;
-      uint32_t sv = src[o];
-      uint32_t i0 = sv & ~PAIR_SINGLE;
-      bool single = (sv & PAIR_SINGLE) != 0;
-      Fp<Q> d = Fp<Q>::one();
-      if (!single) {
-        Fp<Q> x1 = operand_x(i0), x2 = operand_x(i0 + 1);
-        if (x1 != x2 && !x1.is_zero() && !x2.is_zero()) d = fp_sub<Q>(x2, x1);
-        else { Affine<C> P = operand(i0), Qp = operand(i0 + 1); pair_classify<C>(P, Qp, false, d); }   // rare
-      }
+    uint32_t k = 0;
+    for (; k + 1 < kmax; k += 2) {
+      uint32_t oa = k * T + (uint32_t)t, ob = oa + T;
+      uint32_t sa = ldg1(src + oa), sb = ldg1(src + ob);
+      uint32_t ia = sa & ~PAIR_SINGLE, ib = sb & ~PAIR_SINGLE;
+      Fp<Q> xa1 = operand_x(ia), xa2 = operand_x((sa & PAIR_SINGLE) ? ia : ia + 1);
+      Fp<Q> xb1 = operand_x(ib), xb2 = operand_x((sb & PAIR_SINGLE) ? ib : ib + 1);
+      Fp<Q> da = denominator(sa, xa1, xa2), db = denominator(sb, xb1, xb2);
       store_fq<Q>(prefix + ((size_t)k * T + t) * N, acc);
-      acc = fp_mul<Q>(acc, d);
+      acc = fp_mul<Q>(acc, da);
+      store_fq<Q>(prefix + ((size_t)(k + 1) * T + t) * N, acc);
+      acc = fp_mul<Q>(acc, db);
+    }
+    if (k < kmax) {
+      uint32_t oa = k * T + (uint32_t)t;
+      uint32_t sa = ldg1(src + oa), ia = sa & ~PAIR_SINGLE;
+      Fp<Q> xa1 = operand_x(ia), xa2 = operand_x((sa & PAIR_SINGLE) ? ia : ia + 1);
+      Fp<Q> da = denominator(sa, xa1, xa2);
+      store_fq<Q>(prefix + ((size_t)k * T + t) * N, acc);
+      acc = fp_mul<Q>(acc, da);
     }
     Fp<Q> inv = fp_inv_gcd<Q>(acc, pow2);
     // ---- pass 2: walk back, one inverse per pair, emit the sums ----
-    for (uint32_t k = K; k-- > 0;) {
+    for (uint32_t k2 = kmax; k2-- > 0;) {
+      const uint32_t k = k2;
       uint32_t o = k * T + (uint32_t)t;
-      if (o >= total) continue;
-      uint32_t sv = src[o];
+      uint32_t sv = ldg1(src + o);
       uint32_t i0 = sv & ~PAIR_SINGLE;
       bool single = (sv & PAIR_SINGLE) != 0;
       Affine<C> P = operand(i0), Qp = single ? Affine<C>::inf() : operand(i0 + 1);
