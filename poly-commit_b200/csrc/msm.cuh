@@ -404,7 +404,7 @@ inline size_t msm_workspace_bytes(const MsmGeom &g) {
     size_t bound0 = max_entries / 2 + g.TB + 1, bound1 = bound0 / 2 + g.TB + 1;
     b += 3 * rt::Arena::pad((g.TB + 2) * sizeof(uint32_t));
     b += rt::Arena::pad(bound0 * sizeof(uint32_t));
-    b += rt::Arena::pad((bound0 + (1u << 20)) * sizeof(Fp<typename C::Fq>));
+    b += rt::Arena::pad(3 * (bound0 + (1u << 20)) * sizeof(Fp<typename C::Fq>));
     b += rt::Arena::pad(bound0 * sizeof(Affine<C>)) + rt::Arena::pad(bound1 * sizeof(Affine<C>));
   }
   return b + 4096;
@@ -465,7 +465,7 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
     size_t bound0 = max_entries / 2 + g.TB + 1, bound1 = bound0 / 2 + g.TB + 1;
     uint32_t *offA = arena.take<uint32_t>(g.TB + 2), *offB = arena.take<uint32_t>(g.TB + 2), *cnt = arena.take<uint32_t>(g.TB + 2);
     uint32_t *src = arena.take<uint32_t>(bound0);
-    uint32_t *prefix = (uint32_t *)arena.take<QF>(bound0 + (1u << 20));
+    uint32_t *prefix = (uint32_t *)arena.take<QF>(3 * (bound0 + (1u << 20)));   // prefix | x1 | d  (x1, d: round 0 only)
     Affine<C> *ptsA = arena.take<Affine<C>>(bound0), *ptsB = arena.take<Affine<C>>(bound1);
     if (!offA || !offB || !cnt || !src || !prefix || !ptsA || !ptsB) return rt::E_OOM;
     size_t Tmax = 0;

@@ -17,7 +17,7 @@
 
 namespace pcgpu {
 
-enum : uint32_t { PAIR_SINGLE = 0x80000000u };
+enum : uint32_t { PAIR_SINGLE = 0x80000000u, PAIR_EXC = 0x40000000u, PAIR_NONE = 0xffffffffu };
 
 struct PairCountBody {   // cnt_out[b] = ceil(cnt_in[b] / 2)
   const uint32_t *off_in; uint32_t *cnt_out;
@@ -46,6 +46,7 @@ PCGPU_DEV u32x4 ldg4(const u32x4 *p) {
   return *p;
 #endif
 }
+PCGPU_DEV uint32_t ldg_plain(const uint32_t *p) { return *p; }   // coherent load (data written earlier by the same thread)
 PCGPU_DEV uint32_t ldg1(const uint32_t *p) {
 #ifdef __CUDA_ARCH__
   return __ldg(p);
@@ -91,41 +92,50 @@ template <class C, bool FROM_TABLES>
 struct MsmAffinePairBody {
   const uint32_t *tables; MsmGeom g; const uint32_t *entries;  // round 0: operands are (table group, base, sign) entries
   const Affine<C> *pts_in;                                      // later rounds: operands are affine points
-  const uint32_t *src; const uint32_t *off_out;                 // plan; total outputs = off_out[g.TB]
+  uint32_t *src; const uint32_t *off_out;                       // plan; total outputs = off_out[g.TB] (pass 1 may set PAIR_EXC)
   uint32_t T;                                                   // threads in this launch
-  uint32_t *prefix;                                             // one field element per (iteration, thread)
+  uint32_t *prefix;                                             // per (iteration, thread): prefix product; round 0 also x1 and d
   const uint32_t *pow2;                                         // fp_inv_gcd table
   Affine<C> *pts_out;
 
-  PCGPU_DEV Affine<C> operand(uint32_t idx) const {
+  // Slot descriptor: round 0 -> (entry of P, entry of Q or PAIR_NONE); later rounds -> (index of P, PAIR_NONE if single).
+  // Descriptors are fetched ONE iteration ahead so that the only load latency exposed per iteration is the point gather.
+  struct Slot { uint32_t a, b; };
+  PCGPU_DEV Slot fetch_slot(uint32_t o) const {
+    uint32_t sv = ldg1(src + o);
+    uint32_t i0 = sv & ~(PAIR_SINGLE | PAIR_EXC);
+    bool single = (sv & PAIR_SINGLE) != 0;
+    Slot s;
+    if (FROM_TABLES) { s.a = ldg1(entries + i0); s.b = single ? PAIR_NONE : ldg1(entries + i0 + 1); }
+    else { s.a = i0; s.b = single ? PAIR_NONE : 0u; }
+    return s;
+  }
+  PCGPU_DEV const uint32_t *slot_rec(uint32_t v) const {   // record of a round-0 entry
+    uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
+    return table_record<C>(tables, (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK), g);
+  }
+  PCGPU_DEV Fp<typename C::Fq> slot_x(const Slot &s, int which) const {
+    using Q = typename C::Fq;
+    if (FROM_TABLES) return load_fq<Q>(slot_rec(which ? s.b : s.a));
+    return load_fq<Q>(reinterpret_cast<const uint32_t *>(pts_in + s.a + which));
+  }
+  PCGPU_DEV Affine<C> slot_point(const Slot &s, int which) const {
     using Q = typename C::Fq;
     if (FROM_TABLES) {
-      uint32_t v = ldg1(entries + idx);
-      uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
-      Affine<C> a = load_table_point<C>(tables, (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK), g);
+      uint32_t v = which ? s.b : s.a;
+      const uint32_t *rec = slot_rec(v);
+      Affine<C> a; a.x = load_fq<Q>(rec); a.y = load_fq<Q>(rec + g.y_words);
       if (!a.is_inf()) a.y = fp_cneg<Q>(a.y, (v & ENTRY_SIGN) != 0);
       return a;
     }
-    return load_affine<C>(pts_in + idx);
+    return load_affine<C>(pts_in + s.a + which);
   }
-  // x coordinate only (pass 1 fast path); for round 0 the sign does not touch x
-  PCGPU_DEV Fp<typename C::Fq> operand_x(uint32_t idx) const {
+  PCGPU_DEV Fp<typename C::Fq> slot_denominator(const Slot &s) const {
     using Q = typename C::Fq;
-    if (FROM_TABLES) {
-      uint32_t v = ldg1(entries + idx);
-      uint32_t grp = (v & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
-      return load_fq<Q>(table_record<C>(tables, (size_t)grp * g.table_stride + g.base_off + (v & ENTRY_IDX_MASK), g));
-    }
-    return load_fq<Q>(reinterpret_cast<const uint32_t *>(pts_in + idx));
-  }
-
-  // denominator of slot `sv` given the two x coordinates (the exceptional cases re-read the full points; rare)
-  PCGPU_DEV Fp<typename C::Fq> denominator(uint32_t sv, const Fp<typename C::Fq> &x1, const Fp<typename C::Fq> &x2) const {
-    using Q = typename C::Fq;
-    if (sv & PAIR_SINGLE) return Fp<Q>::one();
+    if (s.b == PAIR_NONE) return Fp<Q>::one();
+    Fp<Q> x1 = slot_x(s, 0), x2 = slot_x(s, 1);
     if (x1 != x2 && !x1.is_zero() && !x2.is_zero()) return fp_sub<Q>(x2, x1);
-    uint32_t i0 = sv & ~PAIR_SINGLE;
-    Affine<C> P = operand(i0), Qp = operand(i0 + 1);
+    Affine<C> P = slot_point(s, 0), Qp = slot_point(s, 1);   // exceptional pair: rare
     Fp<Q> d;
     pair_classify<C>(P, Qp, false, d);
     return d;
@@ -136,40 +146,73 @@ struct MsmAffinePairBody {
     constexpr int N = Q::N;
     if (t >= T) return;
     const uint32_t total = off_out[g.TB];
+    uint32_t *xbuf = prefix + (size_t)T * N * ((total + T - 1) / T);   // round 0 only: x1 per slot, then d per slot
+    uint32_t *dbuf = xbuf + (size_t)T * N * ((total + T - 1) / T);
     // ---- pass 1: running product of the denominators, prefix products to memory ----
-    // (two slots per trip so that four x-coordinate gathers are in flight before the first multiplication needs one)
     const uint32_t kmax = (uint32_t)t < total ? (total - (uint32_t)t + T - 1) / T : 0u;   // slots k*T + t < total
     Fp<Q> acc = Fp<Q>::one();
-    uint32_t k = 0;
-    for (; k + 1 < kmax; k += 2) {
-      uint32_t oa = k * T + (uint32_t)t, ob = oa + T;
-      uint32_t sa = ldg1(src + oa), sb = ldg1(src + ob);
-      uint32_t ia = sa & ~PAIR_SINGLE, ib = sb & ~PAIR_SINGLE;
-      Fp<Q> xa1 = operand_x(ia), xa2 = operand_x((sa & PAIR_SINGLE) ? ia : ia + 1);
-      Fp<Q> xb1 = operand_x(ib), xb2 = operand_x((sb & PAIR_SINGLE) ? ib : ib + 1);
-      Fp<Q> da = denominator(sa, xa1, xa2), db = denominator(sb, xb1, xb2);
-      store_fq<Q>(prefix + ((size_t)k * T + t) * N, acc);
-      acc = fp_mul<Q>(acc, da);
-      store_fq<Q>(prefix + ((size_t)(k + 1) * T + t) * N, acc);
-      acc = fp_mul<Q>(acc, db);
-    }
-    if (k < kmax) {
-      uint32_t oa = k * T + (uint32_t)t;
-      uint32_t sa = ldg1(src + oa), ia = sa & ~PAIR_SINGLE;
-      Fp<Q> xa1 = operand_x(ia), xa2 = operand_x((sa & PAIR_SINGLE) ? ia : ia + 1);
-      Fp<Q> da = denominator(sa, xa1, xa2);
-      store_fq<Q>(prefix + ((size_t)k * T + t) * N, acc);
-      acc = fp_mul<Q>(acc, da);
+    {
+      Slot nxt; nxt.a = 0; nxt.b = PAIR_NONE;
+      if (kmax) nxt = fetch_slot((uint32_t)t);
+      for (uint32_t k = 0; k < kmax; k++) {
+        Slot cur = nxt;
+        if (k + 1 < kmax) nxt = fetch_slot((k + 1) * T + (uint32_t)t);   // descriptor of the next slot: in flight during this one
+        Fp<Q> d;
+        if (FROM_TABLES) {
+          // Round 0 gathers every base twice (x here, y in pass 2).  x1 and the denominator are written out next to the
+          // prefix product (coalesced), so pass 2 re-reads them sequentially and gathers ONLY the y halves of the records:
+          // the random traffic of the round halves (random 64/128-byte HBM accesses run at ~1/4 of the streaming rate).
+          Fp<Q> x1 = slot_x(cur, 0);
+          bool exc = false;
+          if (cur.b == PAIR_NONE) d = Fp<Q>::one();
+          else {
+            Fp<Q> x2 = slot_x(cur, 1);
+            if (x1 != x2 && !x1.is_zero() && !x2.is_zero()) d = fp_sub<Q>(x2, x1);
+            else { Affine<C> P = slot_point(cur, 0), Qp = slot_point(cur, 1); pair_classify<C>(P, Qp, false, d); exc = true; }
+          }
+          if (exc) src[k * T + (uint32_t)t] |= PAIR_EXC;
+          store_fq<Q>(xbuf + ((size_t)k * T + t) * N, x1);
+          store_fq<Q>(dbuf + ((size_t)k * T + t) * N, d);
+        } else {
+          d = slot_denominator(cur);
+        }
+        store_fq<Q>(prefix + ((size_t)k * T + t) * N, acc);
+        acc = fp_mul<Q>(acc, d);
+      }
     }
     Fp<Q> inv = fp_inv_gcd<Q>(acc, pow2);
     // ---- pass 2: walk back, one inverse per pair, emit the sums ----
+    Slot nxt2; nxt2.a = 0; nxt2.b = PAIR_NONE;
+    if (kmax) nxt2 = fetch_slot((kmax - 1) * T + (uint32_t)t);
     for (uint32_t k2 = kmax; k2-- > 0;) {
       const uint32_t k = k2;
       uint32_t o = k * T + (uint32_t)t;
-      uint32_t sv = ldg1(src + o);
-      uint32_t i0 = sv & ~PAIR_SINGLE;
-      bool single = (sv & PAIR_SINGLE) != 0;
-      Affine<C> P = operand(i0), Qp = single ? Affine<C>::inf() : operand(i0 + 1);
+      Slot cur = nxt2;
+      const bool exc = FROM_TABLES && (ldg_plain(src + o) & PAIR_EXC) != 0;
+      if (k > 0) nxt2 = fetch_slot(o - T);
+      bool single = cur.b == PAIR_NONE;
+      if (FROM_TABLES && !exc) {
+        // fast path: x1, d from pass 1 (sequential), y halves gathered
+        Fp<Q> x1 = load_fq<Q>(xbuf + ((size_t)k * T + t) * N), d = load_fq<Q>(dbuf + ((size_t)k * T + t) * N);
+        Fp<Q> y1 = fp_cneg<Q>(load_fq<Q>(slot_rec(cur.a) + g.y_words), (cur.a & ENTRY_SIGN) != 0);
+        Fp<Q> dinv = fp_mul<Q>(inv, load_fq<Q>(prefix + ((size_t)k * T + t) * N));
+        inv = fp_mul<Q>(inv, d);
+        Affine<C> R;
+        if (single) { R.x = x1; R.y = y1; if (x1.is_zero() && y1.is_zero()) R = Affine<C>::inf(); }
+        else {
+          Fp<Q> y2 = fp_cneg<Q>(load_fq<Q>(slot_rec(cur.b) + g.y_words), (cur.b & ENTRY_SIGN) != 0);
+          Fp<Q> lam = fp_mul<Q>(fp_sub<Q>(y2, y1), dinv);
+          Fp<Q> x2 = fp_add<Q>(x1, d);
+          Fp<Q> x3 = fp_sub<Q>(fp_sub<Q>(fp_sqr<Q>(lam), x1), x2);
+          R.x = x3;
+          R.y = fp_sub<Q>(fp_mul<Q>(lam, fp_sub<Q>(x1, x3)), y1);
+        }
+        Affine<C> *dst0 = pts_out + o;
+        store_fq<Q>(reinterpret_cast<uint32_t *>(dst0), R.x);
+        store_fq<Q>(reinterpret_cast<uint32_t *>(dst0) + N, R.y);
+        continue;
+      }
+      Affine<C> P = slot_point(cur, 0), Qp = single ? Affine<C>::inf() : slot_point(cur, 1);
       Fp<Q> d;
       uint32_t kind = pair_classify<C>(P, Qp, single, d);
       Fp<Q> dinv = fp_mul<Q>(inv, load_fq<Q>(prefix + ((size_t)k * T + t) * N));
