@@ -122,12 +122,12 @@ def test_msm_edge_scalars(eng, pc):
     assert ei.value.code == -4
 
 
-@pytest.mark.parametrize("rounds", [1, 2, 3, 5])
+@pytest.mark.parametrize("rounds", [1, 3, 5])
 def test_msm_batched_affine_rounds(eng, pc, rounds, monkeypatch):
     """msm_affine.cuh: forced batched-affine pairwise rounds (Montgomery batch inversion with the binary-GCD inverse)
     must give the same point, including the exceptional pairs: P + P, P + (-P), identity operands, odd bucket sizes."""
     monkeypatch.setenv("PCGPU_MSM_AFFINE_ROUNDS", str(rounds))
-    for cname, n in (("bls12_381", 300), ("bn254", 77), ("pallas", 130)):
+    for cname, n in (("bls12_381", 150), ("bn254", 61), ("pallas", 90)):
         C = pyref.Curve(cname)
         pts = util.random_points(cname, n, seed=90 + rounds)
         neg = C.points_to_limbs([C.neg(p) for p in C.points_from_limbs(pts[:3])])[0]
@@ -141,6 +141,8 @@ def test_msm_batched_affine_rounds(eng, pc, rounds, monkeypatch):
         got = eng.msm(srs, sc)
         exp = orc.msm(C.id, bases, sc, inf=inf)
         assert got[1] == exp[1] and (got[0] == exp[0]).all(), (cname, rounds)
+    if rounds != 3:
+        return
     # window-folded tables + rounds
     C = pyref.Curve("bn254")
     bases = util.random_points("bn254", 4200, seed=95)
