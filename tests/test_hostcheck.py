@@ -202,6 +202,48 @@ def test_msm_batch_shared_bases(eng, pc, cname):
     assert inf[2] == 1
 
 
+def test_marlin_pc_host_mirror(eng, pc):
+    """marlin_pc.commit / open (mirror of marlin_pc/mod.rs:172-336) with and without degree bounds vs the oracle composed
+    the same way: two_polys_degree_bound_single_query_test's shape (marlin_pc/mod.rs:720ff)."""
+    from poly_commit_b200 import marlin_pc
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    max_degree, bounds = 40, [20, 33]
+    pp = util.synthetic_srs(cname, max_degree + 1, seed=8)                 # universal powers_of_g[0..=max_degree]
+    supported = 36
+    powers = pp[: supported + 1]
+    shifted = pp[max_degree - bounds[-1]:]                                   # trim(): powers_of_g[lowest_shift_degree..]
+    ck = marlin_pc.CommitterKey(eng, C.id, powers, shifted, bounds)
+    polys = [(util.rand_fr(cname, 30, seed=80, mont=True), None), (util.rand_fr(cname, 18, seed=81, mont=True), 20),
+             (util.rand_fr(cname, 34, seed=82, mont=True), 33)]
+    coms = marlin_pc.commit(ck, polys)
+    for (coeffs, bound), (comm, sh) in zip(polys, coms):
+        rc, exy, _ = orc.kzg_commit(C.id, powers, coeffs)
+        assert rc == 0 and (comm[0] == exy).all()
+        if bound is None:
+            assert sh is None
+        else:
+            rc, sxy, _ = orc.kzg_commit(C.id, shifted[bounds[-1] - bound:], coeffs)
+            assert rc == 0 and (sh[0] == sxy).all()
+    point = util.rand_fr(cname, 1, seed=83, mont=True)[0]
+    chals = util.rand_fr(cname, 5, seed=84, mont=True)
+    w = marlin_pc.open(ck, polys, point, list(chals))
+    # oracle composition of marlin_pc/mod.rs:245-336
+    p = np.zeros((34, 4), dtype=np.uint64); sw = np.zeros((bounds[-1] + 1, 4), dtype=np.uint64); ci = 0
+    for coeffs, bound in polys:
+        p[: len(coeffs)] = orc.fr_axpy(C.id, p[: len(coeffs)], chals[ci], coeffs); ci += 1
+        if bound is not None:
+            wit, _ = orc.fr_div_linear(C.id, coeffs, point)
+            s = np.concatenate([np.zeros((bounds[-1] - bound, 4), dtype=np.uint64), wit])
+            sw[: len(s)] = orc.fr_axpy(C.id, sw[: len(s)], chals[ci], s); ci += 1
+    rc, w0, _, _ = orc.kzg_open(C.id, powers, p, point)
+    rc2, w1, _ = orc.kzg_commit(C.id, shifted, sw)
+    exp, _ = orc.g1_sum(C.id, np.stack([w0, w1]))
+    assert rc == 0 and rc2 == 0 and (w[0] == exp).all()
+    with pytest.raises(ValueError):
+        marlin_pc.commit(ck, [(polys[2][0], 20)])                            # bound below the degree
+
+
 def test_hyrax_host_mirror(eng, pc):
     """hyrax.commit / open_row_mul (mirror of hyrax/mod.rs:230-242, :347) vs the oracle, 4 variables -> dim 4."""
     from poly_commit_b200 import hyrax
