@@ -157,6 +157,14 @@ int pcgpu_ipa_finish(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_key_xy, void
 int pcgpu_kzg_commit(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coeffs, size_t n,
                      const pcgpu_srs *powers_of_gamma_g, const void *blind, size_t n_blind, uint32_t flags,
                      void *out_xy, uint8_t *out_inf);
+/* MarlinKZG10::commit's per-polynomial loop (marlin_pc/mod.rs:192-241) in one call: `count` independent non-hiding
+ * KZG10 commitments over the same powers.  coeffs[i] points at n[i] Montgomery Fr coefficients; out_xy receives count
+ * affine points, out_inf count flags.  Polynomials are processed `PCGPU_BATCH_WAYS` (4) at a time on sibling
+ * contexts (own stream + workspace each) so that the latency-bound stages of one MSM overlap the multiply-bound stages
+ * of another -- what the reference's serial loop leaves on the table.  BASELINE.json cfg5 = 64 such polynomials spread
+ * over 8 GPUs (poly_commit_b200.sharded.poly_assignment). */
+int pcgpu_kzg_commit_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *const *coeffs, const size_t *n,
+                           size_t count, uint32_t flags, void *out_xy, uint8_t *out_inf);
 /* KZG10::open -- kzg10/mod.rs:287-310 (compute_witness_polynomial :217-240 then open_with_witness_polynomial
  * :243-284): witness = p / (X - z) on the device, then the MSM over the witness.  out_random_v (may be NULL)
  * receives blind(z) when n_blind > 0 (:264). */

@@ -70,6 +70,7 @@ def _load(path):
         "pcgpu_ipa_round_fold": [_vp, _vp, _vp, _vp],
         "pcgpu_ipa_finish": [_vp, _vp, _vp, _vp],
         "pcgpu_ntt": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
+        "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
     }
@@ -318,6 +319,22 @@ class Engine:
                                            None if powers_of_gamma_g is None else powers_of_gamma_g.handle,
                                            _ptr(blind), nb, flags, _ptr(out), _ptr(inf)))
         return out, int(inf[0])
+
+    def kzg_commit_batch(self, powers_of_g, polys, flags=0):
+        """MarlinKZG10::commit's loop over polynomials (marlin_pc/mod.rs:192-241), non-hiding: list of coefficient arrays
+        (or (device_ptr, n) tuples with DEVICE_PTRS) -> ((count, 2*limbs) uint64, (count,) uint8)."""
+        count = len(polys)
+        ptrs, lens, keep = (ctypes.c_void_p * count)(), (_sz * count)(), []
+        for i, p in enumerate(polys):
+            if isinstance(p, tuple):
+                ptrs[i], lens[i] = int(p[0]), int(p[1])
+            else:
+                a = _u64(p); keep.append(a)
+                ptrs[i], lens[i] = a.ctypes.data, a.size // 4
+        out = np.zeros((count, 2 * fq_limbs(powers_of_g.curve)), dtype=np.uint64)
+        inf = np.zeros(count, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_kzg_commit_batch(self.ctx, powers_of_g.handle, ptrs, lens, count, flags, _ptr(out), _ptr(inf)))
+        return out, inf
 
     def kzg_open(self, powers_of_g, coeffs, z, n=None, powers_of_gamma_g=None, blind=None, flags=0):
         coeffs, blind, z = _u64(coeffs), _u64(blind), _u64(z)

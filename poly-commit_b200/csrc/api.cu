@@ -1,5 +1,7 @@
 // C ABI entry points (include/pcgpu.h): argument checks, locking, curve dispatch.
 // The per-curve template instantiations live in inst_*.cu so the three curves compile in parallel.
+#include <thread>
+
 #include "impl.cuh"
 
 PCGPU_INSTANTIATE(Bls12381, extern)
@@ -53,6 +55,7 @@ extern "C" void pcgpu_destroy(pcgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
 #endif
   ctx->prof.destroy();
+  for (pcgpu_ctx *s : ctx->siblings) pcgpu_destroy(s);
   for (NttPlan &p : ctx->ntt_plans) rt::dev_free(p.base);
   for (int k = 0; k < 3; k++) rt::dev_free(ctx->d_pow2[k]);
   ctx->msm_arena.release();
@@ -303,4 +306,37 @@ extern "C" int pcgpu_measure_imad_peak(pcgpu_ctx *ctx, double *ops_per_s) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   return measure_imad_peak_impl(ctx, ops_per_s);
+}
+
+enum { PCGPU_BATCH_WAYS = 4 };
+
+extern "C" int pcgpu_kzg_commit_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *const *coeffs, const size_t *n,
+                                      size_t count, uint32_t flags, void *out_xy, uint8_t *out_inf) {
+  if (!ctx || !powers_of_g || (count && (!coeffs || !n || !out_xy))) return PCGPU_E_BADARG;
+  size_t ways = count < (size_t)PCGPU_BATCH_WAYS ? count : (size_t)PCGPU_BATCH_WAYS;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    while (ctx->siblings.size() + 1 < ways) {
+      pcgpu_ctx *s = nullptr;
+      int rc = pcgpu_init(ctx->device, &s);
+      if (rc) return rc;
+      ctx->siblings.push_back(s);
+    }
+  }
+  const size_t psz = (powers_of_g->curve == PCGPU_BLS12_381 ? 6 : 4) * 16;
+  std::vector<int> rcs(ways, PCGPU_OK);
+  auto work = [&](size_t w) {
+    pcgpu_ctx *c = w == 0 ? ctx : ctx->siblings[w - 1];
+    for (size_t i = w; i < count; i += ways) {
+      int rc = pcgpu_kzg_commit(c, powers_of_g, coeffs[i], n[i], nullptr, nullptr, 0, flags, (char *)out_xy + i * psz,
+                                out_inf ? out_inf + i : nullptr);
+      if (rc) { rcs[w] = rc; return; }
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t w = 1; w < ways; w++) th.emplace_back(work, w);
+  if (ways) work(0);
+  for (auto &t : th) t.join();
+  for (int rc : rcs) if (rc) return rc;
+  return PCGPU_OK;
 }

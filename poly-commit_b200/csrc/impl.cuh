@@ -73,6 +73,7 @@ struct pcgpu_ctx {
   void *d_slots;    // 8 XYZZ result slots + 1 affine + err word, generously sized
   Prof prof;
   uint32_t *d_pow2[3] = {nullptr, nullptr, nullptr};  // fp_inv_gcd tables (Fq), per curve
+  std::vector<pcgpu_ctx *> siblings;  // extra contexts on the same device for pcgpu_kzg_commit_batch
   std::vector<NttPlan> ntt_plans;  // twiddle tables, cached per (curve, logn, direction)
   std::mutex mu;
 };

@@ -15,7 +15,7 @@ from tests import util
 from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_fr_vector_ops,  # noqa: F401
                                   test_kzg_commit_open, test_msm_edge_scalars, test_msm_infinity_bases,
                                   test_msm_partial_and_sum, test_msm_precomputed_tables, test_msm_vs_oracle,
-                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror)
+                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror, test_kzg_commit_batch)
 
 pytestmark = pytest.mark.gpu
 
@@ -287,4 +287,8 @@ def test_cfg5_shape_2p22(eng, pc):
     fc1, _ = orc.g1_mul(C.id, c1[0], orc.field_unop("orc_fr_from_mont", C.id, f.reshape(1, 4)))
     exp, _ = orc.g1_sum(C.id, np.stack([c0[0], fc1]))
     assert (cc[0] == exp).all()
+    # the batch entry point (4 polynomials in flight on sibling contexts) returns the same commitments
+    got, inf = eng.kzg_commit_batch(srs, [p0, p1, comb, p0, p1])
+    assert (got[0] == c0[0]).all() and (got[1] == c1[0]).all() and (got[2] == cc[0]).all() and (got[3] == c0[0]).all()
+    assert not inf.any()
     srs.release()

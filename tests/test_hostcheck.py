@@ -202,6 +202,23 @@ def test_msm_batch_shared_bases(eng, pc, cname):
     assert inf[2] == 1
 
 
+def test_kzg_commit_batch(eng, pc):
+    """pcgpu_kzg_commit_batch (cfg5's shape: many polynomials over one SRS, 4 in flight) == one commit per polynomial."""
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    powers = util.synthetic_srs(cname, 65, seed=9)
+    pg = eng.srs_register(C.id, powers)
+    polys = [util.rand_fr(cname, 65 - (i % 3), seed=300 + i, mont=True) for i in range(7)]
+    polys[2][:] = 0                                                        # a zero polynomial commits to the identity
+    got, inf = eng.kzg_commit_batch(pg, polys)
+    for i, p in enumerate(polys):
+        rc, exy, einf = orc.kzg_commit(C.id, powers, p)
+        assert rc == 0 and (got[i] == exy).all() and inf[i] == einf
+    with pytest.raises(pc.PcgpuError) as ei:
+        eng.kzg_commit_batch(pg, [util.rand_fr(cname, 80, seed=1, mont=True)])
+    assert ei.value.code == -6
+
+
 def test_marlin_pc_host_mirror(eng, pc):
     """marlin_pc.commit / open (mirror of marlin_pc/mod.rs:172-336) with and without degree bounds vs the oracle composed
     the same way: two_polys_degree_bound_single_query_test's shape (marlin_pc/mod.rs:720ff)."""

@@ -87,6 +87,17 @@ def main():
         ms = timeit(lambda: eng.msm(srs, x.data_ptr(), n=nm, flags=F | pc.SCALARS_MONT), reps=5)
         report(name, ms, 128 * nm, {"scalar_mults_per_s": round(nm / (ms / 1e3))})
         srs.release()
+    # cfg5 shape: batch of 8 degree-2^22 commits over one SRS (what each of 8 GPUs does for the 64-polynomial batch)
+    n5 = (1 << 22) + 1
+    pows5 = dev(orc.fr_powers_canonical(C.id, beta, n5))
+    bases5 = torch.empty((n5, 12), dtype=torch.int64, device="cuda")
+    eng.fixed_base_mul(C.id, orc.g1_generator(C.id), pows5.data_ptr(), n=n5, flags=F, out=bases5.data_ptr())
+    srs5 = eng.srs_register(C.id, bases5.data_ptr(), n=n5, flags=F | pc.SRS_PRECOMPUTE)
+    polys5 = [dev(util.rand_fr_fast(cname, n5, 40 + i)) for i in range(8)]
+    ms = timeit(lambda: eng.kzg_commit_batch(srs5, [(p.data_ptr(), n5) for p in polys5], flags=F), reps=2, warm=1)
+    report("cfg5 per-GPU share: 8 x KZG commit, degree 2^22, BLS12-381 (pcgpu_kzg_commit_batch)", ms, 8 * 128 * n5,
+           {"polys_per_s": round(8 / (ms / 1e3), 2), "scalar_mults_per_s": round(8 * n5 / (ms / 1e3))})
+    srs5.release(); del polys5, bases5, pows5
     # Hyrax cfg4: 2^11 rows x (2^11 + 1) over one com_key, BN254
     cn = "bn254"
     C2 = pyref.Curve(cn)
