@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 LOG_DEG = 20
 CURVE = "bls12_381"
 ALGO_BYTES_PER_SCALAR_MULT = 128  # 96 B affine base + 32 B scalar
-# dram__bytes_read.sum + dram__bytes_write.sum of one MsmAccumulateBody<Bls12381> launch, from the committed
-# ncu --set full capture profiles/r01_ncu_accumulate_bls12_381_2p20.txt (3.272687 GB + 52.435456 MB)
-NCU_TRAFFIC_BYTES = {20: 3272687000 + 52435456}
+# dram__bytes_read.sum + dram__bytes_write.sum of one MsmAffinePairBody<Bls12381, round 0> launch, from the committed
+# ncu --set full capture profiles/r01_final_ncu_prof_pair0_final.txt (5.710451 GB + 2.001377 GB)
+NCU_TRAFFIC_BYTES = {20: 5710451000 + 2001377000}
 
 
 def parse():
