@@ -110,15 +110,6 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_inputs(log_deg, n_polys, seed0=2):
-    """Seeded synthetic inputs: polynomials = 2^log_deg + 1 uniform Fr coefficients."""
-    from tests import util
-    n = (1 << log_deg) + 1
-    polys = [util.rand_fr_fast(CURVE, n, seed0 + i) for i in range(n_polys)]
-    z = util.rand_fr(CURVE, 1, seed=4, mont=True)[0]
-    return n, polys, z
-
-
 def oracle_step(orc, cid, bases, coeffs, z, nthreads=0):
     rc, cxy, cinf = orc.kzg_commit(cid, bases, coeffs, nthreads=nthreads)
     assert rc == 0

@@ -130,24 +130,6 @@ PCGPU_DEV void xyzz_add(XYZZ<C> &p, const XYZZ<C> &q) {
   p.zzz = fp_mul<Q>(fp_mul<Q>(p.zzz, q.zzz), PPP);
 }
 
-template <class C>
-PCGPU_DEV XYZZ<C> xyzz_neg(const XYZZ<C> &p) {
-  XYZZ<C> r = p;
-  r.y = fp_neg<typename C::Fq>(p.y);
-  return r;
-}
-
-// k * p for a small non-negative integer k (double-and-add, MSB first)
-template <class C>
-PCGPU_DEV XYZZ<C> xyzz_mul_small(const XYZZ<C> &p, uint32_t k) {
-  XYZZ<C> acc = XYZZ<C>::inf();
-  for (int i = 31; i >= 0; i--) {
-    acc = xyzz_dbl<C>(acc);
-    if ((k >> i) & 1) xyzz_add<C>(acc, p);
-  }
-  return acc;
-}
-
 // x = X/ZZ, y = Y/ZZZ with one inversion of ZZ*ZZZ
 template <class C>
 PCGPU_DEV Affine<C> xyzz_to_affine(const XYZZ<C> &p) {

@@ -39,12 +39,6 @@ struct FrFromMontBody {
   const uint32_t *in; uint32_t *out;
   PCGPU_KERNEL_DEV void operator()(size_t i) const { store_fr<R>(out, i, fp_from_mont<R>(load_fr<R>(in, i))); }
 };
-template <class R>
-struct FrToMontBody {
-  const uint32_t *in; uint32_t *out;
-  PCGPU_KERNEL_DEV void operator()(size_t i) const { store_fr<R>(out, i, fp_to_mont<R>(load_fr<R>(in, i))); }
-};
-
 // y[i] += c * x[i]
 template <class R>
 struct FrAxpyBody {

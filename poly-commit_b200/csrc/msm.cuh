@@ -5,16 +5,16 @@
 // with F::into_bigint (kzg10/mod.rs:463-470) fused into the digit pass when scalars arrive in
 // Montgomery form.
 //
-// Pipeline (one stream, no host round trip until the 1-point result):
+// Pipeline (one stream, no host round trip until the S*c bit-plane sums):
 //   1 count      thread/scalar : signed-digit recoding, histogram of (bucket set, |digit|)   [atomics]
 //   2 scan       exclusive prefix sum of the histogram -> bucket offsets
 //   3 scatter    thread/scalar : recompute digits, place (table group, base index, sign) by bucket
-//   4 tasks      split every bucket into tasks of <= L entries (bounds the longest serial chain
-//                whatever the scalar distribution), scan, fill task -> bucket map
-//   5 accumulate thread/task   : XYZZ mixed additions of the gathered affine bases  (DOMINANT)
-//   6 reduce     thread/segment: running-sum  sum_k (k+1) B_k  over a segment of buckets,
-//                then pairwise tree over segments
-//   7 final      Horner over the bucket sets (c doublings each) and conversion to affine
+//   4 pair rounds (msm_affine.cuh) R times: halve every bucket with batched-affine additions  (DOMINANT at large n)
+//   5 tasks      split what is left of every bucket into tasks of <= L points (bounds the longest serial
+//                chain whatever the scalar distribution), scan, fill task -> bucket map
+//   6 accumulate persistent kernel, dynamic task queue: XYZZ mixed additions
+//   7 reduce     bucket sums, bit-plane sums T_j = sum of buckets whose weight has bit j set, pairwise tree
+//   8 tail       (host, host_ec.hpp) sum_j 2^j T_j, Horner over the bucket sets, conversion to affine
 //
 // Window <-> table layout: window w = g*S + s uses table group g (bases pre-multiplied by
 // 2^(c*S*g) at SRS registration) and bucket set s.  S = W, G = 1 is the plain method on raw bases;
@@ -350,12 +350,6 @@ namespace pcgpu {
 // ---------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------
-struct MsmWorkspace {
-  uint32_t *counts, *offsets, *cursor, *ntasks, *task_off, *task_bucket, *entries, *scan_scratch, *err;
-  void *partial, *seg_out;
-  size_t max_tasks;
-};
-
 inline uint32_t ilog2_floor(uint64_t v) { uint32_t l = 0; while (v >>= 1) l++; return l; }
 
 // Window size for the plain (no precomputation) method.

@@ -37,7 +37,6 @@ inline std::atomic<uint64_t> &launch_counter() { static std::atomic<uint64_t> c{
 #ifdef PCGPU_EMUL
 // ------------------------------------------------------------------ host emulation (tests only)
 typedef void *stream_t;
-struct event_t { int dummy; };
 inline int dev_malloc(void **p, size_t bytes) { *p = ::malloc(bytes ? bytes : 1); return *p ? OK : E_OOM; }
 inline void dev_free(void *p) { ::free(p); }
 inline int dev_memset(void *p, int v, size_t bytes, stream_t) { memset(p, v, bytes); return OK; }
@@ -83,12 +82,6 @@ inline int launch_blocks(const Body &body, size_t nblocks, size_t smem_bytes, st
 #else
 // ------------------------------------------------------------------ CUDA (the product)
 typedef cudaStream_t stream_t;
-
-#define PCGPU_CUDA_TRY(expr)                         \
-  do {                                               \
-    cudaError_t _e = (expr);                         \
-    if (_e != cudaSuccess) return ::pcgpu::rt::map_cuda(_e); \
-  } while (0)
 
 inline int map_cuda(cudaError_t e) {
   if (e == cudaSuccess) return OK;
