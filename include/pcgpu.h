@@ -149,6 +149,13 @@ size_t pcgpu_ipa_len(const pcgpu_ipa *st);
 /* final_comm_key = comm_key[0], c = coeffs[0] (:713-720); releases the state. */
 int pcgpu_ipa_finish(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_key_xy, void *out_c);
 
+/* The linear-time step of InnerProductArgPC::check (ipa_pc/mod.rs:760-766): check_poly.compute_coeffs()
+ * (data_structures.rs:204-220; coeffs[idx] = product of challenges[i] over the set bits of idx, challenges[0] on the top
+ * bit) followed by cm_commit(comm_key, coeffs).  challenges: log_d Montgomery Fr (host); comm_key: >= 2^log_d bases.
+ * The caller compares the result with proof.final_comm_key. */
+int pcgpu_ipa_check_final_key(pcgpu_ctx *ctx, const pcgpu_srs *comm_key, const void *challenges, uint32_t log_d,
+                              void *out_xy, uint8_t *out_inf);
+
 /* ---- KZG10 fused prover calls ------------------------------------------------------------------ */
 /* KZG10::commit -- kzg10/mod.rs:157-210.  coeffs: n Montgomery Fr (low degree first; trailing zeros allowed and
  * ignored like DensePolynomial's truncation).  Hiding: pass gamma (powers_of_gamma_g) and n_blind > 0 blinding

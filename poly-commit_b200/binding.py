@@ -68,6 +68,7 @@ def _load(path):
         "pcgpu_ipa_begin": [_vp, ctypes.c_int, _vp, _sz, _vp, _sz, _vp, ctypes.c_uint32, ctypes.POINTER(_vp)],
         "pcgpu_ipa_round_lr": [_vp, _vp, _vp, _vp, _vp, _vp, _vp],
         "pcgpu_ipa_round_fold": [_vp, _vp, _vp, _vp],
+        "pcgpu_ipa_check_final_key": [_vp, _vp, _vp, ctypes.c_uint32, _vp, _vp],
         "pcgpu_ipa_finish": [_vp, _vp, _vp, _vp],
         "pcgpu_ntt": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
         "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
@@ -301,6 +302,15 @@ class Engine:
 
     def ipa_len(self, state):
         return int(self.lib.pcgpu_ipa_len(state))
+
+    def ipa_check_final_key(self, comm_key_srs, challenges):
+        """InnerProductArgPC::check's linear-time step: cm_commit(comm_key, check_poly.compute_coeffs())."""
+        challenges = _u64(challenges)
+        log_d = challenges.size // 4
+        out = np.zeros(2 * fq_limbs(comm_key_srs.curve), dtype=np.uint64)
+        inf = np.zeros(1, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_ipa_check_final_key(self.ctx, comm_key_srs.handle, _ptr(challenges), log_d, _ptr(out), _ptr(inf)))
+        return out, int(inf[0])
 
     def ipa_finish(self, curve, state):
         key, c = np.zeros(2 * fq_limbs(curve), dtype=np.uint64), np.zeros(4, dtype=np.uint64)

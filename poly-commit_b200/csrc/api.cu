@@ -340,3 +340,11 @@ extern "C" int pcgpu_kzg_commit_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of
   for (int rc : rcs) if (rc) return rc;
   return PCGPU_OK;
 }
+
+extern "C" int pcgpu_ipa_check_final_key(pcgpu_ctx *ctx, const pcgpu_srs *comm_key, const void *challenges, uint32_t log_d,
+                                         void *out_xy, uint8_t *out_inf) {
+  if (!ctx || !comm_key || (log_d && !challenges) || !out_xy) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(comm_key->curve, return ipa_check_final_key_impl<C>(ctx, comm_key, challenges, log_d, out_xy, out_inf));
+}

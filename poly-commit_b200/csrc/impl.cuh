@@ -617,6 +617,25 @@ int ipa_finish_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_key_xy, void 
   return rt::stream_sync(s);
 }
 
+template <class C>
+int ipa_check_final_key_impl(pcgpu_ctx *ctx, const pcgpu_srs *key, const void *challenges, uint32_t log_d, void *out_xy,
+                             uint8_t *out_inf) {
+  using R = typename C::Fr;
+  if (log_d > 26) return PCGPU_E_BADARG;
+  size_t n = (size_t)1 << log_d;
+  if (n > key->n) return PCGPU_E_LEN;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  if ((rc = ctx->stage.reserve(rt::Arena::pad(n * 32) + rt::Arena::pad((log_d + 1) * 32) + 4096))) return rc;
+  uint32_t *d_ch = ctx->stage.take<uint32_t>((log_d + 1) * 8), *d_co = ctx->stage.take<uint32_t>(n * 8);
+  if (log_d && (rc = rt::copy_h2d(d_ch, challenges, (size_t)log_d * 32, st))) return rc;
+  if ((rc = rt::launch<256>(FrCheckCoeffsBody<R>{d_ch, log_d, d_co}, n, st))) return rc;
+  host::HXYZZ<C> r;
+  if ((rc = msm_to_host<C>(ctx, key, 0, d_co, n, true, &r))) return rc;
+  host::to_affine<C>(r, out_xy, out_inf);
+  return PCGPU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // NTT
 // ---------------------------------------------------------------------------------------------
@@ -776,4 +795,5 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int ipa_begin_impl<C>(pcgpu_ctx *, const void *, size_t, const void *, size_t, const void *, uint32_t, pcgpu_ipa *); \
   EXT template int ipa_round_lr_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, void *, uint8_t *, void *, uint8_t *); \
   EXT template int ipa_round_fold_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, const void *); \
-  EXT template int ipa_finish_impl<C>(pcgpu_ctx *, pcgpu_ipa *, void *, void *);
+  EXT template int ipa_finish_impl<C>(pcgpu_ctx *, pcgpu_ipa *, void *, void *); \
+  EXT template int ipa_check_final_key_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, uint32_t, void *, uint8_t *);

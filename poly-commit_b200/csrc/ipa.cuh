@@ -38,4 +38,17 @@ struct G1FoldBody {
   }
 };
 
+// SuccinctCheckPolynomial::compute_coeffs (ipa_pc/data_structures.rs:204-220): coeffs[idx] = product of challenge_i over
+// the set bits of idx, challenge_1 on the top bit.  One thread per coefficient (<= log_d multiplications).
+template <class R>
+struct FrCheckCoeffsBody {
+  const uint32_t *challenges; uint32_t log_d; uint32_t *out;
+  PCGPU_KERNEL_DEV void operator()(size_t idx) const {
+    Fp<R> acc = Fp<R>::one();
+    for (uint32_t i = 1; i <= log_d; i++)
+      if ((idx >> (log_d - i)) & 1) acc = fp_mul<R>(acc, load_fr<R>(challenges, i - 1));
+    store_fr<R>(out, idx, acc);
+  }
+};
+
 }  // namespace pcgpu

@@ -57,3 +57,13 @@ def open_rounds(eng, curve, comm_key_xy, coeffs, point, h_prime_xy, round_challe
         eng.ipa_round_fold(st, _fr_mont(curve, round_challenge), _fr_mont(curve, inv))      # :691-708
     final_key, c = eng.ipa_finish(curve, st)
     return dict(l_vec=l_vec, r_vec=r_vec, final_comm_key=final_key, c=c, challenges=chals)
+
+
+def check_final_key(eng, curve, comm_key_xy, challenges):
+    """InnerProductArgPC::check's linear-time step (ipa_pc/mod.rs:760-766): the key the verifier recomputes from the round
+    challenges, cm_commit(vk.comm_key, check_poly.compute_coeffs()) -- must equal proof.final_comm_key."""
+    srs = eng.srs_register(curve, comm_key_xy)
+    ch = np.stack([_fr_mont(curve, int(c)) for c in challenges])
+    out = eng.ipa_check_final_key(srs, ch)
+    srs.release()
+    return out

@@ -227,6 +227,9 @@ def test_cfg3_ipa_open_2p18_pallas(eng, pc):
     assert C.fr_from_limbs(got["c"], True)[0] == c_exp
     fk = orc.msm(C.id, key, C.fr_to_limbs(s_ch, False))
     assert (got["final_comm_key"] == fk[0]).all()
+    # the verifier's linear-time step on the device (check_poly.compute_coeffs() + cm_commit, ipa_pc/mod.rs:760-766)
+    vk = ipa_pc.check_final_key(eng, C.id, key, ch)
+    assert (vk[0] == got["final_comm_key"]).all()
 
 
 def test_cpp_host_mirror(tmp_path):

@@ -392,6 +392,9 @@ def test_ipa_open_rounds(eng, pc, cname, n):
     for a, b in zip(got["l_vec"] + got["r_vec"], exp["l_vec"] + exp["r_vec"]):
         assert (a == b).all()
     assert (got["final_comm_key"] == exp["final_comm_key"]).all() and (got["c"] == exp["c"]).all()
+    # verifier side (ipa_pc/mod.rs:760-766): cm_commit(comm_key, check_poly.compute_coeffs()) == proof.final_comm_key
+    fk = ipa_pc.check_final_key(eng, C.id, key, got["challenges"])
+    assert fk[1] == 0 and (fk[0] == got["final_comm_key"]).all()
 
 
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
