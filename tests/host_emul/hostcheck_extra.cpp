@@ -26,6 +26,7 @@ static void mul_many(const uint32_t *a, const uint32_t *b, uint32_t *out, size_t
       case 4: r = fp_neg<P>(x); break;
       case 5: r = fp_inv<P>(x); break;
       case 8: r = fp_inv_gcd<P>(x, pow2_table<P>()); break;
+      case 9: r = mont_sqr<P>(x); break;
       case 6: if constexpr (mont_mul2_supported<P>()) r = mont_mul2<P>(x, y, y, fp_neg<P>(x)); else r = Fp<P>::zero(); break;  // x*y + y*(-x) = 0
       case 7: if constexpr (mont_mul2_supported<P>()) r = mont_mul2<P>(x, y, fp_add<P>(x, y), fp_sub<P>(y, x));
               else r = fp_add<P>(mont_mul<P>(x, y), mont_mul<P>(fp_add<P>(x, y), fp_sub<P>(y, x)));

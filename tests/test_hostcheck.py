@@ -46,7 +46,8 @@ def test_field_schedule_vs_bigint(hostcheck_path, cname, which, fid):
     A, B = _tol(va, n64), _tol(vb, n64)
     ops = [(0, lambda a, b: a * b * Rinv % mod), (1, lambda a, b: a * b * Rinv % mod), (2, lambda a, b: (a + b) % mod),
            (3, lambda a, b: (a - b) % mod), (4, lambda a, b: (-a) % mod), (6, lambda a, b: 0),
-           (7, lambda a, b: (a * b + (a + b) * (b - a)) * Rinv % mod)]   # 6, 7: sum of two products, one reduction
+           (7, lambda a, b: (a * b + (a + b) * (b - a)) * Rinv % mod),   # 6, 7: sum of two products, one reduction
+           (9, lambda a, b: a * a * Rinv % mod)]                          # dedicated squaring
     vp = ctypes.c_void_p
     for op, fn in ops:
         out = np.zeros_like(A)
