@@ -162,5 +162,23 @@ template <class C> inline HXYZZ<C> combine_bit_planes(const HXYZZ<C> *T, uint32_
   return acc;
 }
 
+// Two-level variant (large windows): per set the device hands back the planes of the column sums C (weights lo+1, bits_c
+// of them) followed by the planes of the row sums R (weights hi, bits_r):  set value = sum_j 2^j TC_j + 2^h * sum_j 2^j TR_j
+template <class C> inline HXYZZ<C> combine_bit_planes_2level(const HXYZZ<C> *T, uint32_t S, uint32_t c, uint32_t h) {
+  const uint32_t bits_c = h + 1, bits_r = c - 1 - h, per = bits_c + bits_r;
+  HXYZZ<C> acc = HXYZZ<C>::inf();
+  for (uint32_t s = S; s-- > 0;) {
+    const HXYZZ<C> *Ts = T + (size_t)s * per;
+    HXYZZ<C> vr = HXYZZ<C>::inf(), vc = HXYZZ<C>::inf();
+    for (uint32_t j = bits_r; j-- > 0;) { vr = pdbl<C>(vr); vr = padd<C>(vr, Ts[bits_c + j]); }
+    for (uint32_t k = 0; k < h; k++) vr = pdbl<C>(vr);
+    for (uint32_t j = bits_c; j-- > 0;) { vc = pdbl<C>(vc); vc = padd<C>(vc, Ts[j]); }
+    HXYZZ<C> v = padd<C>(vr, vc);
+    if (s + 1 < S) for (uint32_t k = 0; k < c; k++) acc = pdbl<C>(acc);
+    acc = padd<C>(acc, v);
+  }
+  return acc;
+}
+
 }  // namespace host
 }  // namespace pcgpu

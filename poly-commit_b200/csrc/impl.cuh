@@ -156,7 +156,10 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
   if (srs->groups > 1 && n >= SRS_PRECOMPUTE_MIN_N) {
     c = srs->c; groups = srs->groups;
     tables = (const uint32_t *)srs->d_folded; pt_words = aligned_pt_words<C>(); y_words = aligned_y_words<C>();
-  } else { c = msm_pick_c(n); groups = 1; }
+  } else {
+    c = msm_pick_c(n); groups = 1;
+    if (const char *e = getenv("PCGPU_MSM_C")) { int v = atoi(e); if (v >= 8 && v <= 22) c = (uint32_t)v; }   // tuning / test knob
+  }
   MsmGeom g = msm_geometry(n, c, groups, C::Fr::BITS, mont, srs->n, base_offset);
   g.pt_words = pt_words; g.y_words = y_words;
   int rc;
@@ -179,7 +182,7 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
   rc = msm_run<C>(tables, g, d_scalars, ctx->msm_arena, &d_planes, &stride, &d_err, st, ctx->prof,
                   ctx->d_pow2[C::ID]);
   if (rc) return rc;
-  size_t np = (size_t)g.S * g.c;
+  size_t np = (size_t)g.S * g.c;   // one-level: c planes per set; two-level: (h+1) + (c-1-h) = c planes per set as well
   std::vector<host::HXYZZ<C>> planes(np);
   static_assert(sizeof(host::HXYZZ<C>) == sizeof(XYZZ<C>), "host/device point layouts must agree");
   uint32_t herr = 0;
@@ -189,7 +192,8 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
   ctx->prof.collect();
   if (herr) return PCGPU_E_RANGE;
   auto t0 = std::chrono::steady_clock::now();
-  *out = host::combine_bit_planes<C>(planes.data(), g.S, g.c);
+  *out = g.h_split ? host::combine_bit_planes_2level<C>(planes.data(), g.S, g.c, g.h_split)
+                   : host::combine_bit_planes<C>(planes.data(), g.S, g.c);
   if (ctx->prof.on) {
     ctx->prof.ms[6] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     ctx->prof.cnt[6]++;

@@ -43,6 +43,8 @@ struct MsmGeom {
   uint64_t table_stride; // points per table group
   uint64_t base_off;     // first base used inside each group
   uint32_t affine_rounds; // batched-affine pairwise rounds before the XYZZ task kernel
+  uint32_t h_split;       // 0: one-level bit-plane reduction; else bucket index = hi * 2^h_split + lo and the weighted sum is
+                          // 2^h * sum_hi hi * R_hi + sum_lo (lo+1) * C_lo over row sums R and column sums C (large c)
   uint32_t pt_words;      // table record stride in 32-bit words (2N raw; 32 for 128-byte aligned BLS12-381 records)
   uint32_t y_words;       // offset of y inside a record, in words (N raw; 16 in the aligned BLS12-381 layout)
 };
@@ -313,21 +315,50 @@ struct MsmBucketSumBody {
   }
 };
 
+// planes[((s*nbits + j) * nseg) + q] = sum of vals[s*NBx + k], k in segment q, over the k whose weight (k + wofs) has bit j set
 template <class C>
 struct MsmBitPlaneBody {
-  MsmGeom g; const XYZZ<C> *buckets; XYZZ<C> *planes;  // planes[((s*c + j) * nseg) + q]
+  const XYZZ<C> *vals; XYZZ<C> *planes;
+  uint32_t NBx, nbits, wofs, seg_len, nseg;
   PCGPU_KERNEL_DEV void operator()(size_t t) const {
-    uint32_t q = (uint32_t)(t % g.nseg);
-    uint32_t j = (uint32_t)((t / g.nseg) % g.c);
-    uint32_t s = (uint32_t)(t / ((size_t)g.nseg * g.c));
-    uint32_t lo = q * g.seg_len;
-    uint32_t hi = lo + g.seg_len < g.NB ? lo + g.seg_len : g.NB;
+    uint32_t q = (uint32_t)(t % nseg);
+    uint32_t j = (uint32_t)((t / nseg) % nbits);
+    uint32_t s = (uint32_t)(t / ((size_t)nseg * nbits));
+    uint32_t lo = q * seg_len;
+    uint32_t hi = lo + seg_len < NBx ? lo + seg_len : NBx;
     XYZZ<C> acc = XYZZ<C>::inf();
     for (uint32_t k = lo; k < hi; k++) {
-      if (((k + 1) >> j) & 1) { XYZZ<C> p = load_xyzz<C>(buckets + (size_t)s * g.NB + k); xyzz_add<C>(acc, p); }
+      if (((k + wofs) >> j) & 1) { XYZZ<C> p = load_xyzz<C>(vals + (size_t)s * NBx + k); xyzz_add<C>(acc, p); }
     }
     store_xyzz<C>(planes + t, acc);
   }
+};
+
+// part[(s*cnt + i)*nq + q] = sum_{e < len} in[s*NB + base_mul*i + (q*len + e)*stride]      (row sums: base_mul = row length,
+// stride = 1; column sums: base_mul = 1, stride = row length)
+template <class C>
+struct MsmStrideSumBody {
+  const XYZZ<C> *in; XYZZ<C> *part;
+  uint32_t NB, cnt, per, base_mul, stride, len, nq;   // cnt outputs per set, `per` inputs per output
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    uint32_t q = (uint32_t)(t % nq);
+    uint32_t i = (uint32_t)((t / nq) % cnt);
+    uint32_t s = (uint32_t)(t / ((size_t)nq * cnt));
+    uint32_t e0 = q * len, e1 = e0 + len < per ? e0 + len : per;
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (uint32_t e = e0; e < e1; e++) {
+      XYZZ<C> p = load_xyzz<C>(in + (size_t)s * NB + (size_t)base_mul * i + (size_t)e * stride);
+      xyzz_add<C>(acc, p);
+    }
+    store_xyzz<C>(part + t, acc);
+  }
+};
+
+// out[i] = in[i * stride]
+template <class C>
+struct XyzzGatherBody {
+  const XYZZ<C> *in; XYZZ<C> *out; uint32_t stride;
+  PCGPU_KERNEL_DEV void operator()(size_t i) const { store_xyzz<C>(out + i, load_xyzz<C>(in + i * (size_t)stride)); }
 };
 
 template <class C>
@@ -377,8 +408,19 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
   g.scalar_bits = scalar_bits; g.scalars_mont = mont ? 1 : 0;
   g.table_stride = table_stride; g.base_off = base_off;
   g.affine_rounds = 0;
+  g.h_split = c > 17 ? (c - 1) / 2 : 0;
   g.pt_words = 0; g.y_words = 0;  // set by the caller (table_layout)
   return g;
+}
+
+// XYZZ scratch elements of the reduction stage (bit planes, and for the two-level mode the row/column partial sums)
+inline size_t msm_plane_scratch_elems(const MsmGeom &g) {
+  if (!g.h_split) return (size_t)g.S * g.c * g.nseg;
+  size_t cols = (size_t)1 << g.h_split, rows = g.NB >> g.h_split;
+  size_t part = (size_t)g.S * (rows * ((cols + 15) / 16) + cols * ((rows + 15) / 16));     // partial sums
+  size_t rc = (size_t)g.S * (rows + cols);                                                  // compacted R and C
+  size_t planes = (size_t)g.S * 32 * ((rows + 15) / 16 + (cols + 15) / 16);                 // bit planes of R and C
+  return part + rc + planes;
 }
 
 template <class C>
@@ -393,7 +435,7 @@ inline size_t msm_workspace_bytes(const MsmGeom &g) {
   b += rt::Arena::pad(64);
   b += rt::Arena::pad(max_tasks * sizeof(XYZZ<C>));
   b += rt::Arena::pad((size_t)g.TB * sizeof(XYZZ<C>));
-  b += rt::Arena::pad((size_t)g.S * g.c * g.nseg * sizeof(XYZZ<C>));
+  b += rt::Arena::pad(msm_plane_scratch_elems(g) * sizeof(XYZZ<C>)) + rt::Arena::pad((size_t)g.S * 2 * g.c * sizeof(XYZZ<C>));
   if (g.affine_rounds) {
     size_t bound0 = max_entries / 2 + g.TB + 1, bound1 = bound0 / 2 + g.TB + 1;
     b += 3 * rt::Arena::pad((g.TB + 2) * sizeof(uint32_t));
@@ -431,11 +473,12 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
   uint32_t *err = arena.take<uint32_t>(16);  // err[0]: scalar out of range; err[8]: accumulate task queue
   XYZZ<C> *partial = arena.take<XYZZ<C>>(max_tasks);
   XYZZ<C> *buckets = arena.take<XYZZ<C>>(g.TB);
-  XYZZ<C> *planes = arena.take<XYZZ<C>>((size_t)g.S * g.c * g.nseg);
+  XYZZ<C> *planes = arena.take<XYZZ<C>>(msm_plane_scratch_elems(g));
+  XYZZ<C> *plane_out = arena.take<XYZZ<C>>((size_t)g.S * 2 * g.c);   // compact plane sums handed to the host
   if (!counts || !offsets || !cursor || !ntasks || !task_off || !task_bucket || !entries || !scratch || !err || !partial ||
-      !buckets || !planes)
+      !buckets || !planes || !plane_out)
     return rt::E_OOM;
-  *d_err_out = err; *d_planes = planes; *plane_stride = g.nseg;
+  *d_err_out = err; *d_planes = plane_out; *plane_stride = 1;
 
   prof.begin(0, st);
   if ((rc = rt::dev_memset(counts, 0, (g.TB + 2) * sizeof(uint32_t), st))) return rc;
@@ -502,11 +545,39 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
 
   prof.begin(5, st);
   if ((rc = rt::launch<128>(MsmBucketSumBody<C>{task_off, partial, buckets}, g.TB, st))) return rc;
-  if ((rc = rt::launch<128>(MsmBitPlaneBody<C>{g, buckets, planes}, (size_t)g.S * g.c * g.nseg, st))) return rc;
-  for (uint32_t m = g.nseg; m > 1;) {
-    uint32_t half = (m + 1) / 2;
-    if ((rc = rt::launch<128>(MsmTreeAddBody<C>{planes, g.nseg, m, half}, (size_t)g.S * g.c * (m - half), st))) return rc;
-    m = half;
+  // weighted sum of `cnt` values per set (weights index + wofs, `nbits` bits) -> nbits plane sums per set at dst[s*dst_stride + j]
+  auto reduce_planes = [&](const XYZZ<C> *vals, uint32_t cnt, uint32_t wofs, uint32_t nbits, XYZZ<C> *scratch, XYZZ<C> *dst,
+                           uint32_t dst_stride) -> int {
+    uint32_t seg_len = 16, nseg = (cnt + seg_len - 1) / seg_len;
+    int r2;
+    if ((r2 = rt::launch<128>(MsmBitPlaneBody<C>{vals, scratch, cnt, nbits, wofs, seg_len, nseg}, (size_t)g.S * nbits * nseg, st))) return r2;
+    for (uint32_t m = nseg; m > 1;) {
+      uint32_t half = (m + 1) / 2;
+      if ((r2 = rt::launch<128>(MsmTreeAddBody<C>{scratch, nseg, m, half}, (size_t)g.S * nbits * (m - half), st))) return r2;
+      m = half;
+    }
+    for (uint32_t sset = 0; sset < g.S; sset++)   // compact: plane (s, j) sits at scratch[(s*nbits + j) * nseg]
+      if ((r2 = rt::launch<32>(XyzzGatherBody<C>{scratch + (size_t)sset * nbits * nseg, dst + (size_t)sset * dst_stride, nseg}, nbits, st))) return r2;
+    return rt::OK;
+  };
+  if (!g.h_split) {
+    if ((rc = reduce_planes(buckets, g.NB, 1u, g.c, planes, plane_out, g.c))) return rc;
+  } else {
+    // two-level: bucket k = hi * 2^h + lo.  R_hi = sum_lo B, C_lo = sum_hi B (plain sums), then
+    //   sum_k (k+1) B_k = 2^h * sum_hi hi * R_hi + sum_lo (lo+1) * C_lo      -> planes of C first (h+1 bits), then of R
+    const uint32_t h = g.h_split, cols = 1u << h, rows = g.NB >> h;
+    const uint32_t nq_r = (cols + 15) / 16, nq_c = (rows + 15) / 16;
+    XYZZ<C> *part_r = planes, *part_c = part_r + (size_t)g.S * rows * nq_r;
+    XYZZ<C> *Rv = part_c + (size_t)g.S * cols * nq_c, *Cv = Rv + (size_t)g.S * rows, *pl = Cv + (size_t)g.S * cols;
+    if ((rc = rt::launch<128>(MsmStrideSumBody<C>{buckets, part_r, g.NB, rows, cols, cols, 1u, 16u, nq_r}, (size_t)g.S * rows * nq_r, st))) return rc;
+    if ((rc = rt::launch<128>(MsmStrideSumBody<C>{buckets, part_c, g.NB, cols, rows, 1u, cols, 16u, nq_c}, (size_t)g.S * cols * nq_c, st))) return rc;
+    for (uint32_t m = nq_r; m > 1;) { uint32_t half = (m + 1) / 2; if ((rc = rt::launch<128>(MsmTreeAddBody<C>{part_r, nq_r, m, half}, (size_t)g.S * rows * (m - half), st))) return rc; m = half; }
+    for (uint32_t m = nq_c; m > 1;) { uint32_t half = (m + 1) / 2; if ((rc = rt::launch<128>(MsmTreeAddBody<C>{part_c, nq_c, m, half}, (size_t)g.S * cols * (m - half), st))) return rc; m = half; }
+    if ((rc = rt::launch<128>(XyzzGatherBody<C>{part_r, Rv, nq_r}, (size_t)g.S * rows, st))) return rc;
+    if ((rc = rt::launch<128>(XyzzGatherBody<C>{part_c, Cv, nq_c}, (size_t)g.S * cols, st))) return rc;
+    const uint32_t bits_c = h + 1, bits_r = g.c - 1 - h;
+    if ((rc = reduce_planes(Cv, cols, 1u, bits_c, pl, plane_out, bits_c + bits_r))) return rc;
+    if ((rc = reduce_planes(Rv, rows, 0u, bits_r, pl, plane_out + bits_c, bits_c + bits_r))) return rc;
   }
   prof.end(5, st);
   return rt::OK;

@@ -16,6 +16,7 @@ namespace pcgpu {
 enum : size_t { SRS_PRECOMPUTE_MIN_N = 1u << 12 };
 
 inline uint32_t srs_precompute_window(size_t n) {
+  if (const char *e = getenv("PCGPU_SRS_C")) { int v = atoi(e); if (v >= 8 && v <= 22) return (uint32_t)v; }   // tuning knob
   uint32_t lg = ilog2_floor(n ? n : 1);
   if (lg >= 18) return 16;
   if (lg >= 15) return 14;

@@ -15,7 +15,7 @@ from tests import util
 from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_fr_vector_ops,  # noqa: F401
                                   test_kzg_commit_open, test_msm_edge_scalars, test_msm_infinity_bases,
                                   test_msm_partial_and_sum, test_msm_precomputed_tables, test_msm_vs_oracle,
-                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror, test_kzg_commit_batch)
+                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror, test_kzg_commit_batch, test_msm_two_level_reduction)
 
 pytestmark = pytest.mark.gpu
 

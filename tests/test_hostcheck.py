@@ -153,6 +153,28 @@ def test_msm_batched_affine_rounds(eng, pc, rounds, monkeypatch):
     assert (got[0] == exp[0]).all()
 
 
+@pytest.mark.parametrize("c", [18, 19])
+def test_msm_two_level_reduction(eng, pc, c, monkeypatch):
+    """large windows (c > 17): the weighted bucket sum goes through row / column sums (msm.cuh, h_split) -- forced here through
+    the tuning knobs on the raw-base path and on window-folded tables."""
+    monkeypatch.setenv("PCGPU_MSM_C", str(c))
+    monkeypatch.setenv("PCGPU_SRS_C", str(c))
+    cname = "bn254"
+    C = pyref.Curve(cname)
+    n = 4200
+    bases = util.random_points(cname, n, seed=97)
+    sc = util.rand_fr(cname, n, seed=98, mont=False)
+    sc[5] = C.fr_to_limbs([C.r - 1], False)[0]; sc[6] = 0; sc[7] = C.fr_to_limbs([1 << (c - 1)], False)[0]   # top bucket of window 0
+    exp = orc.msm(C.id, bases, sc)
+    srs = eng.srs_register(C.id, bases[:60])
+    got = eng.msm(srs, sc[:60])
+    assert (got[0] == orc.msm(C.id, bases[:60], sc[:60])[0]).all()
+    if c == 18:
+        srs = eng.srs_register(C.id, bases, flags=pc.SRS_PRECOMPUTE)
+        got = eng.msm(srs, sc)
+        assert (got[0] == exp[0]).all()
+
+
 def test_msm_infinity_bases(eng):
     cname = "bn254"
     C = pyref.Curve(cname)
