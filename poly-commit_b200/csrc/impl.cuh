@@ -169,7 +169,7 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
     if ((rc = rt::resident_threads_occ<128, PAIR_MIN_BLOCKS, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
     size_t entries = (size_t)g.n * g.W, avg = entries / g.TB;
     uint32_t R = 0;
-    while (R < 8 && (avg >> R) >= 128 && (entries >> (R + 1)) >= 16 * Tmax) R++;
+    while (R < 8 && (avg >> R) >= 4 && (entries >> (R + 1)) >= 16 * Tmax) R++;
     if (const char *e = getenv("PCGPU_MSM_AFFINE_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= 12) R = (uint32_t)v; }
     g.affine_rounds = R;
   }

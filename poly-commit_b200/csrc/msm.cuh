@@ -304,14 +304,46 @@ struct MsmAccumulateBody {
 // (every stage is a plain sum, so the serial depth stays at chunk + log2(chunks) additions; the
 // c-term Horner combination  sum_j 2^j T[s][j]  and the final inversion run on the host, host_ec.hpp)
 // ---------------------------------------------------------------------------------------------
+enum { HEAVY_BUCKET_TASKS = 8, HEAVY_BLOCK = 128, HEAVY_GRID = 64 };
+
+// buckets[b] = sum of the bucket's task partials.  Buckets with more than HEAVY_BUCKET_TASKS partials (repeated scalars:
+// many coefficients equal to 1 or -1, or a short top window) are appended to a list and reduced by whole thread blocks.
 template <class C>
 struct MsmBucketSumBody {
-  const uint32_t *task_off; const XYZZ<C> *partial; XYZZ<C> *buckets;
+  const uint32_t *task_off; const XYZZ<C> *partial; XYZZ<C> *buckets; uint32_t *heavy_count; uint32_t *heavy_list;
   PCGPU_KERNEL_DEV void operator()(size_t b) const {
     uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+    if (t1 - t0 > HEAVY_BUCKET_TASKS) { heavy_list[rt::atomic_add(heavy_count, 1u)] = (uint32_t)b; return; }
     XYZZ<C> acc = XYZZ<C>::inf();
     for (uint32_t q = t0; q < t1; q++) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add<C>(acc, p); }
     store_xyzz<C>(buckets + b, acc);
+  }
+};
+
+// one thread block per heavy bucket (grid-strided over the list): strided partial sums, then a shared-memory tree
+template <class C>
+struct MsmHeavyBucketBody {
+  const uint32_t *task_off; const XYZZ<C> *partial; XYZZ<C> *buckets; const uint32_t *heavy_count; const uint32_t *heavy_list;
+  PCGPU_KERNEL_DEV void operator()(size_t blk, uint32_t *smem) const {
+    constexpr uint32_t WORDS = sizeof(XYZZ<C>) / 4;
+    XYZZ<C> *sh = reinterpret_cast<XYZZ<C> *>(smem);
+    const uint32_t nheavy = *heavy_count;
+    for (uint32_t hb = (uint32_t)blk; hb < nheavy; hb += HEAVY_GRID) {
+      const uint32_t b = heavy_list[hb], t0 = task_off[b], t1 = task_off[b + 1];
+      PCGPU_BLOCK_FOR(i, HEAVY_BLOCK) {
+        XYZZ<C> acc = XYZZ<C>::inf();
+        for (uint32_t q = t0 + i; q < t1; q += HEAVY_BLOCK) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add<C>(acc, p); }
+        sh[i] = acc;
+      }
+      PCGPU_BLOCK_SYNC();
+      for (uint32_t half = HEAVY_BLOCK / 2; half >= 1; half >>= 1) {
+        PCGPU_BLOCK_FOR(i, half) { XYZZ<C> x = sh[i], y = sh[i + half]; xyzz_add<C>(x, y); sh[i] = x; }
+        PCGPU_BLOCK_SYNC();
+      }
+      PCGPU_BLOCK_FOR(i, 1) { store_xyzz<C>(buckets + b, sh[0]); }
+      PCGPU_BLOCK_SYNC();
+    }
+    (void)WORDS;
   }
 };
 
@@ -544,7 +576,10 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
   prof.end(4, st);
 
   prof.begin(5, st);
-  if ((rc = rt::launch<128>(MsmBucketSumBody<C>{task_off, partial, buckets}, g.TB, st))) return rc;
+  if ((rc = rt::dev_memset(err + 12, 0, 4, st))) return rc;   // err[12]: number of heavy buckets
+  if ((rc = rt::launch<128>(MsmBucketSumBody<C>{task_off, partial, buckets, err + 12, cursor}, g.TB, st))) return rc;   // cursor[] is free again: heavy list
+  if ((rc = rt::launch_blocks<HEAVY_BLOCK>(MsmHeavyBucketBody<C>{task_off, partial, buckets, err + 12, cursor}, HEAVY_GRID,
+                                           HEAVY_BLOCK * sizeof(XYZZ<C>), st))) return rc;
   // weighted sum of `cnt` values per set (weights index + wofs, `nbits` bits) -> nbits plane sums per set at dst[s*dst_stride + j]
   auto reduce_planes = [&](const XYZZ<C> *vals, uint32_t cnt, uint32_t wofs, uint32_t nbits, XYZZ<C> *scratch, XYZZ<C> *dst,
                            uint32_t dst_stride) -> int {

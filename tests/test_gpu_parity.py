@@ -15,7 +15,7 @@ from tests import util
 from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_fr_vector_ops,  # noqa: F401
                                   test_kzg_commit_open, test_msm_edge_scalars, test_msm_infinity_bases,
                                   test_msm_partial_and_sum, test_msm_precomputed_tables, test_msm_vs_oracle,
-                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror, test_kzg_commit_batch, test_msm_two_level_reduction)
+                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror, test_kzg_commit_batch, test_msm_two_level_reduction, test_msm_heavy_buckets)
 
 pytestmark = pytest.mark.gpu
 
@@ -55,6 +55,28 @@ def test_msm_medium(eng, pc, cname, logn):
         srs = eng.srs_register(C.id, bases, flags=flags)
         got = eng.msm(srs, sc)
         assert got[1] == exp[1] and (got[0] == exp[0]).all(), (cname, logn, flags)
+        srs.release()
+
+
+def test_msm_repeated_scalars_2p18(eng, pc):
+    """2^18 coefficients of which 60 % are 1, -1 or 2 (heavy buckets of ~50 000 points in every window) plus 40 % uniform."""
+    cname, n = "bls12_381", 1 << 18
+    C = pyref.Curve(cname)
+    bases = gpu_srs(eng, cname, n, seed=9)
+    sc = util.rand_fr(cname, n, seed=62, mont=False)
+    kind = util.rng(63).integers(0, 10, size=n)
+    sc[kind < 2] = C.fr_to_limbs([1], False)[0]
+    sc[(kind >= 2) & (kind < 4)] = C.fr_to_limbs([C.r - 1], False)[0]
+    sc[(kind >= 4) & (kind < 6)] = C.fr_to_limbs([2], False)[0]
+    exp = orc.msm(C.id, bases, sc)
+    import time
+    for flags in (0, pc.SRS_PRECOMPUTE):
+        srs = eng.srs_register(C.id, bases, flags=flags)
+        t0 = time.perf_counter()
+        got = eng.msm(srs, sc)
+        dt = time.perf_counter() - t0
+        assert (got[0] == exp[0]).all()
+        assert dt < 0.5, f"heavy-bucket MSM took {dt:.3f}s"
         srs.release()
 
 

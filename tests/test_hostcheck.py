@@ -175,6 +175,23 @@ def test_msm_two_level_reduction(eng, pc, c, monkeypatch):
         assert (got[0] == exp[0]).all()
 
 
+@pytest.mark.parametrize("rounds", ["0", "2"])
+def test_msm_heavy_buckets(eng, pc, rounds, monkeypatch):
+    """repeated scalars (many coefficients equal to 1, -1 or one constant -- common in real witness polynomials) put
+    hundreds of points into single buckets: block-cooperative heavy-bucket reduction (MsmHeavyBucketBody)."""
+    monkeypatch.setenv("PCGPU_MSM_AFFINE_ROUNDS", rounds)
+    cname = "bn254"
+    C = pyref.Curve(cname)
+    n = 1500
+    bases = util.random_points(cname, n, seed=110)
+    vals = [1] * 500 + [C.r - 1] * 400 + [0x1234567890abcdef1234567890abcdef] * 450 + util.rand_fr_ints(cname, 150, 111)
+    sc = C.fr_to_limbs(vals, False)
+    srs = eng.srs_register(C.id, bases)
+    got = eng.msm(srs, sc)
+    exp = orc.msm(C.id, bases, sc)
+    assert got[1] == exp[1] and (got[0] == exp[0]).all()
+
+
 def test_msm_infinity_bases(eng):
     cname = "bn254"
     C = pyref.Curve(cname)
