@@ -87,6 +87,26 @@ def main():
         ms = timeit(lambda: eng.msm(srs, x.data_ptr(), n=nm, flags=F | pc.SCALARS_MONT), reps=5)
         report(name, ms, 128 * nm, {"scalar_mults_per_s": round(nm / (ms / 1e3))})
         srs.release()
+    # BASELINE.md second row: "witness-like" scalars (50 % zero / 25 % < 2^16 / 25 % uniform), and repeated small constants
+    srs = eng.srs_register(C.id, bases.data_ptr(), n=nm, flags=F | pc.SRS_PRECOMPUTE)
+    g = util.rng(3)
+    w = util.rand_fr(cname, nm, seed=3, mont=False)
+    kind = g.integers(0, 4, size=nm)
+    w[kind < 2] = 0
+    small = kind == 2
+    w[small, 1:] = 0
+    w[small, 0] &= np.uint64(0xFFFF)
+    dw = dev(w)
+    ms = timeit(lambda: eng.msm(srs, dw.data_ptr(), n=nm, flags=F), reps=5)
+    report("msm 2^20 witness-like scalars (50% zero, 25% < 2^16, 25% uniform)", ms, 128 * nm, {"scalar_mults_per_s": round(nm / (ms / 1e3))})
+    w2 = util.rand_fr(cname, nm, seed=4, mont=False)
+    kind = g.integers(0, 10, size=nm)
+    w2[kind < 3] = C.fr_to_limbs([1], False)[0]
+    w2[(kind >= 3) & (kind < 5)] = C.fr_to_limbs([C.r - 1], False)[0]
+    dw2 = dev(w2)
+    ms = timeit(lambda: eng.msm(srs, dw2.data_ptr(), n=nm, flags=F), reps=5)
+    report("msm 2^20 repeated scalars (30% = 1, 20% = -1, 50% uniform): heavy buckets", ms, 128 * nm, {"scalar_mults_per_s": round(nm / (ms / 1e3))})
+    srs.release(); del dw, dw2
     # cfg5 shape: batch of 8 degree-2^22 commits over one SRS (what each of 8 GPUs does for the 64-polynomial batch)
     n5 = (1 << 22) + 1
     pows5 = dev(orc.fr_powers_canonical(C.id, beta, n5))
