@@ -110,6 +110,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_threads():
+    """threads the CPU arm may use: every core this process is allowed on (torchrun exports OMP_NUM_THREADS=1, which
+    would otherwise cripple the OpenMP default)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def oracle_step(orc, cid, bases, coeffs, z, nthreads=0):
     rc, cxy, cinf = orc.kzg_commit(cid, bases, coeffs, nthreads=nthreads)
     assert rc == 0
@@ -139,7 +148,7 @@ def cpu_reference_run(args, log_deg, steps, warmup, budget_s):
     # like ark-ec's Rayon MSM the port parallelises over Pippenger windows only, so at most n_windows threads do work
     # (splitting the index range as well was tried: 8 slices x 17 windows on the 128-thread box ran 2x SLOWER -- every
     # slice pays its own 2^c-bucket reduction and the bucket arrays fall out of cache)
-    cores = min(orc.num_threads(), n_windows)
+    cores = min(host_threads(), n_windows)
     # SRS for the CPU run: random multiples of G (fixed-base batch mul on the host is the slow part, so the
     # base set is 2^14 distinct points tiled -- MSM cost does not depend on the base values)
     tile = 1 << 14
@@ -151,7 +160,7 @@ def cpu_reference_run(args, log_deg, steps, warmup, budget_s):
         bases = np.tile(pts, (reps, 1))[:n]
         coeffs = util.rand_fr_fast(CURVE, n, 7)
         t0 = time.perf_counter()
-        oracle_step(orc, C.id, bases, coeffs, z)
+        oracle_step(orc, C.id, bases, coeffs, z, nthreads=host_threads())
         return time.perf_counter() - t0
 
     # probe at 1/16 size to choose the sample
@@ -171,7 +180,7 @@ def cpu_reference_run(args, log_deg, steps, warmup, budget_s):
         run(n_s)
     times = [run(n_s) for _ in range(steps)]
     t = sum(times) / len(times) * scale
-    sample += f"; OpenMP over the {n_windows} Pippenger windows ({orc.num_threads()} host threads available)"
+    sample += f"; OpenMP over the {n_windows} Pippenger windows ({host_threads()} host threads available)"
     return {"value": 1.0 / t, "unit": "polys/s", "cores": cores, "kind": "port", "sample": sample,
             "ms_per_step": t * 1e3, "msm_scalar_mults_per_s": 2 * n_full / t}
 
