@@ -1,0 +1,40 @@
+#!/usr/bin/env python3
+"""Wall-clock of the InnerProductArgPC::open halving loop (cfg3: Pallas, 2^18) through the device-resident round API,
+with a per-phase split (l/r MSMs + inner products vs folds)."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import pkgload
+pc = pkgload.load()
+from poly_commit_b200 import ipa_pc
+from oracle import orc, pyref
+from tests import util
+
+def main():
+    eng = pc.Engine(0)
+    cname = "pallas"; C = pyref.Curve(cname); logn = 18; n = 1 << logn
+    beta = util.rand_fr(cname, 1, 1001, mont=True)[0]
+    key = eng.fixed_base_mul(C.id, orc.g1_generator(C.id), orc.fr_powers_canonical(C.id, beta, n))
+    h_prime = util.random_points(cname, 1, seed=41)[0]
+    coeffs = util.rand_fr_fast(cname, n, seed=42)
+    point = util.rand_fr(cname, 1, seed=43, mont=True)[0]
+    ipa_pc.open_rounds(eng, C.id, key, coeffs, point, h_prime, 1)   # warm-up
+    t0 = time.perf_counter()
+    st = eng.ipa_begin(C.id, key, coeffs, point)
+    t_begin = time.perf_counter() - t0
+    t_lr = t_fold = 0.0
+    rc = 7
+    while eng.ipa_len(st) > 1:
+        t1 = time.perf_counter(); l, r = eng.ipa_round_lr(C.id, st, h_prime); t_lr += time.perf_counter() - t1
+        rc = ipa_pc.compute_random_oracle_challenge(C.id, int(rc).to_bytes(32, "little") + l.tobytes() + r.tobytes())
+        inv = pow(rc, -1, C.r)
+        t1 = time.perf_counter(); eng.ipa_round_fold(st, ipa_pc._fr_mont(C.id, rc), ipa_pc._fr_mont(C.id, inv)); t_fold += time.perf_counter() - t1
+    eng.ipa_finish(C.id, st)
+    tot = time.perf_counter() - t0
+    print(json.dumps({"workload": "IPA open halving loop, Pallas, 2^18, 18 rounds (host buffers in, device-resident rounds)",
+                      "total_ms": round(tot * 1e3, 2), "begin_upload_ms": round(t_begin * 1e3, 2),
+                      "lr_msm_ip_ms": round(t_lr * 1e3, 2), "folds_ms": round(t_fold * 1e3, 2)}))
+
+if __name__ == "__main__":
+    main()
