@@ -131,6 +131,17 @@ int pcgpu_fr_row_mul(pcgpu_ctx *ctx, int curve, const void *v, const void *m, si
  * includes the 1/N factor).  1 <= logn <= 22.  out: 2^logn elements. */
 int pcgpu_ntt(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in, uint32_t logn, uint32_t flags, void *out);
 
+/* Multi-GPU building block ("NTT shards by the four-step row/column split"): N = N1 * N2 with
+ * N1 = 2^m1, N2 = 2^m2 from pcgpu_ntt_split (m2 = 0 means the transform is a single block pass and does not shard).
+ * All pointers are DEVICE pointers.
+ *   which = 1: columns n2 in [lo, lo+count) of the zero-padded input `in` (n_in elements, natural order)
+ *              -> out[k1 * count + (n2 - lo)]   (N1 x count, step-2 twiddles applied)
+ *   which = 2: rows k1 in [lo, lo+count) given as in[(k1 - lo) * N2 + n2] -> out[k2 * count + (k1 - lo)] = X[k1 + N1 k2]
+ * Between the two passes the ranks exchange blocks with an all-to-all (poly_commit_b200.sharded.ShardedNtt). */
+int pcgpu_ntt_split(uint32_t logn, uint32_t *m1, uint32_t *m2);
+int pcgpu_ntt_pass(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, int which, size_t lo, size_t count,
+                   const void *in, size_t n_in, void *out);
+
 /* ---- InnerProductArgPC::open halving loop, device-resident (ipa_pc/mod.rs:636-711) ------------------------- */
 typedef struct pcgpu_ipa pcgpu_ipa;
 /* Upload the committer key (n = d+1 affine points, n a power of two) and the combined polynomial's coefficients

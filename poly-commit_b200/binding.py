@@ -70,6 +70,8 @@ def _load(path):
         "pcgpu_ipa_round_fold": [_vp, _vp, _vp, _vp],
         "pcgpu_ipa_check_final_key": [_vp, _vp, _vp, ctypes.c_uint32, _vp, _vp],
         "pcgpu_ipa_finish": [_vp, _vp, _vp, _vp],
+        "pcgpu_ntt_split": [ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)],
+        "pcgpu_ntt_pass": [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _sz, _sz, _vp, _sz, _vp],
         "pcgpu_ntt": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
         "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
@@ -278,6 +280,16 @@ class Engine:
             out = np.zeros((1 << logn, 4), dtype=np.uint64)
         self._ck(self.lib.pcgpu_ntt(self.ctx, curve, _ptr(coeffs), n_in, logn, flags | (NTT_INVERSE if inverse else 0), _ptr(out)))
         return out
+
+    def ntt_split(self, logn):
+        m1, m2 = ctypes.c_uint32(), ctypes.c_uint32()
+        self._ck(self.lib.pcgpu_ntt_split(logn, ctypes.byref(m1), ctypes.byref(m2)))
+        return m1.value, m2.value
+
+    def ntt_pass(self, curve, logn, which, lo, count, in_ptr, n_in, out_ptr, inverse=False):
+        """one four-step pass on a slice of its batches; in_ptr / out_ptr are DEVICE pointers (ints)"""
+        self._ck(self.lib.pcgpu_ntt_pass(self.ctx, curve, logn, NTT_INVERSE if inverse else 0, which, lo, count, _ptr(in_ptr), n_in,
+                                         _ptr(out_ptr)))
 
     # ---- IPA halving loop (device-resident state) ----
     def ipa_begin(self, curve, comm_key_xy, coeffs, point, n=None, flags=0):

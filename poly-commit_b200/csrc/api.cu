@@ -348,3 +348,17 @@ extern "C" int pcgpu_ipa_check_final_key(pcgpu_ctx *ctx, const pcgpu_srs *comm_k
   SET_DEVICE(ctx);
   DISPATCH_CURVE(comm_key->curve, return ipa_check_final_key_impl<C>(ctx, comm_key, challenges, log_d, out_xy, out_inf));
 }
+
+extern "C" int pcgpu_ntt_split(uint32_t logn, uint32_t *m1, uint32_t *m2) {
+  if (!m1 || !m2 || !ntt_supported(logn)) return PCGPU_E_BADARG;
+  ntt_split(logn, m1, m2);
+  return PCGPU_OK;
+}
+
+extern "C" int pcgpu_ntt_pass(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, int which, size_t lo, size_t count,
+                              const void *in, size_t n_in, void *out) {
+  if (!ctx || !out || (n_in && !in)) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(curve, return ntt_pass_impl<C>(ctx, logn, flags, which, lo, count, in, n_in, out));
+}

@@ -677,6 +677,30 @@ int ntt_impl(pcgpu_ctx *ctx, const void *in, size_t n_in, uint32_t logn, uint32_
   return rc;
 }
 
+template <class C>
+int ntt_pass_impl(pcgpu_ctx *ctx, uint32_t logn, uint32_t flags, int which, size_t lo, size_t count, const void *in, size_t n_in,
+                  void *out) {
+  using R = typename C::Fr;
+  if (!ntt_supported(logn) || logn > (uint32_t)R::TWO_ADICITY || (which != 1 && which != 2)) return PCGPU_E_BADARG;
+  uint32_t m1, m2;
+  ntt_split(logn, &m1, &m2);
+  if (m2 == 0) return PCGPU_E_BADARG;
+  const size_t lim = which == 1 ? ((size_t)1 << m2) : ((size_t)1 << m1);
+  if (lo > lim || count > lim - lo) return PCGPU_E_LEN;
+  rt::stream_t st = ctx->stream;
+  int rc, inverse = (flags & PCGPU_NTT_INVERSE) ? 1 : 0;
+  const NttPlan *plan = nullptr;
+  for (const NttPlan &p : ctx->ntt_plans) if (p.curve == C::ID && p.logn == logn && p.inverse == inverse) plan = &p;
+  if (!plan) {
+    NttPlan p;
+    if ((rc = ntt_build_plan<R>(p, C::ID, logn, inverse, st))) return rc;
+    ctx->ntt_plans.push_back(p);
+    plan = &ctx->ntt_plans.back();
+  }
+  if (count && (rc = ntt_run_pass<R>(*plan, which, lo, count, (const uint32_t *)in, n_in, (uint32_t *)out, st))) return rc;
+  return rt::stream_sync(st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // device self-test of the field layer
 // ---------------------------------------------------------------------------------------------
@@ -800,4 +824,5 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int ipa_round_lr_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, void *, uint8_t *, void *, uint8_t *); \
   EXT template int ipa_round_fold_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, const void *); \
   EXT template int ipa_finish_impl<C>(pcgpu_ctx *, pcgpu_ipa *, void *, void *); \
-  EXT template int ipa_check_final_key_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, uint32_t, void *, uint8_t *);
+  EXT template int ipa_check_final_key_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, uint32_t, void *, uint8_t *); \
+  EXT template int ntt_pass_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, int, size_t, size_t, const void *, size_t, void *);

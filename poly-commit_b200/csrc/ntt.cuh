@@ -78,6 +78,7 @@ struct NttBlockBody {
   const uint32_t *tw;                       // w_M^j, j < M/2
   const uint32_t *lo, *hi; int step2;       // step-2 twiddle w_N^(i * batch)
   const uint32_t *scale;                    // optional final factor
+  uint64_t batch_off;                       // global index of local batch 0 (sharded passes); enters the step-2 twiddle only
   PCGPU_KERNEL_DEV void operator()(size_t batch, uint32_t *smem) const {
     const uint32_t M = 1u << m;
     PCGPU_BLOCK_FOR(i, M) {
@@ -108,7 +109,7 @@ struct NttBlockBody {
 #pragma unroll
       for (int l = 0; l < 8; l++) v.l[l] = smem[l * M + i];
       if (step2) {
-        uint64_t e = (uint64_t)i * batch;
+        uint64_t e = (uint64_t)i * (batch + batch_off);
         if (e) v = fp_mul<R>(v, fp_mul<R>(load_fr<R>(hi, e >> NTT_LO_BITS), load_fr<R>(lo, e & ((1u << NTT_LO_BITS) - 1))));
       }
       if (scale) v = fp_mul<R>(v, load_fr<R>(scale, 0));
@@ -147,14 +148,31 @@ template <class R>
 inline int ntt_run(const NttPlan &p, const uint32_t *in, size_t n_in, uint32_t *out, uint32_t *tmp, rt::stream_t st) {
   const uint64_t N1 = (uint64_t)1 << p.m1, N2 = (uint64_t)1 << p.m2;
   if (p.m2 == 0) {
-    NttBlockBody<R> b{in, out, p.m1, 1, 0, 1, 0, n_in, p.tw1, p.lo, p.hi, 0, p.scale};
+    NttBlockBody<R> b{in, out, p.m1, 1, 0, 1, 0, n_in, p.tw1, p.lo, p.hi, 0, p.scale, 0};
     return rt::launch_blocks<256>(b, 1, (size_t)N1 * 32, st);
   }
-  NttBlockBody<R> b1{in, tmp, p.m1, N2, 1, N2, 1, n_in, p.tw1, p.lo, p.hi, 1, nullptr};
+  NttBlockBody<R> b1{in, tmp, p.m1, N2, 1, N2, 1, n_in, p.tw1, p.lo, p.hi, 1, nullptr, 0};
   int rc = rt::launch_blocks<256>(b1, N2, (size_t)N1 * 32, st);
   if (rc) return rc;
-  NttBlockBody<R> b2{tmp, out, p.m2, 1, N2, N1, 1, N1 * N2, p.tw2, p.lo, p.hi, 0, p.scale};
+  NttBlockBody<R> b2{tmp, out, p.m2, 1, N2, N1, 1, N1 * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0};
   return rt::launch_blocks<256>(b2, N1, (size_t)N2 * 32, st);
+}
+
+// One pass of the four-step transform on a slice of its batches -- the building block of the multi-GPU NTT:
+//   pass 1: columns n2 in [lo, lo+count) of the full (zero-padded) input -> local matrix out[k1 * count + (n2 - lo)]
+//           (N1 x count, step-2 twiddles applied);  the ranks then exchange blocks (all-to-all) so that each owns whole rows
+//   pass 2: rows k1 in [lo, lo+count), given contiguously as in[(k1 - lo) * N2 + n2] -> out[k2 * count + (k1 - lo)]
+//           (natural-order element k1 + N1 k2; the caller gathers and interleaves)
+template <class R>
+inline int ntt_run_pass(const NttPlan &p, int which, uint64_t lo, uint64_t count, const uint32_t *in, size_t n_in, uint32_t *out,
+                        rt::stream_t st) {
+  const uint64_t N1 = (uint64_t)1 << p.m1, N2 = (uint64_t)1 << p.m2;
+  if (which == 1) {
+    NttBlockBody<R> b{in + 8 * lo, out, p.m1, N2, 1, count, 1, n_in > lo ? n_in - lo : 0, p.tw1, p.lo, p.hi, 1, nullptr, lo};
+    return rt::launch_blocks<256>(b, count, (size_t)N1 * 32, st);
+  }
+  NttBlockBody<R> b{in, out, p.m2, 1, N2, count, 1, count * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0};
+  return rt::launch_blocks<256>(b, count, (size_t)N2 * 32, st);
 }
 
 }  // namespace pcgpu

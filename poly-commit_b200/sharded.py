@@ -56,3 +56,48 @@ class ShardedMsm:
         part = self.eng.msm_partial(self.srs, scalars[lo:hi], n=hi - lo, flags=flags)
         parts = all_gather_bytes(part, self.dist, self.device)
         return self.eng.g1_sum_xyzz(self.curve, np.concatenate(parts))
+
+
+class ShardedNtt:
+    """Four-step NTT over the ranks of a process group: rank g transforms the columns n2 of its slice
+    (pass 1, step-2 twiddles fused), an all-to-all hands every rank whole rows k1, pass 2 transforms them, an all-gather
+    assembles the natural-order output on every rank.  `xp` abstracts where buffers live: torch CUDA tensors with NCCL on
+    GPUs; plain CPU tensors with gloo in the host-emulation tests ("device" pointers are then host pointers)."""
+
+    def __init__(self, engine, curve, logn, dist, device=None):
+        self.eng, self.curve, self.logn, self.dist, self.device = engine, curve, logn, dist, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.m1, self.m2 = engine.ntt_split(logn)
+        if self.m2 == 0:
+            raise ValueError("transform too small to shard (single block pass)")
+        self.N1, self.N2 = 1 << self.m1, 1 << self.m2
+        if self.N1 % self.world or self.N2 % self.world:
+            raise ValueError("world size must divide both factors")
+
+    def forward(self, coeffs, inverse=False):
+        """coeffs: (n_in, 4) uint64 (the full input on every rank) -> (2^logn, 4) uint64 natural-order output on every rank."""
+        import torch
+        W, N1, N2 = self.world, self.N1, self.N2
+        cols, rows = N2 // W, N1 // W
+        dev = self.device if self.device is not None else torch.device("cpu")
+        x = torch.from_numpy(np.ascontiguousarray(coeffs, dtype=np.uint64).view(np.int64).reshape(-1, 4).copy()).to(dev)
+        n_in = x.shape[0]
+        # the engine launches on its own stream and synchronises it before returning; torch / NCCL work in between runs on
+        # torch's current stream, so drain that before handing pointers to the engine
+        sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == "cuda" else (lambda: None)
+        sync()
+        a = torch.empty((N1, cols, 4), dtype=torch.int64, device=dev)                   # local A[k1][n2 - lo]
+        self.eng.ntt_pass(self.curve, self.logn, 1, self.rank * cols, cols, x.data_ptr(), n_in, a.data_ptr(), inverse)
+        # all-to-all: block r of my rows (k1 in rank r's range) goes to rank r
+        send = a.reshape(W, rows, cols, 4).contiguous()
+        recv = torch.empty_like(send)
+        self.dist.all_to_all_single(recv.view(-1), send.view(-1))
+        # recv[src][k1_local][n2_local] -> rows[k1_local][src * cols + n2_local]
+        rowbuf = recv.permute(1, 0, 2, 3).contiguous().reshape(rows, N2, 4)
+        out_local = torch.empty((N2, rows, 4), dtype=torch.int64, device=dev)           # [k2][k1_local]
+        sync()
+        self.eng.ntt_pass(self.curve, self.logn, 2, self.rank * rows, rows, rowbuf.data_ptr(), rows * N2, out_local.data_ptr(), inverse)
+        gathered = [torch.empty_like(out_local) for _ in range(W)]
+        self.dist.all_gather(gathered, out_local)
+        full = torch.stack(gathered, dim=0).permute(1, 0, 2, 3).contiguous()            # [k2][r][k1_local] = natural order
+        return full.reshape(N1 * N2, 4).cpu().numpy().view(np.uint64)

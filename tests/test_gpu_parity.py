@@ -180,6 +180,36 @@ def test_ntt_large(eng, cname, logn):
     assert (back[:n_in] == x).all() and not back[n_in:].any()
 
 
+@pytest.mark.parametrize("cname,logn,world", [("bls12_381", 20, 4), ("bn254", 14, 2)])
+def test_ntt_passes_sharded_on_one_gpu(eng, cname, logn, world):
+    """pcgpu_ntt_pass (the building block of sharded.ShardedNtt): run every rank's slice of both passes on one
+    device, do the all-to-all as a tensor permutation, and compare with the single-call transform."""
+    import torch
+    C = pyref.Curve(cname)
+    m1, m2 = eng.ntt_split(logn)
+    N1, N2 = 1 << m1, 1 << m2
+    cols, rows = N2 // world, N1 // world
+    n_in = (1 << logn) - 77
+    x = util.rand_fr_fast(cname, n_in, seed=410 + logn)
+    dev = torch.device("cuda", 0)
+    xd = torch.from_numpy(x.view(np.int64).copy()).to(dev)
+    a = [torch.empty((N1, cols, 4), dtype=torch.int64, device=dev) for _ in range(world)]
+    torch.cuda.synchronize()
+    for r in range(world):
+        eng.ntt_pass(C.id, logn, 1, r * cols, cols, xd.data_ptr(), n_in, a[r].data_ptr())
+    outs = []
+    for r in range(world):
+        rowbuf = torch.cat([a[s][r * rows:(r + 1) * rows] for s in range(world)], dim=1).contiguous()   # [k1_local][n2]
+        o = torch.empty((N2, rows, 4), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        eng.ntt_pass(C.id, logn, 2, r * rows, rows, rowbuf.data_ptr(), rows * N2, o.data_ptr())
+        outs.append(o)
+    got = torch.stack(outs, 0).permute(1, 0, 2, 3).contiguous().reshape(-1, 4).cpu().numpy().view(np.uint64)
+    assert (got == eng.ntt(C.id, x, logn)).all()
+    with pytest.raises(Exception):
+        eng.ntt_pass(C.id, logn, 1, N2 - 1, 2, xd.data_ptr(), n_in, a[0].data_ptr())
+
+
 def test_cfg4_hyrax_commit_rows(eng, pc):
     """BASELINE.json cfg4: Hyrax, 22 variables, BN254 -- 2^11 Pedersen row commitments over one com_key (+ h * r_i)
     (hyrax/mod.rs:233-242).  Row randomness is an INPUT (the reference draws it from thread_rng, :237-238, so parity is

@@ -50,6 +50,15 @@ def _worker(rank, world, port, lib_path, q):
     for i in polys:
         rc, exy, _ = orc.kzg_commit(C.id, powers, util.rand_fr("bls12_381", 33, seed=200 + i, mont=True))
         ok &= bool((total[i] == exy).all())
+    # four-step NTT sharded over the ranks with an all-to-all between the passes (host emulation: device ptr == host ptr)
+    for cname, logn, n_in in (("bls12_381", 12, 4000), ("bn254", 13, 8192)):
+        C = pyref.Curve(cname)
+        x = util.rand_fr(cname, n_in, seed=9, mont=True)
+        sn = sharded.ShardedNtt(eng, C.id, logn, dist)
+        got = sn.forward(x)
+        ok &= bool((got == orc.fr_ntt(C.id, x, logn)).all())
+        back = sn.forward(got, inverse=True)
+        ok &= bool((back[:n_in] == x).all() and not back[n_in:].any())
     q.put((rank, ok))
     dist.destroy_process_group()
 

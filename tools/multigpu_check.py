@@ -53,6 +53,21 @@ def main():
             ok = bool((got[0] == exp[0]).all() and got[1] == exp[1])
             res[f"sharded_msm_2p{logn}"] = {"ok": ok, "ms_per_msm_host_buffers": round(dt * 1e3, 3), "world": world,
                                             "scalar_mults_per_s": round(n / dt)}
+    # four-step NTT sharded over the ranks (NCCL all-to-all between the passes) against the single-GPU transform
+    for logn in (16, 22):
+        x = util.rand_fr_fast(cname, (1 << logn) - 3, seed=5)
+        sn = sharded.ShardedNtt(eng, C.id, logn, dist, device=torch.device("cuda", local))
+        got_n = sn.forward(x)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        got_n = sn.forward(x)
+        torch.cuda.synchronize(); dist.barrier()
+        dt = time.perf_counter() - t0
+        exp_n = eng.ntt(C.id, x, logn)
+        okn = torch.tensor([int(bool((got_n == exp_n).all()))], device="cuda")
+        dist.all_reduce(okn, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            res[f"sharded_ntt_2p{logn}"] = {"ok": bool(okn.item()), "ms_host_buffers": round(dt * 1e3, 3), "world": world}
     # every rank must hold the same result
     h = torch.tensor([int(got[0][0] & np.uint64(0x7FFFFFFF))], device="cuda")
     hs = [torch.zeros_like(h) for _ in range(world)]
