@@ -46,7 +46,8 @@ enum {
   PCGPU_E_LEN = -4,    /* base_offset + n exceeds the registered bases (msm() returns Err(len) in ark-ec) */
   PCGPU_E_RANGE = -5,  /* a canonical scalar is >= 2^255 (2^254 for BN254): not a reduced field element */
   PCGPU_E_DEGREE = -6, /* Error::TooManyCoefficients, kzg10/mod.rs:392-402 */
-  PCGPU_E_HIDING = -7  /* Error::HidingBoundToolarge, kzg10/mod.rs:404-422 */
+  PCGPU_E_HIDING = -7, /* Error::HidingBoundToolarge, kzg10/mod.rs:404-422 */
+  PCGPU_E_INVALID = -8 /* SerializationError::{InvalidData, UnexpectedFlags}: a wire-format element failed to decode / validate */
 };
 
 /* flags */
@@ -55,7 +56,9 @@ enum {
   PCGPU_DEVICE_PTRS = 2u,    /* bulk array arguments are device pointers (results stay host pointers) */
   PCGPU_SRS_PRECOMPUTE = 4u, /* srs_register: also store 2^(c*k)-multiples of the bases (window folding) */
   PCGPU_NTT_INVERSE = 8u,    /* pcgpu_ntt: ifft instead of fft */
-  PCGPU_SRS_COMB = 16u       /* srs_register: build fixed-base comb tables for pcgpu_msm_batch (shared-base batches) */
+  PCGPU_SRS_COMB = 16u,      /* srs_register: build fixed-base comb tables for pcgpu_msm_batch (shared-base batches) */
+  PCGPU_WIRE_COMPRESSED = 32u,   /* g1_serialize / g1_deserialize: Compress::Yes (x + flag bits) instead of Compress::No */
+  PCGPU_WIRE_NO_VALIDATE = 64u   /* g1_deserialize: Validate::No (skip the on-curve and subgroup checks) */
 };
 
 /* ---- context ---------------------------------------------------------------------------------- */
@@ -108,6 +111,23 @@ int pcgpu_msm_batch(pcgpu_ctx *ctx, const pcgpu_srs *srs, const void *scalars, s
  * (an identity result is written as x = y = 0).  With PCGPU_DEVICE_PTRS scalars and out_xy are device pointers. */
 int pcgpu_g1_fixed_base_mul(pcgpu_ctx *ctx, int curve, const void *base_xy, const void *scalars, size_t n, uint32_t flags,
                             void *out_xy);
+
+/* ---- G1 wire formats ------------------------------------------------
+ * The bytes CanonicalSerialize / CanonicalDeserialize produce for the G1Affine elements of kzg10::Powers
+ * (kzg10/data_structures.rs:142-177), UniversalParams.powers_of_g (:57-112), Commitment (:315-328) and Proof.w (:479-495).
+ * The encodings come from un-vendored crates (ark-serialize / ark-ec 0.5.0; ark-bls12-381 0.5.0's ZCash form) and are
+ * restated from their published behaviour -- see poly-commit_b200/csrc/wire.cuh for the byte layouts.
+ * pcgpu_g1_wire_size: bytes per point (BLS12-381 48 / 96, BN254 32 / 64, Pallas 33 / 65), 0 for an unknown curve.
+ * pcgpu_g1_serialize: n affine points (Montgomery x||y + infinity bytes, inf may be NULL) -> n * wire_size bytes.
+ * pcgpu_g1_deserialize: the inverse; decompression (one square root in Fq per point) and, unless PCGPU_WIRE_NO_VALIDATE,
+ *   Valid::check (on curve, prime-order subgroup) run on the device.  On PCGPU_E_INVALID *first_bad (may be NULL) receives
+ *   the index of the first offending element and *reason 1 = unexpected flags, 2 = coordinate >= p, 3 = not on the curve
+ *   (no square root), 4 = not in the subgroup; the outputs of offending elements are zeroed.
+ * With PCGPU_DEVICE_PTRS the point / byte / inf arrays are device pointers. */
+size_t pcgpu_g1_wire_size(int curve, uint32_t flags);
+int pcgpu_g1_serialize(pcgpu_ctx *ctx, int curve, const void *xy, const uint8_t *inf, size_t n, uint32_t flags, uint8_t *out_bytes);
+int pcgpu_g1_deserialize(pcgpu_ctx *ctx, int curve, const uint8_t *bytes, size_t n, uint32_t flags, void *out_xy, uint8_t *out_inf,
+                         size_t *first_bad, int *reason);
 
 /* ---- Fr vector work around the MSM (all elements Montgomery) ----------------------------------- */
 /* F::into_bigint over a slice -- convert_to_bigints, kzg10/mod.rs:463-470 */

@@ -7,7 +7,8 @@ import numpy as np
 
 BLS12_381, BN254, PALLAS = 0, 1, 2
 CURVES = {"bls12_381": BLS12_381, "bn254": BN254, "pallas": PALLAS}
-SCALARS_MONT, DEVICE_PTRS, SRS_PRECOMPUTE, NTT_INVERSE, SRS_COMB = 1, 2, 4, 8, 16
+SCALARS_MONT, DEVICE_PTRS, SRS_PRECOMPUTE, NTT_INVERSE, SRS_COMB, WIRE_COMPRESSED, WIRE_NO_VALIDATE = 1, 2, 4, 8, 16, 32, 64
+E_INVALID = -8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -24,6 +25,15 @@ class PcgpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"pcgpu error {code}: {msg}")
         self.code = code
+
+
+class WireError(PcgpuError):
+    """SerializationError from g1_deserialize: `index` of the first offending element and `reason`
+    (1 unexpected flags, 2 coordinate >= p, 3 not on the curve, 4 not in the prime-order subgroup)."""
+
+    def __init__(self, code, msg, index, reason):
+        super().__init__(code, f"{msg} (element {index}, reason {reason})")
+        self.index, self.reason = index, reason
 
 
 _sz = ctypes.c_size_t
@@ -43,6 +53,8 @@ def _load(path):
     lib.pcgpu_srs_curve.argtypes = [_vp]
     lib.pcgpu_ipa_len.restype = _sz
     lib.pcgpu_ipa_len.argtypes = [_vp]
+    lib.pcgpu_g1_wire_size.restype = _sz
+    lib.pcgpu_g1_wire_size.argtypes = [ctypes.c_int, ctypes.c_uint32]
     lib.pcgpu_launch_count.restype = ctypes.c_uint64
     lib.pcgpu_launch_count.argtypes = []
     sigs = {
@@ -70,6 +82,9 @@ def _load(path):
         "pcgpu_ipa_round_fold": [_vp, _vp, _vp, _vp],
         "pcgpu_ipa_check_final_key": [_vp, _vp, _vp, ctypes.c_uint32, _vp, _vp],
         "pcgpu_ipa_finish": [_vp, _vp, _vp, _vp],
+        "pcgpu_g1_serialize": [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_uint32, _vp],
+        "pcgpu_g1_deserialize": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint32, _vp, _vp, ctypes.POINTER(_sz),
+                                 ctypes.POINTER(ctypes.c_int)],
         "pcgpu_ntt_split": [ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)],
         "pcgpu_ntt_pass": [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _sz, _sz, _vp, _sz, _vp],
         "pcgpu_ntt": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
@@ -280,6 +295,39 @@ class Engine:
             out = np.zeros((1 << logn, 4), dtype=np.uint64)
         self._ck(self.lib.pcgpu_ntt(self.ctx, curve, _ptr(coeffs), n_in, logn, flags | (NTT_INVERSE if inverse else 0), _ptr(out)))
         return out
+
+    # ---- G1 wire formats (ark-serialize CanonicalSerialize / CanonicalDeserialize of G1Affine) ----
+    def g1_wire_size(self, curve, compressed=True):
+        return int(self.lib.pcgpu_g1_wire_size(curve, WIRE_COMPRESSED if compressed else 0))
+
+    def g1_serialize(self, curve, xy, inf=None, compressed=True):
+        """n affine points (Montgomery x||y, optional infinity bytes) -> (n, wire_size) uint8"""
+        xy = _u64(xy)
+        n = xy.size // (2 * fq_limbs(curve))
+        inf = None if inf is None else np.ascontiguousarray(inf, dtype=np.uint8)
+        out = np.zeros((n, self.g1_wire_size(curve, compressed)), dtype=np.uint8)
+        self._ck(self.lib.pcgpu_g1_serialize(self.ctx, curve, _ptr(xy), _ptr(inf), n, WIRE_COMPRESSED if compressed else 0, _ptr(out)))
+        return out
+
+    def g1_deserialize(self, curve, data, n=None, compressed=True, validate=True):
+        """bytes -> ((n, 2*limbs) uint64 Montgomery x||y, (n,) uint8 infinity); raises WireError like SerializationError"""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else data,
+                                    dtype=np.uint8).reshape(-1)
+        sz = self.g1_wire_size(curve, compressed)
+        if n is None:
+            n = data.size // sz
+        if data.size < n * sz:
+            raise ValueError("byte buffer shorter than n elements")
+        xy = np.zeros((n, 2 * fq_limbs(curve)), dtype=np.uint64)
+        inf = np.zeros(n, dtype=np.uint8)
+        bad, reason = _sz(0), ctypes.c_int(0)
+        flags = (WIRE_COMPRESSED if compressed else 0) | (0 if validate else WIRE_NO_VALIDATE)
+        rc = self.lib.pcgpu_g1_deserialize(self.ctx, curve, _ptr(data), n, flags, _ptr(xy), _ptr(inf), ctypes.byref(bad),
+                                           ctypes.byref(reason))
+        if rc == E_INVALID:
+            raise WireError(rc, self.lib.pcgpu_strerror(rc).decode(), int(bad.value), int(reason.value))
+        self._ck(rc)
+        return xy, inf
 
     def ntt_split(self, logn):
         m1, m2 = ctypes.c_uint32(), ctypes.c_uint32()

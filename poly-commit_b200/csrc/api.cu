@@ -18,6 +18,7 @@ extern "C" const char *pcgpu_strerror(int code) {
     case PCGPU_E_RANGE: return "canonical scalar out of range (not a reduced field element)";
     case PCGPU_E_DEGREE: return "TooManyCoefficients: polynomial degree too large for the powers";
     case PCGPU_E_HIDING: return "HidingBoundToolarge: blinding polynomial too large for powers_of_gamma_g";
+    case PCGPU_E_INVALID: return "SerializationError: wire-format element failed to decode or validate";
     default: return "unknown error";
   }
 }
@@ -361,4 +362,30 @@ extern "C" int pcgpu_ntt_pass(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return ntt_pass_impl<C>(ctx, logn, flags, which, lo, count, in, n_in, out));
+}
+
+extern "C" size_t pcgpu_g1_wire_size(int curve, uint32_t flags) {
+  const bool comp = (flags & PCGPU_WIRE_COMPRESSED) != 0;
+  switch (curve) {
+    case PCGPU_BLS12_381: return wire_size<Bls12381>(comp);
+    case PCGPU_BN254: return wire_size<Bn254>(comp);
+    case PCGPU_PALLAS: return wire_size<Pallas>(comp);
+    default: return 0;
+  }
+}
+
+extern "C" int pcgpu_g1_serialize(pcgpu_ctx *ctx, int curve, const void *xy, const uint8_t *inf, size_t n, uint32_t flags,
+                                  uint8_t *out_bytes) {
+  if (!ctx || (n && (!xy || !out_bytes))) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(curve, return g1_serialize_impl<C>(ctx, xy, inf, n, flags, out_bytes));
+}
+
+extern "C" int pcgpu_g1_deserialize(pcgpu_ctx *ctx, int curve, const uint8_t *bytes, size_t n, uint32_t flags, void *out_xy,
+                                    uint8_t *out_inf, size_t *first_bad, int *reason) {
+  if (!ctx || (n && (!bytes || !out_xy || !out_inf))) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(curve, return g1_deserialize_impl<C>(ctx, bytes, n, flags, out_xy, out_inf, first_bad, reason));
 }

@@ -17,6 +17,7 @@
 #include <chrono>
 #include "msm.cuh"
 #include "srs.cuh"
+#include "wire.cuh"
 
 using namespace pcgpu;
 
@@ -702,6 +703,72 @@ int ntt_pass_impl(pcgpu_ctx *ctx, uint32_t logn, uint32_t flags, int which, size
 }
 
 // ---------------------------------------------------------------------------------------------
+// G1 wire formats (wire.cuh)
+// ---------------------------------------------------------------------------------------------
+template <class C>
+int g1_serialize_impl(pcgpu_ctx *ctx, const void *xy, const uint8_t *inf, size_t n, uint32_t flags, uint8_t *out) {
+  constexpr size_t PT = 2 * C::Fq::N * 4;
+  rt::stream_t st = ctx->stream;
+  const int comp = (flags & PCGPU_WIRE_COMPRESSED) ? 1 : 0;
+  const size_t sz = wire_size<C>(comp != 0);
+  int rc;
+  if (n == 0) return PCGPU_OK;
+  if (flags & PCGPU_DEVICE_PTRS) {
+    if ((rc = rt::launch<128>(G1EncodeBody<C>{(const uint32_t *)xy, inf, out, comp}, n, st))) return rc;
+    return rt::stream_sync(st);
+  }
+  if ((rc = ctx->stage.reserve(rt::Arena::pad(n * PT) + rt::Arena::pad(n) + rt::Arena::pad(n * sz) + 4096))) return rc;
+  uint32_t *d_xy = ctx->stage.take<uint32_t>(n * PT / 4);
+  uint8_t *d_inf = inf ? ctx->stage.take<uint8_t>(n) : nullptr;
+  uint8_t *d_out = ctx->stage.take<uint8_t>(n * sz);
+  if ((rc = rt::copy_h2d(d_xy, xy, n * PT, st))) return rc;
+  if (inf && (rc = rt::copy_h2d(d_inf, inf, n, st))) return rc;
+  if ((rc = rt::launch<128>(G1EncodeBody<C>{d_xy, d_inf, d_out, comp}, n, st))) return rc;
+  if ((rc = rt::copy_d2h(out, d_out, n * sz, st))) return rc;
+  return rt::stream_sync(st);
+}
+
+template <class C>
+int g1_deserialize_impl(pcgpu_ctx *ctx, const uint8_t *bytes, size_t n, uint32_t flags, void *out_xy, uint8_t *out_inf,
+                        size_t *first_bad, int *reason) {
+  constexpr size_t PT = 2 * C::Fq::N * 4;
+  rt::stream_t st = ctx->stream;
+  const int comp = (flags & PCGPU_WIRE_COMPRESSED) ? 1 : 0, validate = (flags & PCGPU_WIRE_NO_VALIDATE) ? 0 : 1;
+  const size_t sz = wire_size<C>(comp != 0);
+  const bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  int rc;
+  if (n == 0) return PCGPU_OK;
+  if ((rc = ctx->stage.reserve((dev ? 0 : rt::Arena::pad(n * PT) + rt::Arena::pad(n) + rt::Arena::pad(n * sz)) + rt::Arena::pad(n) + 4096)))
+    return rc;
+  uint8_t *d_status = ctx->stage.take<uint8_t>(n);
+  const uint8_t *d_bytes = bytes;
+  uint32_t *d_xy = (uint32_t *)out_xy;
+  uint8_t *d_inf = out_inf;
+  if (!dev) {
+    uint8_t *tb = ctx->stage.take<uint8_t>(n * sz);
+    d_xy = ctx->stage.take<uint32_t>(n * PT / 4);
+    d_inf = ctx->stage.take<uint8_t>(n);
+    if ((rc = rt::copy_h2d(tb, bytes, n * sz, st))) return rc;
+    d_bytes = tb;
+  }
+  if ((rc = rt::launch<128>(G1DecodeBody<C>{d_bytes, d_xy, d_inf, d_status, comp, validate}, n, st))) return rc;
+  std::vector<uint8_t> status(n);
+  if ((rc = rt::copy_d2h(status.data(), d_status, n, st))) return rc;
+  if (!dev) {
+    if ((rc = rt::copy_d2h(out_xy, d_xy, n * PT, st))) return rc;
+    if ((rc = rt::copy_d2h(out_inf, d_inf, n, st))) return rc;
+  }
+  if ((rc = rt::stream_sync(st))) return rc;
+  for (size_t i = 0; i < n; i++)
+    if (status[i]) {
+      if (first_bad) *first_bad = i;
+      if (reason) *reason = status[i];
+      return PCGPU_E_INVALID;
+    }
+  return PCGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // device self-test of the field layer
 // ---------------------------------------------------------------------------------------------
 template <class P>
@@ -825,4 +892,6 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int ipa_round_fold_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, const void *); \
   EXT template int ipa_finish_impl<C>(pcgpu_ctx *, pcgpu_ipa *, void *, void *); \
   EXT template int ipa_check_final_key_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, uint32_t, void *, uint8_t *); \
-  EXT template int ntt_pass_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, int, size_t, size_t, const void *, size_t, void *);
+  EXT template int ntt_pass_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, int, size_t, size_t, const void *, size_t, void *); \
+  EXT template int g1_serialize_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, uint8_t *); \
+  EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *);

@@ -15,7 +15,9 @@ from tests import util
 from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_fr_vector_ops,  # noqa: F401
                                   test_kzg_commit_open, test_msm_edge_scalars, test_msm_infinity_bases,
                                   test_msm_partial_and_sum, test_msm_precomputed_tables, test_msm_vs_oracle,
-                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror, test_kzg_commit_batch, test_msm_two_level_reduction, test_msm_heavy_buckets)
+                                  test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror, test_kzg_commit_batch, test_msm_two_level_reduction, test_msm_heavy_buckets,
+                                  test_wire_roundtrip_vs_oracle, test_wire_bls12_381_generator_known_answer,
+                                  test_wire_rejects_like_the_oracle, test_wire_kzg_containers)
 
 pytestmark = pytest.mark.gpu
 
@@ -208,6 +210,28 @@ def test_ntt_passes_sharded_on_one_gpu(eng, cname, logn, world):
     assert (got == eng.ntt(C.id, x, logn)).all()
     with pytest.raises(Exception):
         eng.ntt_pass(C.id, logn, 1, N2 - 1, 2, xd.data_ptr(), n_in, a[0].data_ptr())
+
+
+@pytest.mark.parametrize("cname,logn", [("bls12_381", 18), ("pallas", 16)])
+def test_wire_srs_ingest_large(eng, pc, cname, logn):
+    """SRS ingestion at size: serialize 2^k powers, read them back compressed with validation
+    (square root + subgroup check per point on the device) and uncompressed; sampled elements against the Python
+    restatement; a corrupted element deep in the file is located exactly."""
+    C = pyref.Curve(cname)
+    n = 1 << logn
+    g = gpu_srs(eng, cname, n, seed=70)
+    for compressed in (True, False):
+        blob = eng.g1_serialize(C.id, g, None, compressed)
+        idx = np.unique(np.concatenate([[0, 1, n - 1], util.rng(71).integers(0, n, size=40)]))
+        assert blob[idx].tobytes() == pyref.g1_serialize(C, C.points_from_limbs(g[idx]), compressed)
+        back, inf = eng.g1_deserialize(C.id, blob, n, compressed, validate=True)
+        assert (back == g).all() and not inf.any()
+    bad = blob.copy()
+    k = n - 12345
+    bad[k, 3] ^= 0x55                                           # uncompressed y no longer matches x
+    with pytest.raises(pc.binding.WireError) as ei:
+        eng.g1_deserialize(C.id, bad, n, False, validate=True)
+    assert ei.value.index == k and ei.value.reason in (pyref.WIRE_NOT_ON_CURVE, pyref.WIRE_NOT_CANONICAL)
 
 
 def test_cfg4_hyrax_commit_rows(eng, pc):

@@ -488,3 +488,162 @@ def test_kzg_commit_open(eng, pc, cname):
     zero = np.zeros((4, 4), dtype=np.uint64)
     c0 = eng.kzg_commit(pg, zero)
     assert c0[1] == 1
+
+
+# ---- G1 wire formats -----------------------------------------------------------------------------
+def _wire_points(cname, n, seed):
+    C = pyref.Curve(cname)
+    xy = util.random_points(cname, n, seed)
+    pts = C.points_from_limbs(xy)
+    # edge elements: identity, generator, -generator
+    pts[0] = None
+    pts[1] = C.g
+    pts[2] = C.neg(C.g)
+    xy2, inf = C.points_to_limbs(pts)
+    return C, pts, xy2, inf
+
+
+@pytest.mark.parametrize("cname", ["bls12_381", "bn254", "pallas"])
+@pytest.mark.parametrize("compressed", [True, False])
+def test_wire_roundtrip_vs_oracle(eng, cname, compressed):
+    """serialize == the Python restatement byte for byte; deserialize(serialize(P)) == P with validation on
+    (decompression square root, sign selection, on-curve and subgroup checks all exercised)."""
+    C, pts, xy, inf = _wire_points(cname, 40, seed=61)
+    assert eng.g1_wire_size(C.id, compressed) == pyref.wire_size(C, compressed)
+    got = eng.g1_serialize(C.id, xy, inf, compressed)
+    exp = pyref.g1_serialize(C, pts, compressed)
+    assert got.tobytes() == exp
+    back_xy, back_inf = eng.g1_deserialize(C.id, exp, len(pts), compressed, validate=True)
+    assert (back_inf == inf).all() and (back_xy == xy).all()
+    # the oracle's reader agrees with the device's on the same bytes
+    assert pyref.g1_deserialize(C, got.tobytes(), len(pts), compressed) == pts
+    # device convention: (0, 0) without an infinity byte is the identity as well
+    assert eng.g1_serialize(C.id, xy, None, compressed).tobytes() == exp
+
+
+def test_wire_bls12_381_generator_known_answer(eng):
+    """the one published byte vector for this path: the ZCash compressed encoding of the BLS12-381 G1 generator"""
+    C = pyref.Curve("bls12_381")
+    kat = bytes.fromhex("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac58"
+                        "6c55e83ff97a1aeffb3af00adb22c6bb")
+    xy, inf = C.points_to_limbs([C.g])
+    assert eng.g1_serialize(C.id, xy, inf, True).tobytes() == kat
+    back, binf = eng.g1_deserialize(C.id, kat, 1, True)
+    assert (back == xy).all() and not binf.any()
+    assert eng.g1_serialize(C.id, xy, np.array([1], dtype=np.uint8), True).tobytes() == bytes([0xC0]) + bytes(47)
+
+
+@pytest.mark.parametrize("cname", ["bls12_381", "bn254", "pallas"])
+def test_wire_rejects_like_the_oracle(eng, pc, cname):
+    """every failure class of CanonicalDeserialize: unexpected flags, non-canonical coordinate, x with no point, off-curve
+    uncompressed point, (BLS12-381) on-curve point outside the prime-order subgroup -- the device reports the same first
+    offending index and reason as the Python restatement, and Validate::No accepts what only validation rejects."""
+    C, pts, xy, inf = _wire_points(cname, 12, seed=62)
+    p = C.p
+    zc = cname == "bls12_381"
+
+    def both(data, n, compressed, validate=True):
+        try:
+            exp = pyref.g1_deserialize(C, data, n, compressed, validate)
+            exp_err = None
+        except pyref.WireError as e:
+            exp, exp_err = None, (e.index, e.reason)
+        try:
+            got = eng.g1_deserialize(C.id, data, n, compressed, validate)
+            got_err = None
+        except pc.binding.WireError as e:
+            got, got_err = None, (e.index, e.reason)
+            assert e.code == pc.binding.E_INVALID
+        assert got_err == exp_err, (cname, compressed, got_err, exp_err)
+        if exp is not None:
+            gx, gi = got
+            ex, ei = C.points_to_limbs(exp)
+            assert (gx == ex).all() and (gi == ei).all()
+        return exp_err
+
+    for compressed in (True, False):
+        good = bytearray(pyref.g1_serialize(C, pts, compressed))
+        sz = pyref.wire_size(C, compressed)
+        assert both(bytes(good), len(pts), compressed) is None
+        # (1) flags
+        bad = bytearray(good)
+        if zc:
+            bad[5 * sz] ^= 0x80                              # compression bit contradicts the mode
+        else:
+            bad[6 * sz - 1] |= 0xC0                          # YIsNegative and PointAtInfinity together
+        assert both(bytes(bad), len(pts), compressed) == (5, pyref.WIRE_BAD_FLAGS)
+        # (2) x = p (not canonical)
+        bad = bytearray(good)
+        if zc:
+            enc = bytearray(p.to_bytes(48, "big")); enc[0] |= 0x80 if compressed else 0
+            bad[3 * sz:3 * sz + 48] = enc
+        else:
+            nb = (p.bit_length() + (2 if compressed else 0) + 7) // 8
+            bad[3 * sz:3 * sz + nb] = p.to_bytes(nb, "little")
+        assert both(bytes(bad), len(pts), compressed) == (3, pyref.WIRE_NOT_CANONICAL)
+        # (3) no point with that x / y does not match x
+        x = 1
+        while pyref.fq_sqrt(C, x ** 3 + C.b) is not None:
+            x += 1
+        bad = bytearray(good)
+        if compressed:
+            one = pyref.g1_serialize(C, [(x, 0)], True)      # y only feeds the sign flag
+        else:
+            one = pyref.g1_serialize(C, [(pts[4][0], (pts[4][1] + 1) % p)], False)
+        bad[4 * sz:5 * sz] = one
+        assert both(bytes(bad), len(pts), compressed) == (4, pyref.WIRE_NOT_ON_CURVE)
+        if not compressed:
+            assert both(bytes(bad), len(pts), compressed, validate=False) is None
+        # (4) on the curve, outside the subgroup (only BLS12-381 has a cofactor)
+        if zc:
+            Q = pyref.curve_point_from_x_search(C, 1000)
+            assert C.on_curve(Q) and C.mul(C.r, Q) is not None
+            h = (0xd201000000010000 + 1) ** 2 // 3                      # cofactor (z - 1)^2 / 3 with z = -0xd201000000010000
+            assert C.mul(h * C.r, Q) is None
+            small = C.mul(C.r * (h // (0xd201000000010000 + 1)), Q)     # order divides z - 1: the [x]P == P branch
+            cleared = C.mul(h, Q)                                        # in the subgroup again
+            for k, pt in ((7, Q), (8, small)):
+                if pt is None:
+                    continue
+                bad = bytearray(good)
+                bad[k * sz:(k + 1) * sz] = pyref.g1_serialize(C, [pt], compressed)
+                assert both(bytes(bad), len(pts), compressed) == (k, pyref.WIRE_NOT_IN_SUBGROUP)
+                assert both(bytes(bad), len(pts), compressed, validate=False) is None
+            ok = bytearray(good)
+            ok[7 * sz:8 * sz] = pyref.g1_serialize(C, [cleared], compressed)
+            assert both(bytes(ok), len(pts), compressed) is None
+
+
+def test_wire_kzg_containers(eng, pc):
+    """Powers (two Vec<G1Affine>), Commitment and Proof framing around the element codec (kzg10/data_structures.rs:142-177,
+    :315-328, :479-495): bytes equal the restated ark-serialize layout and read back to the same SRS."""
+    import struct
+    from poly_commit_b200 import wire
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    g = util.synthetic_srs(cname, 33, seed=5)
+    gamma = util.random_points(cname, 3, seed=6)
+    for compressed in (True, False):
+        blob = wire.powers_serialize(eng, C.id, g, gamma, compressed)
+        exp = (struct.pack("<Q", 33) + pyref.g1_serialize(C, C.points_from_limbs(g), compressed)
+               + struct.pack("<Q", 3) + pyref.g1_serialize(C, C.points_from_limbs(gamma), compressed))
+        assert blob == exp
+        (g2, gi), (h2, hi) = wire.powers_deserialize(eng, C.id, blob, compressed)
+        assert (g2 == g).all() and (h2 == gamma).all() and not gi.any() and not hi.any()
+        with pytest.raises(ValueError):
+            wire.powers_deserialize(eng, C.id, blob[:-1], compressed)
+    # a commitment and a proof produced by the prover path
+    srs = eng.srs_register(C.id, g)
+    poly = util.rand_fr(cname, 33, seed=7, mont=True)
+    comm, cinf = eng.kzg_commit(srs, poly)
+    cb = wire.commitment_serialize(eng, C.id, comm, cinf)
+    assert cb == pyref.g1_serialize(C, C.points_from_limbs(comm.reshape(1, -1), [cinf]), True)
+    back, binf = wire.commitment_deserialize(eng, C.id, cb)
+    assert (back == comm).all() and binf == bool(cinf)
+    z = util.rand_fr(cname, 1, seed=8, mont=True)[0]
+    w, winf, _ = eng.kzg_open(srs, poly, z)
+    pb = wire.proof_serialize(eng, C.id, w, winf, None)
+    assert pb == pyref.g1_serialize(C, C.points_from_limbs(w.reshape(1, -1), [winf]), True) + b"\x00"
+    rv = util.rand_fr(cname, 1, seed=9, mont=True)[0]
+    pb = wire.proof_serialize(eng, C.id, w, winf, rv)
+    assert pb[-33] == 1 and int.from_bytes(pb[-32:], "little") == C.fr_from_limbs(rv, True)[0]
