@@ -106,6 +106,13 @@ int pcgpu_g1_sum_xyzz(pcgpu_ctx *ctx, int curve, const void *xyzz, size_t count,
 int pcgpu_msm_batch(pcgpu_ctx *ctx, const pcgpu_srs *srs, const void *scalars, size_t n, size_t count, uint32_t flags,
                     void *out_xy, uint8_t *out_inf);
 
+/* <G as VariableBaseMSM>::msm_bigint(bases, scalars) on bases that are NOT a registered key -- the verifier-side
+ * combinations: HyraxPC::check's t_prime over row_coms (hyrax/mod.rs:501-504), KZG10::batch_check's combination loop
+ * (kzg10/mod.rs:357-373), Marlin::accumulate_commitments_and_values (marlin/mod.rs:109-148).  Host pointers only; the bases
+ * are uploaded, used once and dropped.  flags: PCGPU_SCALARS_MONT. */
+int pcgpu_msm_bases(pcgpu_ctx *ctx, int curve, const void *bases_xy, const uint8_t *inf, const void *scalars, size_t n,
+                    uint32_t flags, void *out_xy, uint8_t *out_inf);
+
 /* g.batch_mul(scalars): out[i] = scalars[i] * base -- KZG10::setup, kzg10/mod.rs:76, :82-86 (used to build synthetic
  * SRSs on the device).  base_xy: one affine point (host).  scalars: n canonical.  out_xy: n affine points, x||y only
  * (an identity result is written as x = y = 0).  With PCGPU_DEVICE_PTRS scalars and out_xy are device pointers. */
@@ -132,6 +139,9 @@ int pcgpu_g1_deserialize(pcgpu_ctx *ctx, int curve, const uint8_t *bytes, size_t
 /* ---- Fr vector work around the MSM (all elements Montgomery) ----------------------------------- */
 /* F::into_bigint over a slice -- convert_to_bigints, kzg10/mod.rs:463-470 */
 int pcgpu_fr_from_mont(pcgpu_ctx *ctx, int curve, const void *in, void *out, size_t n, uint32_t flags);
+/* out[i] = a[i] * b[i] -- the randomizer * point / randomizer * value products of the verifier-side combinations,
+ * kzg10/mod.rs:360-367 */
+int pcgpu_fr_mul(pcgpu_ctx *ctx, int curve, const void *a, const void *b, void *out, size_t n, uint32_t flags);
 /* y += c * x -- DensePolynomial AddAssign<(F, &P)>, marlin_pc/mod.rs:286; ipa_pc/mod.rs:691-697.  c: host, 1 element */
 int pcgpu_fr_axpy(pcgpu_ctx *ctx, int curve, void *y, const void *c, const void *x, size_t n, uint32_t flags);
 /* q = p / (X - z), rem = p(z) -- compute_witness_polynomial, kzg10/mod.rs:217-240.  p: n coefficients, q: n-1,

@@ -71,6 +71,8 @@ def _load(path):
         "pcgpu_g1_sum_xyzz": [_vp, ctypes.c_int, _vp, _sz, _vp, _vp],
         "pcgpu_g1_fixed_base_mul": [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_uint32, _vp],
         "pcgpu_fr_from_mont": [_vp, ctypes.c_int, _vp, _vp, _sz, ctypes.c_uint32],
+        "pcgpu_fr_mul": [_vp, ctypes.c_int, _vp, _vp, _vp, _sz, ctypes.c_uint32],
+        "pcgpu_msm_bases": [_vp, ctypes.c_int, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_fr_axpy": [_vp, ctypes.c_int, _vp, _vp, _vp, _sz, ctypes.c_uint32],
         "pcgpu_fr_div_linear": [_vp, ctypes.c_int, _vp, _sz, _vp, _vp, _vp, ctypes.c_uint32],
         "pcgpu_fr_inner_product": [_vp, ctypes.c_int, _vp, _vp, _sz, _vp, ctypes.c_uint32],
@@ -243,6 +245,26 @@ class Engine:
         return out
 
     # ---- Fr ----
+    def fr_mul(self, curve, a, b):
+        """elementwise Montgomery product of two (n, 4) arrays"""
+        a, b = _u64(a), _u64(b)
+        n = a.size // 4
+        out = np.zeros((n, 4), dtype=np.uint64)
+        self._ck(self.lib.pcgpu_fr_mul(self.ctx, curve, _ptr(a), _ptr(b), _ptr(out), n, 0))
+        return out
+
+    def msm_bases(self, curve, bases_xy, scalars, inf=None, flags=0):
+        """VariableBaseMSM::msm_bigint on unregistered bases -> (xy, is_identity)"""
+        bases_xy, scalars = _u64(bases_xy), _u64(scalars)
+        n = scalars.size // 4
+        if bases_xy.size // (2 * fq_limbs(curve)) < n:
+            raise ValueError("fewer bases than scalars")
+        inf = None if inf is None else np.ascontiguousarray(inf, dtype=np.uint8)
+        out = np.zeros(2 * fq_limbs(curve), dtype=np.uint64)
+        oinf = np.zeros(1, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_msm_bases(self.ctx, curve, _ptr(bases_xy), _ptr(inf), _ptr(scalars), n, flags, _ptr(out), _ptr(oinf)))
+        return out, bool(oinf[0])
+
     def fr_from_mont(self, curve, a, n=None, flags=0, out=None):
         a = _u64(a)
         if n is None:

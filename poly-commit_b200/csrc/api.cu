@@ -389,3 +389,24 @@ extern "C" int pcgpu_g1_deserialize(pcgpu_ctx *ctx, int curve, const uint8_t *by
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return g1_deserialize_impl<C>(ctx, bytes, n, flags, out_xy, out_inf, first_bad, reason));
 }
+
+extern "C" int pcgpu_fr_mul(pcgpu_ctx *ctx, int curve, const void *a, const void *b, void *out, size_t n, uint32_t flags) {
+  if (!ctx || (n && (!a || !b || !out))) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(curve, return fr_mul_impl<C>(ctx, a, b, out, n, flags));
+}
+
+// VariableBaseMSM::msm_bigint(bases, scalars) on bases that are not a registered key: the verifier-side combinations
+// (hyrax/mod.rs:501-504 over row_coms; kzg10/mod.rs:357-373; marlin/mod.rs:109-148).  Composes the public entry points.
+extern "C" int pcgpu_msm_bases(pcgpu_ctx *ctx, int curve, const void *bases_xy, const uint8_t *inf, const void *scalars, size_t n,
+                               uint32_t flags, void *out_xy, uint8_t *out_inf) {
+  if (!ctx || !out_xy || (n && (!bases_xy || !scalars)) || (flags & (PCGPU_DEVICE_PTRS | PCGPU_SRS_PRECOMPUTE | PCGPU_SRS_COMB)))
+    return PCGPU_E_BADARG;
+  pcgpu_srs *srs = nullptr;
+  int rc = pcgpu_srs_register(ctx, curve, bases_xy, inf, n, 0, &srs);
+  if (rc) return rc;
+  rc = pcgpu_msm(ctx, srs, 0, scalars, n, flags, out_xy, out_inf);
+  pcgpu_srs_release(ctx, srs);
+  return rc;
+}

@@ -39,6 +39,12 @@ struct FrFromMontBody {
   const uint32_t *in; uint32_t *out;
   PCGPU_KERNEL_DEV void operator()(size_t i) const { store_fr<R>(out, i, fp_from_mont<R>(load_fr<R>(in, i))); }
 };
+// out[i] = a[i] * b[i]
+template <class R>
+struct FrMulBody {
+  const uint32_t *a, *b; uint32_t *out;
+  PCGPU_KERNEL_DEV void operator()(size_t i) const { store_fr<R>(out, i, fp_mul<R>(load_fr<R>(a, i), load_fr<R>(b, i))); }
+};
 // y[i] += c * x[i]
 template <class R>
 struct FrAxpyBody {

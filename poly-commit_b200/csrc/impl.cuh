@@ -347,6 +347,25 @@ int fr_from_mont_impl(pcgpu_ctx *ctx, const void *in, void *out, size_t n, uint3
 }
 
 template <class C>
+int fr_mul_impl(pcgpu_ctx *ctx, const void *a, const void *b, void *out, size_t n, uint32_t flags) {
+  using R = typename C::Fr;
+  rt::stream_t st = ctx->stream;
+  int rc;
+  if (n == 0) return PCGPU_OK;
+  if (flags & PCGPU_DEVICE_PTRS) {
+    if ((rc = rt::launch<256>(FrMulBody<R>{(const uint32_t *)a, (const uint32_t *)b, (uint32_t *)out}, n, st))) return rc;
+    return rt::stream_sync(st);
+  }
+  if ((rc = ctx->stage.reserve(3 * rt::Arena::pad(n * 32) + 4096))) return rc;
+  uint32_t *d_a = ctx->stage.take<uint32_t>(n * 8), *d_b = ctx->stage.take<uint32_t>(n * 8), *d_o = ctx->stage.take<uint32_t>(n * 8);
+  if ((rc = rt::copy_h2d(d_a, a, n * 32, st))) return rc;
+  if ((rc = rt::copy_h2d(d_b, b, n * 32, st))) return rc;
+  if ((rc = rt::launch<256>(FrMulBody<R>{d_a, d_b, d_o}, n, st))) return rc;
+  if ((rc = rt::copy_d2h(out, d_o, n * 32, st))) return rc;
+  return rt::stream_sync(st);
+}
+
+template <class C>
 int fr_axpy_impl(pcgpu_ctx *ctx, void *y, const void *c, const void *x, size_t n, uint32_t flags) {
   using R = typename C::Fr;
   rt::stream_t st = ctx->stream;
@@ -894,4 +913,5 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int ipa_check_final_key_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, uint32_t, void *, uint8_t *); \
   EXT template int ntt_pass_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, int, size_t, size_t, const void *, size_t, void *); \
   EXT template int g1_serialize_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, uint8_t *); \
-  EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *);
+  EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *); \
+  EXT template int fr_mul_impl<C>(pcgpu_ctx *, const void *, const void *, void *, size_t, uint32_t);

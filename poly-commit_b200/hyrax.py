@@ -4,6 +4,7 @@
   pedersen_commit               hyrax/mod.rs:86-93
   commit (row loop)             hyrax/mod.rs:230-242   -> Engine.msm_batch over comb tables of com_key || h
   open: lt = mat.row_mul(l)     hyrax/mod.rs:347 -> utils.rs:127-146 -> Engine.fr_row_mul
+  check: t_prime                hyrax/mod.rs:498-504   msm_bigint(&row_coms, &l_bigint) -> Engine.msm_bases (fresh bases)
 
 The reference draws the row randomness r_i from `thread_rng()` when built with the `parallel` feature (:237-238), so its
 commitments are not reproducible; here the randomness is an argument.
@@ -51,3 +52,8 @@ def open_row_mul(ck, mat, l):
     """lt = mat.row_mul(l)  (hyrax/mod.rs:347): l (dim) times the dim x dim matrix."""
     dim = ck.dim
     return ck.eng.fr_row_mul(ck.curve, l, np.ascontiguousarray(mat).reshape(-1, 4), dim, dim)
+
+
+def check_t_prime(eng, curve, row_coms_xy, l, row_coms_inf=None):
+    """hyrax/mod.rs:498-504: the verifier's multi-exponentiation of the row commitments by the tensor l (Montgomery Fr)."""
+    return eng.msm_bases(curve, row_coms_xy, np.asarray(l, dtype=np.uint64).reshape(-1, 4), inf=row_coms_inf, flags=SCALARS_MONT)

@@ -322,6 +322,11 @@ def test_hyrax_host_mirror(eng, pc):
     assert (lt == orc.fr_row_mul(C.id, l, mat.reshape(-1, 4), dim, dim)).all()
     pc0 = hyrax.pedersen_commit(ck, mat[0])
     assert (pc0[0] == orc.msm(C.id, gens[:dim], orc.field_unop("orc_fr_from_mont", C.id, mat[0]))[0]).all()
+    # verifier side (hyrax/mod.rs:498-504): t_prime = <l, row_coms> must commit to lt with randomness <l, r>
+    t_prime, tinf = hyrax.check_t_prime(eng, C.id, row_coms, l, inf)
+    lr = eng.fr_inner_product(C.id, l, rnd)
+    exp = orc.msm(C.id, gens, orc.field_unop("orc_fr_from_mont", C.id, np.concatenate([lt, lr.reshape(1, 4)])))
+    assert (t_prime == exp[0]).all() and not tinf
 
 
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
@@ -647,3 +652,84 @@ def test_wire_kzg_containers(eng, pc):
     rv = util.rand_fr(cname, 1, seed=9, mont=True)[0]
     pb = wire.proof_serialize(eng, C.id, w, winf, rv)
     assert pb[-33] == 1 and int.from_bytes(pb[-32:], "little") == C.fr_from_limbs(rv, True)[0]
+
+
+# ---- verifier-side combinations -------------------------------------------------------------------
+@pytest.mark.parametrize("cname,n", [("bls12_381", 300), ("bn254", 65), ("pallas", 1)])
+def test_msm_bases_unregistered(eng, pc, cname, n):
+    """pcgpu_msm_bases == msm_bigint(bases, scalars) on fresh bases (hyrax/mod.rs:501-504), with an identity base and a
+    zero scalar in the input; pcgpu_fr_mul == elementwise product."""
+    C = pyref.Curve(cname)
+    bases = util.random_points(cname, n, seed=80)
+    inf = np.zeros(n, dtype=np.uint8)
+    sc = util.rand_fr(cname, n, seed=81, mont=False)
+    if n > 2:
+        inf[1] = 1
+        sc[2] = 0
+    pts = C.points_from_limbs(bases, inf)
+    exp = C.msm(pts, C.fr_from_limbs(sc, False))
+    got, ginf = eng.msm_bases(C.id, bases, sc, inf=inf)
+    ex, ei = C.points_to_limbs([exp])
+    assert ginf == bool(ei[0]) and (got == ex[0]).all()
+    a, b = util.rand_fr(cname, n, seed=82, mont=True), util.rand_fr(cname, n, seed=83, mont=True)
+    prod = [x * y % C.r for x, y in zip(C.fr_from_limbs(a, True), C.fr_from_limbs(b, True))]
+    assert (eng.fr_mul(C.id, a, b) == C.fr_to_limbs(prod, True)).all()
+
+
+@pytest.mark.parametrize("hiding", [False, True])
+def test_kzg10_batch_check_combination(eng, pc, hiding):
+    """KZG10::batch_check's combination (kzg10/mod.rs:345-377) and check's inner point (:322-325) against the definition
+    in Python integers, on REAL proofs from the prover path: the combined points must also satisfy the relation the pairing
+    tests -- total_c = beta * (-neg_total_w) for the SRS's beta -- i.e. the batch verifies."""
+    from poly_commit_b200 import kzg10
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    deg, m = 24, 5
+    beta = C.fr_from_limbs(util.rand_fr(cname, 1, 1000 + 11, mont=True), True)[0]       # util.synthetic_srs's beta for seed 11
+    g_pows = util.synthetic_srs(cname, deg + 1, seed=11)
+    gamma_scalar = 0x1234567
+    gamma_pts = [C.mul(gamma_scalar * pow(beta, i, C.r) % C.r, C.g) for i in range(3)]
+    gamma_pows, _ = C.points_to_limbs(gamma_pts)
+    srs, srs_gamma = eng.srs_register(C.id, g_pows), eng.srs_register(C.id, gamma_pows)
+    comms, ws, zs, vs, rvs = [], [], [], [], []
+    for k in range(m):
+        poly = util.rand_fr(cname, deg + 1 - k, seed=90 + k, mont=True)
+        blind = util.rand_fr(cname, 2, seed=95 + k, mont=True) if hiding else None
+        z = util.rand_fr(cname, 1, seed=100 + k, mont=True)[0]
+        if hiding:
+            comm, cinf = eng.kzg_commit(srs, poly, powers_of_gamma_g=srs_gamma, blind=blind)
+            w, winf, rv = eng.kzg_open(srs, poly, z, powers_of_gamma_g=srs_gamma, blind=blind)
+            rvs.append(rv)
+        else:
+            comm, cinf = eng.kzg_commit(srs, poly)
+            w, winf, _ = eng.kzg_open(srs, poly, z)
+        assert not cinf and not winf
+        comms.append(comm); ws.append(w); zs.append(z)
+        vs.append(C.fr_to_limbs([pyref.poly_eval(C.fr_from_limbs(poly, True), C.fr_from_limbs(z, True)[0], C.r)], True)[0])
+    rnd_int = [1] + [int(x) for x in util.rng(7).integers(1, 2**62, size=m - 1)]
+    rnd_int = [x * x + 12345 for x in rnd_int]                                       # ~124-bit values, first one stays small
+    rnd_int[0] = 1
+    rnd = C.fr_to_limbs(rnd_int, True)
+    g, gamma_g = g_pows[0], gamma_pows[0]
+    (neg_w, nwinf), (tot_c, tcinf) = kzg10.batch_check_combine(eng, C.id, g, gamma_g, np.stack(comms), np.stack(zs), np.stack(vs),
+                                                               np.stack(ws), rnd, np.stack(rvs) if hiding else None)
+    # definition in Python integers
+    cp, wp = C.points_from_limbs(np.stack(comms)), C.points_from_limbs(np.stack(ws))
+    zi, vi = C.fr_from_limbs(np.stack(zs), True), C.fr_from_limbs(np.stack(vs), True)
+    ri = C.fr_from_limbs(np.stack(rvs), True) if hiding else [0] * m
+    tc, tw, gm, ggm = None, None, 0, 0
+    for k in range(m):
+        tc = C.add(tc, C.mul(rnd_int[k], C.add(cp[k], C.mul(zi[k], wp[k]))))
+        tw = C.add(tw, C.mul(rnd_int[k], wp[k]))
+        gm, ggm = (gm + rnd_int[k] * vi[k]) % C.r, (ggm + rnd_int[k] * ri[k]) % C.r
+    tc = C.add(tc, C.neg(C.mul(gm, C.g)))
+    tc = C.add(tc, C.neg(C.mul(ggm, gamma_pts[0])))
+    ex, ei = C.points_to_limbs([C.neg(tw), tc])
+    assert (neg_w == ex[0]).all() and (tot_c == ex[1]).all() and not nwinf and not tcinf
+    # e(-total_w, beta h) * e(total_c, h) == 1  <=>  total_c == beta * total_w
+    assert C.mul(beta, tw) == tc
+    # single check: e(comm - g v - gamma_g rv, h) == e(w, beta h - z h)  <=>  inner == (beta - z) * w
+    inner, iinf = kzg10.check_inner(eng, C.id, g, gamma_g, comms[0], vs[0], rvs[0] if hiding else None)
+    exp_inner = C.mul((beta - zi[0]) % C.r, wp[0])
+    ex, _ = C.points_to_limbs([exp_inner])
+    assert (inner == ex[0]).all() and not iinf
