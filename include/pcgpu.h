@@ -161,6 +161,12 @@ int pcgpu_fr_row_mul(pcgpu_ctx *ctx, int curve, const void *v, const void *m, si
  * includes the 1/N factor).  1 <= logn <= 22.  out: 2^logn elements. */
 int pcgpu_ntt(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in, uint32_t logn, uint32_t flags, void *out);
 
+/* `count` independent transforms: row r = in[r * n_in .. (r + 1) * n_in) zero-padded to 2^logn, out row stride 2^logn --
+ * the row-wise Reed-Solomon encoding of LinearEncode::compute_matrices (linear_codes/mod.rs:118-138: every row of the
+ * coefficient matrix through reed_solomon, linear_codes/utils.rs:112-127).  Rows up to 2^11 are one launch for the whole
+ * matrix.  Same flags as pcgpu_ntt. */
+int pcgpu_ntt_batch(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in, size_t count, uint32_t logn, uint32_t flags, void *out);
+
 /* Multi-GPU building block ("NTT shards by the four-step row/column split"): N = N1 * N2 with
  * N1 = 2^m1, N2 = 2^m2 from pcgpu_ntt_split (m2 = 0 means the transform is a single block pass and does not shard).
  * All pointers are DEVICE pointers.

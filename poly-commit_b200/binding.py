@@ -89,6 +89,7 @@ def _load(path):
                                  ctypes.POINTER(ctypes.c_int)],
         "pcgpu_ntt_split": [ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)],
         "pcgpu_ntt_pass": [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _sz, _sz, _vp, _sz, _vp],
+        "pcgpu_ntt_batch": [_vp, ctypes.c_int, _vp, _sz, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
         "pcgpu_ntt": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
         "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
@@ -350,6 +351,14 @@ class Engine:
             raise WireError(rc, self.lib.pcgpu_strerror(rc).decode(), int(bad.value), int(reason.value))
         self._ck(rc)
         return xy, inf
+
+    def ntt_batch(self, curve, rows, logn, inverse=False):
+        """(count, n_in, 4) rows -> (count, 2^logn, 4): every row zero-padded and transformed (Ligero row encoding)"""
+        rows = _u64(rows)
+        count, n_in = rows.shape[0], rows.shape[1]
+        out = np.zeros((count, 1 << logn, 4), dtype=np.uint64)
+        self._ck(self.lib.pcgpu_ntt_batch(self.ctx, curve, _ptr(rows), n_in, count, logn, NTT_INVERSE if inverse else 0, _ptr(out)))
+        return out
 
     def ntt_split(self, logn):
         m1, m2 = ctypes.c_uint32(), ctypes.c_uint32()

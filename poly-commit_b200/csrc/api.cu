@@ -410,3 +410,11 @@ extern "C" int pcgpu_msm_bases(pcgpu_ctx *ctx, int curve, const void *bases_xy, 
   pcgpu_srs_release(ctx, srs);
   return rc;
 }
+
+extern "C" int pcgpu_ntt_batch(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in, size_t count, uint32_t logn, uint32_t flags,
+                               void *out) {
+  if (!ctx || (count && (!out || (n_in && !in)))) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(curve, return ntt_batch_impl<C>(ctx, in, n_in, count, logn, flags, out));
+}

@@ -698,6 +698,43 @@ int ntt_impl(pcgpu_ctx *ctx, const void *in, size_t n_in, uint32_t logn, uint32_
 }
 
 template <class C>
+int ntt_batch_impl(pcgpu_ctx *ctx, const void *in, size_t n_in, size_t count, uint32_t logn, uint32_t flags, void *out) {
+  using R = typename C::Fr;
+  if (!ntt_supported(logn) || logn > (uint32_t)R::TWO_ADICITY) return PCGPU_E_BADARG;
+  const size_t N = (size_t)1 << logn;
+  if (n_in > N) return PCGPU_E_LEN;
+  if (count == 0) return PCGPU_OK;
+  if (count > ((size_t)1 << 40) / N) return PCGPU_E_BADARG;
+  rt::stream_t st = ctx->stream;
+  int rc, inverse = (flags & PCGPU_NTT_INVERSE) ? 1 : 0;
+  const NttPlan *plan = nullptr;
+  for (const NttPlan &p : ctx->ntt_plans) if (p.curve == C::ID && p.logn == logn && p.inverse == inverse) plan = &p;
+  if (!plan) {
+    NttPlan p;
+    if ((rc = ntt_build_plan<R>(p, C::ID, logn, inverse, st))) return rc;
+    ctx->ntt_plans.push_back(p);
+    plan = &ctx->ntt_plans.back();
+  }
+  const bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  if ((rc = ctx->stage.reserve(rt::Arena::pad(N * 32) + (dev ? 0 : rt::Arena::pad(count * (n_in ? n_in : 1) * 32) + rt::Arena::pad(count * N * 32)) + 4096)))
+    return rc;
+  uint32_t *tmp = ctx->stage.take<uint32_t>(N * 8);
+  const uint32_t *d_in = (const uint32_t *)in; uint32_t *d_out = (uint32_t *)out;
+  if (!dev) {
+    uint32_t *ti = ctx->stage.take<uint32_t>(count * (n_in ? n_in : 1) * 8); d_out = ctx->stage.take<uint32_t>(count * N * 8);
+    if (n_in && (rc = rt::copy_h2d(ti, in, count * n_in * 32, st))) return rc;
+    d_in = ti;
+  }
+  ctx->prof.begin(9, st);
+  if ((rc = ntt_run_batch<R>(*plan, d_in, n_in, count, d_out, tmp, st))) return rc;
+  ctx->prof.end(9, st);
+  if (!dev && (rc = rt::copy_d2h(out, d_out, count * N * 32, st))) return rc;
+  rc = rt::stream_sync(st);
+  ctx->prof.collect();
+  return rc;
+}
+
+template <class C>
 int ntt_pass_impl(pcgpu_ctx *ctx, uint32_t logn, uint32_t flags, int which, size_t lo, size_t count, const void *in, size_t n_in,
                   void *out) {
   using R = typename C::Fr;
@@ -914,4 +951,5 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int ntt_pass_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, int, size_t, size_t, const void *, size_t, void *); \
   EXT template int g1_serialize_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, uint8_t *); \
   EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *); \
-  EXT template int fr_mul_impl<C>(pcgpu_ctx *, const void *, const void *, void *, size_t, uint32_t);
+  EXT template int fr_mul_impl<C>(pcgpu_ctx *, const void *, const void *, void *, size_t, uint32_t); \
+  EXT template int ntt_batch_impl<C>(pcgpu_ctx *, const void *, size_t, size_t, uint32_t, uint32_t, void *);

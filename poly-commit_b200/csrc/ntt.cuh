@@ -79,11 +79,12 @@ struct NttBlockBody {
   const uint32_t *lo, *hi; int step2;       // step-2 twiddle w_N^(i * batch)
   const uint32_t *scale;                    // optional final factor
   uint64_t batch_off;                       // global index of local batch 0 (sharded passes); enters the step-2 twiddle only
+  uint32_t i_valid;                         // elements i >= i_valid of every batch read as zero (row-batched transforms)
   PCGPU_KERNEL_DEV void operator()(size_t batch, uint32_t *smem) const {
     const uint32_t M = 1u << m;
     PCGPU_BLOCK_FOR(i, M) {
       uint64_t idx = batch * in_batch_stride + (uint64_t)i * in_stride;
-      Fp<R> v = idx < n_valid ? load_fr<R>(in, idx) : Fp<R>::zero();
+      Fp<R> v = (idx < n_valid && (uint32_t)i < i_valid) ? load_fr<R>(in, idx) : Fp<R>::zero();
       uint32_t r = bitrev32(i, m);
 #pragma unroll
       for (int l = 0; l < 8; l++) smem[l * M + r] = v.l[l];
@@ -148,13 +149,13 @@ template <class R>
 inline int ntt_run(const NttPlan &p, const uint32_t *in, size_t n_in, uint32_t *out, uint32_t *tmp, rt::stream_t st) {
   const uint64_t N1 = (uint64_t)1 << p.m1, N2 = (uint64_t)1 << p.m2;
   if (p.m2 == 0) {
-    NttBlockBody<R> b{in, out, p.m1, 1, 0, 1, 0, n_in, p.tw1, p.lo, p.hi, 0, p.scale, 0};
+    NttBlockBody<R> b{in, out, p.m1, 1, 0, 1, 0, n_in, p.tw1, p.lo, p.hi, 0, p.scale, 0, ~0u};
     return rt::launch_blocks<256>(b, 1, (size_t)N1 * 32, st);
   }
-  NttBlockBody<R> b1{in, tmp, p.m1, N2, 1, N2, 1, n_in, p.tw1, p.lo, p.hi, 1, nullptr, 0};
+  NttBlockBody<R> b1{in, tmp, p.m1, N2, 1, N2, 1, n_in, p.tw1, p.lo, p.hi, 1, nullptr, 0, ~0u};
   int rc = rt::launch_blocks<256>(b1, N2, (size_t)N1 * 32, st);
   if (rc) return rc;
-  NttBlockBody<R> b2{tmp, out, p.m2, 1, N2, N1, 1, N1 * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0};
+  NttBlockBody<R> b2{tmp, out, p.m2, 1, N2, N1, 1, N1 * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0, ~0u};
   return rt::launch_blocks<256>(b2, N1, (size_t)N2 * 32, st);
 }
 
@@ -168,11 +169,29 @@ inline int ntt_run_pass(const NttPlan &p, int which, uint64_t lo, uint64_t count
                         rt::stream_t st) {
   const uint64_t N1 = (uint64_t)1 << p.m1, N2 = (uint64_t)1 << p.m2;
   if (which == 1) {
-    NttBlockBody<R> b{in + 8 * lo, out, p.m1, N2, 1, count, 1, n_in > lo ? n_in - lo : 0, p.tw1, p.lo, p.hi, 1, nullptr, lo};
+    NttBlockBody<R> b{in + 8 * lo, out, p.m1, N2, 1, count, 1, n_in > lo ? n_in - lo : 0, p.tw1, p.lo, p.hi, 1, nullptr, lo, ~0u};
     return rt::launch_blocks<256>(b, count, (size_t)N1 * 32, st);
   }
-  NttBlockBody<R> b{in, out, p.m2, 1, N2, count, 1, count * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0};
+  NttBlockBody<R> b{in, out, p.m2, 1, N2, count, 1, count * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0, ~0u};
   return rt::launch_blocks<256>(b, count, (size_t)N2 * 32, st);
+}
+
+// `count` independent transforms of rows laid out back to back (row r = in[r * n_in .. (r+1) * n_in), zero-padded to N) --
+// the row-wise Reed-Solomon encoding of LinearEncode::compute_matrices, linear_codes/mod.rs:118-138.  Rows that fit one
+// block pass go out as ONE launch of `count` blocks; longer rows run the four-step passes row by row (each pass already
+// fills the device).  tmp: N elements, used only when m2 != 0.
+template <class R>
+inline int ntt_run_batch(const NttPlan &p, const uint32_t *in, size_t n_in, size_t count, uint32_t *out, uint32_t *tmp, rt::stream_t st) {
+  const uint64_t N = (uint64_t)1 << p.logn;
+  if (p.m2 == 0) {
+    NttBlockBody<R> b{in, out, p.m1, 1, n_in, 1, N, (uint64_t)count * n_in, p.tw1, p.lo, p.hi, 0, p.scale, 0, (uint32_t)n_in};
+    return rt::launch_blocks<256>(b, count, (size_t)N * 32, st);
+  }
+  for (size_t r = 0; r < count; r++) {
+    int rc = ntt_run<R>(p, in + r * n_in * 8, n_in, out + r * N * 8, tmp, st);
+    if (rc) return rc;
+  }
+  return rt::OK;
 }
 
 }  // namespace pcgpu

@@ -18,7 +18,8 @@ from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_
                                   test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror, test_kzg_commit_batch, test_msm_two_level_reduction, test_msm_heavy_buckets,
                                   test_wire_roundtrip_vs_oracle, test_wire_bls12_381_generator_known_answer,
                                   test_wire_rejects_like_the_oracle, test_wire_kzg_containers, test_msm_bases_unregistered,
-                                  test_kzg10_batch_check_combination)
+                                  test_kzg10_batch_check_combination, test_ligero_reed_solomon_like_the_reference,
+                                  test_ligero_compute_matrices)
 
 pytestmark = pytest.mark.gpu
 
@@ -233,6 +234,20 @@ def test_wire_srs_ingest_large(eng, pc, cname, logn):
     with pytest.raises(pc.binding.WireError) as ei:
         eng.g1_deserialize(C.id, bad, n, False, validate=True)
     assert ei.value.index == k and ei.value.reason in (pyref.WIRE_NOT_ON_CURVE, pyref.WIRE_NOT_CANONICAL)
+
+
+def test_ligero_rows_at_size(eng):
+    """Ligero matrix for a 2^20-coefficient polynomial: 1024 rows of 1024 coefficients encoded at rate 1/4 in ONE launch;
+    sampled rows against the oracle, all rows through decode(encode(row)) == row."""
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    n_rows, n_cols, logn = 1024, 1024, 12 - 1
+    mat = util.rand_fr_fast(cname, n_rows * n_cols, seed=140).reshape(n_rows, n_cols, 4)
+    ext = eng.ntt_batch(C.id, mat, logn)
+    for r in (0, 1, 511, 1023):
+        assert (ext[r] == orc.fr_ntt(C.id, mat[r], logn)).all()
+    back = eng.ntt_batch(C.id, ext, logn, inverse=True)
+    assert (back[:, :n_cols] == mat).all() and not back[:, n_cols:].any()
 
 
 def test_cfg4_hyrax_commit_rows(eng, pc):

@@ -733,3 +733,57 @@ def test_kzg10_batch_check_combination(eng, pc, hiding):
     exp_inner = C.mul((beta - zi[0]) % C.r, wp[0])
     ex, _ = C.points_to_limbs([exp_inner])
     assert (inner == ex[0]).all() and not iinf
+
+
+# ---- Ligero row encoding --------------------------------------------------------------------------
+def test_ligero_reed_solomon_like_the_reference(eng):
+    """mirror of test_reed_solomon (linear_codes/utils.rs:303-331): rho_inv = 3, m = 2^i for i in 1..10 -- every encoded
+    element equals the polynomial evaluated at the element of the larger domain."""
+    from poly_commit_b200 import linear_codes
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    for i in range(1, 10):
+        m = 1 << i
+        coeffs = util.rand_fr(cname, m, seed=120 + i, mont=True)
+        enc = linear_codes.reed_solomon(eng, C.id, coeffs, 3)
+        logn = (3 * m - 1).bit_length()
+        assert enc.shape[0] == 1 << logn
+        w = C.domain_generator(logn)
+        ci = C.fr_from_limbs(coeffs, True)
+        for j in sorted({0, 1, 2, 3 * m - 1, (1 << logn) - 1, (7 * j0 + 3) % (3 * m) if (j0 := i) else 0}):
+            assert C.fr_from_limbs(enc[j], True)[0] == pyref.poly_eval(ci, pow(w, j, C.r), C.r)
+        assert (enc == orc.fr_ntt(C.id, coeffs, logn)).all()
+
+
+def test_ligero_dimensions_like_the_reference():
+    """test_calculate_t_with_good_parameters / _bad_parameters (linear_codes/utils.rs:344-360) on BLS12-377's 377-bit Fq"""
+    from poly_commit_b200 import linear_codes
+    assert linear_codes.calculate_t(377, 128, (3, 4), 2**32) < 200
+    assert linear_codes.calculate_t(377, 256, (3, 4), 2**32) < 400
+    with pytest.raises(ValueError):
+        linear_codes.calculate_t(377, 377 - 60, (3, 4), 2**60)
+    with pytest.raises(ValueError):
+        linear_codes.calculate_t(377, 400, (3, 4), 2**32)
+    n, m = linear_codes.compute_dimensions(0, 128, 4, 1 << 20)
+    assert n & (n - 1) == 0 and n * m >= 1 << 20 and (m - 1) * n < 1 << 20
+
+
+@pytest.mark.parametrize("cname,n_rows,n_cols,rho_inv,used", [("bls12_381", 8, 16, 4, 120), ("bn254", 3, 5, 2, 15),
+                                                               ("pallas", 2, 1024, 4, 2048)])
+def test_ligero_compute_matrices(eng, cname, n_rows, n_cols, rho_inv, used):
+    """compute_matrices (linear_codes/mod.rs:118-138): row-major matrix, zero padding, every row through the NTT;
+    the last case takes the four-step path (rows of 2^12)."""
+    from poly_commit_b200 import linear_codes
+    C = pyref.Curve(cname)
+    coeffs = util.rand_fr(cname, used, seed=130, mont=True)
+    mat, ext = linear_codes.compute_matrices(eng, C.id, coeffs, n_rows, n_cols, rho_inv)
+    logn = (n_cols * rho_inv - 1).bit_length()
+    assert ext.shape == (n_rows, 1 << logn, 4)
+    flat = np.zeros((n_rows * n_cols, 4), dtype=np.uint64)
+    flat[:used] = coeffs
+    assert (mat.reshape(-1, 4) == flat).all() and (mat[1, 2] == flat[n_cols + 2]).all() if n_cols > 2 else True
+    for r in range(n_rows):
+        assert (ext[r] == orc.fr_ntt(C.id, flat[r * n_cols:(r + 1) * n_cols], logn)).all()
+    # ifft of a row gives the row back (zero-padded)
+    back = eng.ntt_batch(C.id, ext, logn, inverse=True)
+    assert (back[:, :n_cols] == mat).all() and not back[:, n_cols:].any()
