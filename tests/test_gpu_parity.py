@@ -237,7 +237,7 @@ def test_wire_srs_ingest_large(eng, pc, cname, logn):
 
 
 def test_ligero_rows_at_size(eng):
-    """Ligero matrix for a 2^20-coefficient polynomial: 1024 rows of 1024 coefficients encoded at rate 1/4 in ONE launch;
+    """Ligero matrix for a 2^20-coefficient polynomial: 1024 rows of 1024 coefficients encoded at rate 1/2 (2^11-point rows) in ONE launch;
     sampled rows against the oracle, all rows through decode(encode(row)) == row."""
     cname = "bls12_381"
     C = pyref.Curve(cname)
