@@ -152,12 +152,19 @@ template <class R> inline void fr_from_mont_host(const void *in, uint64_t *out) 
 // Combination of the device's bit-plane sums T[s][j] = sum of the buckets of set s whose weight has bit j set:
 //   result = sum_s 2^(c s) * sum_j 2^j T[s][j]
 template <class C> inline HXYZZ<C> combine_bit_planes(const HXYZZ<C> *T, uint32_t S, uint32_t c) {
+  // plane j of set s carries weight 2^(c s + j): one Horner pass over the bit positions, S*c doublings and additions
   HXYZZ<C> acc = HXYZZ<C>::inf();
-  for (uint32_t s = S; s-- > 0;) {
-    HXYZZ<C> v = HXYZZ<C>::inf();
-    for (uint32_t j = c; j-- > 0;) { v = pdbl<C>(v); v = padd<C>(v, T[(size_t)s * c + j]); }
-    if (s + 1 < S) for (uint32_t k = 0; k < c; k++) acc = pdbl<C>(acc);
-    acc = padd<C>(acc, v);
+  for (uint32_t b = S * c; b-- > 0;) { acc = pdbl<C>(acc); acc = padd<C>(acc, T[b]); }
+  return acc;
+}
+
+// Small-MSM path (msm_small.cuh): the device hands back one point per window, U_w = sum_k k B_{w,k};
+//   result = sum_w 2^(c w) U_w   -- c * (W - 1) doublings and W additions
+template <class C> inline HXYZZ<C> combine_windows(const HXYZZ<C> *U, uint32_t W, uint32_t c) {
+  HXYZZ<C> acc = HXYZZ<C>::inf();
+  for (uint32_t w = W; w-- > 0;) {
+    if (w + 1 < W) for (uint32_t k = 0; k < c; k++) acc = pdbl<C>(acc);
+    acc = padd<C>(acc, U[w]);
   }
   return acc;
 }

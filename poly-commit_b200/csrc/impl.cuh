@@ -18,6 +18,7 @@
 #include "msm.cuh"
 #include "srs.cuh"
 #include "wire.cuh"
+#include "msm_small.cuh"
 
 using namespace pcgpu;
 
@@ -143,6 +144,56 @@ int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, siz
 // ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
+// Small MSMs (msm_small.cuh): up to SMALL_MAX_PROB problems of <= SMALL_MAX_N terms in one launch; one point per window
+// comes back and the host finishes with the doublings.  PCGPU_MSM_SMALL=0 forces the bucket pipeline (tests, A/B timing).
+inline bool msm_small_enabled() {
+  const char *e = getenv("PCGPU_MSM_SMALL");
+  return !(e && e[0] == '0');
+}
+template <class C>
+static int msm_small_to_host(pcgpu_ctx *ctx, const MsmSmallProblem<C> *probs, uint32_t nprob, bool mont, host::HXYZZ<C> *out) {
+  using R = typename C::Fr;
+  constexpr uint32_t W = small_windows<R>();
+  rt::stream_t st = ctx->stream;
+  int rc;
+  if (nprob == 0 || nprob > SMALL_MAX_PROB) return PCGPU_E_BADARG;
+  uint32_t nmax = 0;
+  for (uint32_t p = 0; p < nprob; p++) nmax = probs[p].n > nmax ? probs[p].n : nmax;
+  const uint32_t split = nmax >= SMALL_SPLIT_MIN_N ? SMALL_SPLIT : 1;
+  const size_t npts = (size_t)nprob * W * split;
+  if ((rc = ctx->msm_arena.reserve(rt::Arena::pad(npts * sizeof(XYZZ<C>)) + 4096))) return rc;
+  uint32_t *d_err = ctx->msm_arena.take<uint32_t>(16);
+  XYZZ<C> *d_out = ctx->msm_arena.take<XYZZ<C>>(npts);
+  if ((rc = rt::dev_memset(d_err, 0, 64, st))) return rc;
+  MsmSmallBody<C> body;
+  memset(&body, 0, sizeof body);
+  for (uint32_t p = 0; p < nprob; p++) body.prob[p] = probs[p];
+  body.mont = mont ? 1u : 0u; body.split = split; body.out = d_out; body.err = d_err;
+  ctx->prof.begin(4, st);
+  if ((rc = rt::launch_blocks<SMALL_BLOCK>(body, npts, msm_small_smem<C>(), st))) return rc;
+  ctx->prof.end(4, st);
+  static_assert(sizeof(host::HXYZZ<C>) == sizeof(XYZZ<C>), "host/device point layouts must agree");
+  std::vector<host::HXYZZ<C>> U(npts);
+  uint32_t herr = 0;
+  if ((rc = rt::copy_d2h(U.data(), d_out, U.size() * sizeof(XYZZ<C>), st))) return rc;
+  if ((rc = rt::copy_d2h(&herr, d_err, sizeof herr, st))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  ctx->prof.collect();
+  if (herr) return PCGPU_E_RANGE;
+  auto t0 = std::chrono::steady_clock::now();
+  for (size_t v = 0; v < (size_t)nprob * W && split > 1; v++) {       // fold the partial window sums of the split blocks
+    host::HXYZZ<C> a = U[v * split];
+    for (uint32_t q = 1; q < split; q++) a = host::padd<C>(a, U[v * split + q]);
+    U[v] = a;
+  }
+  for (uint32_t p = 0; p < nprob; p++) out[p] = host::combine_windows<C>(U.data() + (size_t)p * W, W, SMALL_C);
+  if (ctx->prof.on) {
+    ctx->prof.ms[6] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    ctx->prof.cnt[6]++;
+  }
+  return PCGPU_OK;
+}
+
 // One MSM: device pipeline, then the S*c bit-plane sums come back to the host, which combines them
 // (host_ec.hpp).  d_scalars: device, n x 8 u32.  Synchronises the stream.
 template <class C>
@@ -151,6 +202,10 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
   rt::stream_t st = ctx->stream;
   *out = host::HXYZZ<C>::inf();
   if (n == 0) return PCGPU_OK;
+  if (n <= SMALL_MAX_N && msm_small_enabled()) {
+    MsmSmallProblem<C> pr{(const Affine<C> *)srs->d_tables + base_offset, d_scalars, nullptr, nullptr, (uint32_t)n};
+    return msm_small_to_host<C>(ctx, &pr, 1, mont, out);
+  }
   uint32_t c, groups;
   const uint32_t *tables = (const uint32_t *)srs->d_tables;
   uint32_t pt_words = 2 * C::Fq::N, y_words = C::Fq::N;
@@ -592,6 +647,21 @@ int ipa_round_lr_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_prime_xy, voi
   const uint32_t *cl = st->d_coeffs, *cr = st->d_coeffs + 8 * m, *zl = st->d_z, *zr = st->d_z + 8 * m;
   uint32_t *d_ip = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 6);
   uint64_t ip_m[2][4], ip_c[2][4];
+  if (m < SMALL_MAX_N && msm_small_enabled()) {
+    // late rounds: both commitments, each with its  + h' * <.,.>  term, in ONE launch; the inner products never leave HBM
+    uint32_t *d_h = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 12);   // 3 slots, clear of d_ip / d_ch
+    if ((rc = fr_inner_product<R>(cr, zl, m, d_ip, st->d_scr, s))) return rc;
+    if ((rc = fr_inner_product<R>(cl, zr, m, d_ip + 8, st->d_scr, s))) return rc;
+    if ((rc = rt::copy_h2d(d_h, h_prime_xy, sizeof(Affine<C>), s))) return rc;
+    const Affine<C> *key = (const Affine<C> *)st->view.d_tables;
+    MsmSmallProblem<C> pr[2] = {{key, cr, (const Affine<C> *)d_h, d_ip, (uint32_t)m},          // cm_commit(key_l, coeffs_r) + h' <c_r, z_l>
+                                {key + m, cl, (const Affine<C> *)d_h, d_ip + 8, (uint32_t)m}};  // cm_commit(key_r, coeffs_l) + h' <c_l, z_r>
+    host::HXYZZ<C> lr[2];
+    if ((rc = msm_small_to_host<C>(ctx, pr, 2, true, lr))) return rc;
+    host::to_affine<C>(lr[0], out_l_xy, out_l_inf);
+    host::to_affine<C>(lr[1], out_r_xy, out_r_inf);
+    return PCGPU_OK;
+  }
   // <coeffs_r, z_l>, <coeffs_l, z_r>
   if ((rc = fr_inner_product<R>(cr, zl, m, d_ip, st->d_scr, s))) return rc;
   if ((rc = rt::copy_d2h(ip_m[0], d_ip, 32, s))) return rc;

@@ -70,6 +70,8 @@ template <int BLOCK, int MINB, class Body> inline int resident_threads_occ(size_
 // PCGPU_BLOCK_FOR loops separated by PCGPU_BLOCK_SYNC(); anything that must survive a sync lives in shared memory.
 #define PCGPU_BLOCK_FOR(i, n) for (uint32_t i = 0; i < (uint32_t)(n); i++)
 #define PCGPU_BLOCK_SYNC() do { } while (0)
+// warp vote over a FULL warp (every lane must reach it): also the point where diverged lanes reconverge
+#define PCGPU_WARP_ANY(x) (x)
 template <int BLOCK, class Body>
 inline int launch_blocks(const Body &body, size_t nblocks, size_t smem_bytes, stream_t) {
   uint32_t *smem = (uint32_t *)::malloc(smem_bytes ? smem_bytes : 16);
@@ -144,6 +146,7 @@ inline int resident_threads_occ(size_t *out) {
 }
 #define PCGPU_BLOCK_FOR(i, n) for (uint32_t i = threadIdx.x; i < (uint32_t)(n); i += blockDim.x)
 #define PCGPU_BLOCK_SYNC() __syncthreads()
+#define PCGPU_WARP_ANY(x) __any_sync(0xffffffffu, (x))
 template <class Body, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) run_block_kernel(const Body body) {
   extern __shared__ uint4 pcgpu_smem[];

@@ -40,3 +40,11 @@ def gpu_engine(pc):
     eng = pc.Engine(0)
     yield eng
     eng.close()
+
+
+@pytest.fixture(params=["small", "buckets"])
+def msm_path(request, monkeypatch):
+    """MSMs of <= 4096 terms take the one-launch path (csrc/msm_small.cuh); PCGPU_MSM_SMALL=0 sends them through the bucket
+    pipeline instead, so the small-n cases keep covering both."""
+    monkeypatch.setenv("PCGPU_MSM_SMALL", "1" if request.param == "small" else "0")
+    return request.param

@@ -71,7 +71,7 @@ def test_field_schedule_vs_bigint(hostcheck_path, cname, which, fid):
 
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
 @pytest.mark.parametrize("n", [0, 1, 2, 33, 300])
-def test_msm_vs_oracle(eng, pc, cname, n):
+def test_msm_vs_oracle(eng, pc, cname, n, msm_path):
     C = pyref.Curve(cname)
     bases = util.random_points(cname, max(n, 1) + 7, seed=n)
     srs = eng.srs_register(C.id, bases)
@@ -90,7 +90,7 @@ def test_msm_vs_oracle(eng, pc, cname, n):
         assert (got3[0] == exp3[0]).all()
 
 
-def test_msm_edge_scalars(eng, pc):
+def test_msm_edge_scalars(eng, pc, msm_path):
     """zeros, ones, r-1, small values, repeated bases (P+P inside a bucket), P and -P cancelling."""
     cname = "bls12_381"
     C = pyref.Curve(cname)
@@ -127,6 +127,7 @@ def test_msm_edge_scalars(eng, pc):
 def test_msm_batched_affine_rounds(eng, pc, rounds, monkeypatch):
     """msm_affine.cuh: forced batched-affine pairwise rounds (Montgomery batch inversion with the binary-GCD inverse)
     must give the same point, including the exceptional pairs: P + P, P + (-P), identity operands, odd bucket sizes."""
+    monkeypatch.setenv("PCGPU_MSM_SMALL", "0")          # these cases target the bucket pipeline
     monkeypatch.setenv("PCGPU_MSM_AFFINE_ROUNDS", str(rounds))
     for cname, n in (("bls12_381", 150), ("bn254", 61), ("pallas", 90)):
         C = pyref.Curve(cname)
@@ -157,6 +158,7 @@ def test_msm_batched_affine_rounds(eng, pc, rounds, monkeypatch):
 def test_msm_two_level_reduction(eng, pc, c, monkeypatch):
     """large windows (c > 17): the weighted bucket sum goes through row / column sums (msm.cuh, h_split) -- forced here through
     the tuning knobs on the raw-base path and on window-folded tables."""
+    monkeypatch.setenv("PCGPU_MSM_SMALL", "0")          # these cases target the bucket pipeline
     monkeypatch.setenv("PCGPU_MSM_C", str(c))
     monkeypatch.setenv("PCGPU_SRS_C", str(c))
     cname = "bn254"
@@ -179,6 +181,7 @@ def test_msm_two_level_reduction(eng, pc, c, monkeypatch):
 def test_msm_heavy_buckets(eng, pc, rounds, monkeypatch):
     """repeated scalars (many coefficients equal to 1, -1 or one constant -- common in real witness polynomials) put
     hundreds of points into single buckets: block-cooperative heavy-bucket reduction (MsmHeavyBucketBody)."""
+    monkeypatch.setenv("PCGPU_MSM_SMALL", "0")          # these cases target the bucket pipeline
     monkeypatch.setenv("PCGPU_MSM_AFFINE_ROUNDS", rounds)
     cname = "bn254"
     C = pyref.Curve(cname)
@@ -192,7 +195,7 @@ def test_msm_heavy_buckets(eng, pc, rounds, monkeypatch):
     assert got[1] == exp[1] and (got[0] == exp[0]).all()
 
 
-def test_msm_infinity_bases(eng):
+def test_msm_infinity_bases(eng, msm_path):
     cname = "bn254"
     C = pyref.Curve(cname)
     pts = util.random_points(cname, 6, seed=4)
@@ -389,7 +392,7 @@ def test_row_mul_reference_kat(eng):
 
 
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
-def test_golden_vectors(eng, cname):
+def test_golden_vectors(eng, cname, msm_path):
     golden_cases.check_engine(eng, cname)
 
 
@@ -423,7 +426,7 @@ def oracle_ipa_rounds(cname, comm_key, coeffs, point, h_prime, round_challenge):
 
 
 @pytest.mark.parametrize("cname,n", [("pallas", 64), ("bls12_381", 16), ("bn254", 32)])
-def test_ipa_open_rounds(eng, pc, cname, n):
+def test_ipa_open_rounds(eng, pc, cname, n, msm_path):
     """cfg3's dataflow (Pallas; the reference instantiates IPA on Jubjub only): every l, r, the final key and c."""
     from poly_commit_b200 import ipa_pc
     C = pyref.Curve(cname)
@@ -455,7 +458,7 @@ def test_ntt_vs_oracle(eng, cname, logn, n_in):
 
 
 @pytest.mark.parametrize("cname", ["bls12_381", "bn254"])
-def test_kzg_commit_open(eng, pc, cname):
+def test_kzg_commit_open(eng, pc, cname, msm_path):
     """KZG10::commit / open dataflow (kzg10/mod.rs:157-310), non-hiding and hiding, vs the C oracle."""
     C = pyref.Curve(cname)
     n = 200
@@ -787,3 +790,27 @@ def test_ligero_compute_matrices(eng, cname, n_rows, n_cols, rho_inv, used):
     # ifft of a row gives the row back (zero-padded)
     back = eng.ntt_batch(C.id, ext, logn, inverse=True)
     assert (back[:, :n_cols] == mat).all() and not back[:, n_cols:].any()
+
+
+def test_msm_small_path_limits(eng, pc, monkeypatch):
+    """csrc/msm_small.cuh at its edges: n = 4096 (largest one-launch size) and 4097 (first bucket-pipeline size) agree with
+    the oracle; every digit value occurs (scalars built from all 64 six-bit patterns, incl. the -32 digit and the carry
+    into the top window); the result does not depend on the path."""
+    cname = "bn254"
+    C = pyref.Curve(cname)
+    bases = util.random_points(cname, 4097, seed=150)
+    sc = util.rand_fr(cname, 4097, seed=151, mont=False)
+    pats = []
+    for d in range(64):
+        v = sum(d << (6 * w) for w in range(43)) % C.r
+        pats += [v, (C.r - 1 - v) % C.r]
+    pats += [C.r - 1, C.r - 2, (1 << 253) - 1, 1 << 253, 32, 31, 33, (1 << 6) - 1]
+    sc[:len(pats)] = C.fr_to_limbs(pats, False)
+    srs = eng.srs_register(C.id, bases)
+    for n in (4096, 4097, len(pats)):
+        exp = orc.msm(C.id, bases, sc, n=n)
+        got = eng.msm(srs, sc[:n], n=n)
+        assert got[1] == exp[1] and (got[0] == exp[0]).all(), n
+    monkeypatch.setenv("PCGPU_MSM_SMALL", "0")
+    got = eng.msm(srs, sc[:len(pats)])
+    assert (got[0] == orc.msm(C.id, bases, sc, n=len(pats))[0]).all()
