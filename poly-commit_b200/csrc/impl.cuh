@@ -12,6 +12,7 @@
 #include "../../include/pcgpu.h"
 #include "frops.cuh"
 #include "host_ec.hpp"
+#include "host_glv.hpp"
 #include "ntt.cuh"
 #include "ipa.cuh"
 #include <chrono>
@@ -693,11 +694,24 @@ int ipa_round_fold_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *challenge, co
   if ((rc = rt::copy_h2d(d_chi, challenge_inv, 32, s))) return rc;
   if ((rc = rt::launch<256>(FrAxpyBody<R>{st->d_coeffs, d_chi, st->d_coeffs + 8 * m}, m, s))) return rc;  // :691-693
   if ((rc = rt::launch<256>(FrAxpyBody<R>{st->d_z, d_ch, st->d_z + 8 * m}, m, s))) return rc;              // :695-697
-  G1FoldBody<C> fb; fb.key = (Affine<C> *)st->d_key; fb.m = (uint32_t)m;
   uint64_t canon[4];
   host::fr_from_mont_host<R>(challenge, canon);
-  memcpy(fb.chal, canon, 32);
-  if ((rc = rt::launch<128>(fb, m, s))) return rc;                                                          // :699-707
+  host::GlvSplit gs;
+  gs.ok = false;
+  if (C::Fq::COFACTOR_ONE) {                       // phi acts as lambda on the whole curve only when the cofactor is 1
+    const char *e = getenv("PCGPU_IPA_GLV");
+    if (!(e && e[0] == '0')) gs = host::glv_decompose<C>(canon);
+  }
+  if (gs.ok) {
+    G1FoldGlvBody<C> gb; gb.key = (Affine<C> *)st->d_key; gb.m = (uint32_t)m;
+    memcpy(gb.k1, gs.k1, sizeof gb.k1); memcpy(gb.k2, gs.k2, sizeof gb.k2);
+    gb.neg1 = gs.neg1; gb.neg2 = gs.neg2; gb.nbits = gs.nbits;
+    if ((rc = rt::launch<128>(gb, m, s))) return rc;                                                        // :699-707
+  } else {
+    G1FoldBody<C> fb; fb.key = (Affine<C> *)st->d_key; fb.m = (uint32_t)m;
+    memcpy(fb.chal, canon, 32);
+    if ((rc = rt::launch<128>(fb, m, s))) return rc;                                                        // :699-707
+  }
   st->n = m; st->view.n = m;
   return rt::stream_sync(s);
 }

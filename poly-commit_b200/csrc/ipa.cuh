@@ -38,6 +38,38 @@ struct G1FoldBody {
   }
 };
 
+// The same fold through the GLV endomorphism (curves with cofactor 1: Pallas, BN254): chal = k1 + k2 lambda with ~128-bit
+// k1, k2 (host_glv.hpp), chal * R = k1 * R + k2 * phi(R), phi(x, y) = (zeta x, y) -- one joint double-and-add ladder of
+// nbits <= 132 steps over {P1 = +-R, P2 = +-phi(R), P1 + P2} instead of 256 steps over {R}.  Every thread runs the same
+// scalar, so the ladder's control flow is uniform across the grid.
+template <class C>
+struct G1FoldGlvBody {
+  Affine<C> *key; uint32_t m; uint32_t k1[5], k2[5]; uint32_t neg1, neg2, nbits;
+  PCGPU_KERNEL_DEV void operator()(size_t i) const {
+    using Q = typename C::Fq;
+    Affine<C> r = load_affine<C>(key + m + i);
+    Affine<C> l = load_affine<C>(key + i);
+    if (r.is_inf()) { key[i] = l; return; }
+    Fp<Q> zeta;
+    for (int j = 0; j < Q::N; j++) zeta.l[j] = Q::glv_zeta(j);
+    Affine<C> p1 = r, p2;
+    p1.y = fp_cneg<Q>(r.y, neg1 != 0);
+    p2.x = fp_mul<Q>(r.x, zeta); p2.y = fp_cneg<Q>(r.y, neg2 != 0);
+    XYZZ<C> t = xyzz_from_affine<C>(p1);
+    xyzz_madd<C>(t, p2, false);                       // P1 + P2 (never exceptional for R != O: lambda != +-1)
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (int b = (int)nbits - 1; b >= 0; b--) {
+      acc = xyzz_dbl<C>(acc);
+      const uint32_t s = ((k1[b >> 5] >> (b & 31)) & 1) | (((k2[b >> 5] >> (b & 31)) & 1) << 1);
+      if (s == 1) xyzz_madd<C>(acc, p1, false);
+      else if (s == 2) xyzz_madd<C>(acc, p2, false);
+      else if (s == 3) xyzz_add<C>(acc, t);
+    }
+    xyzz_madd<C>(acc, l, false);
+    key[i] = xyzz_to_affine<C>(acc);
+  }
+};
+
 // SuccinctCheckPolynomial::compute_coeffs (ipa_pc/data_structures.rs:204-220): coeffs[idx] = product of challenge_i over
 // the set bits of idx, challenge_1 on the top bit.  One thread per coefficient (<= log_d multiplications).
 template <class R>

@@ -50,3 +50,15 @@ extern "C" int hostcheck_field_op(int field, int which, const uint32_t *a, const
   }
   return 0;
 }
+
+// GLV split of one canonical scalar (host_glv.hpp): curve 1 = BN254, 2 = Pallas.  out: k1[5], k2[5], neg1, neg2, nbits, ok
+#include "../../poly-commit_b200/csrc/host_glv.hpp"
+extern "C" int hostcheck_glv(int curve, const uint64_t *k, uint32_t *out) {
+  host::GlvSplit g;
+  if (curve == 1) g = host::glv_decompose<Bn254>(k);
+  else if (curve == 2) g = host::glv_decompose<Pallas>(k);
+  else return -1;
+  for (int i = 0; i < 5; i++) { out[i] = g.k1[i]; out[5 + i] = g.k2[i]; }
+  out[10] = g.neg1; out[11] = g.neg2; out[12] = g.nbits; out[13] = g.ok ? 1 : 0;
+  return 0;
+}

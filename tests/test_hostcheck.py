@@ -814,3 +814,59 @@ def test_msm_small_path_limits(eng, pc, monkeypatch):
     monkeypatch.setenv("PCGPU_MSM_SMALL", "0")
     got = eng.msm(srs, sc[:len(pats)])
     assert (got[0] == orc.msm(C.id, bases, sc, n=len(pats))[0]).all()
+
+
+@pytest.mark.parametrize("cname", ["bn254", "pallas"])
+def test_glv_split_of_the_fold_challenge(hostcheck_path, cname):
+    """host_glv.hpp: k = k1 + k2 * lambda (mod r) with both halves below 2^130, on edge and random scalars; lambda is the
+    eigenvalue of phi(x, y) = (zeta x, y) on the generator (re-derived here in Python integers)."""
+    lib = ctypes.CDLL(hostcheck_path)
+    C = pyref.Curve(cname)
+    r, p = C.r, C.p
+    cands_l = [l for l in (pow(g, (r - 1) // 3, r) for g in range(2, 12)) if l != 1]
+    cands_z = [z for z in (pow(g, (p - 1) // 3, p) for g in range(2, 12)) if z != 1]
+    pairs = {(z, l) for z in cands_z for l in cands_l if C.mul(l, C.g) == (z * C.g[0] % p, C.g[1])}
+    assert pairs
+    lams = {l for _, l in pairs}
+    g = np.random.default_rng(5)
+    ks = [0, 1, 2, r - 1, r - 2, (r - 1) // 2, 1 << 128, (1 << 128) - 1, 1 << 254 if r > 1 << 254 else 1 << 253]
+    ks += [int.from_bytes(g.bytes(32), "little") % r for _ in range(200)]
+    used = None
+    for k in ks:
+        kin = np.array([(k >> (64 * j)) & (2**64 - 1) for j in range(4)], dtype=np.uint64)
+        out = np.zeros(14, dtype=np.uint32)
+        assert lib.hostcheck_glv(C.id, kin.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert out[13] == 1, k
+        k1 = sum(int(out[i]) << (32 * i) for i in range(5)) * (-1 if out[10] else 1)
+        k2 = sum(int(out[5 + i]) << (32 * i) for i in range(5)) * (-1 if out[11] else 1)
+        assert abs(k1) < 1 << 130 and abs(k2) < 1 << 130 and out[12] == max(abs(k1).bit_length(), abs(k2).bit_length())
+        ok = [l for l in lams if (k1 + k2 * l) % r == k]
+        assert ok, k
+        used = ok[0] if k > 2 else used
+    assert used is not None
+
+
+@pytest.mark.parametrize("cname,n", [("pallas", 16), ("bn254", 8)])
+def test_ipa_fold_glv_equals_plain_ladder(eng, pc, cname, n, monkeypatch):
+    """the GLV key fold (G1FoldGlvBody) and the 256-step ladder (G1FoldBody) give the same keys: identical l / r / final key
+    with PCGPU_IPA_GLV=0 and =1, with an identity point in the key (the fold's early-out) and a tiny challenge."""
+    from poly_commit_b200 import ipa_pc
+    C = pyref.Curve(cname)
+    key = util.random_points(cname, n, seed=170)
+    key[n - 2] = 0                                               # identity in the right half
+    h_prime = util.random_points(cname, 1, seed=171)[0]
+    coeffs = util.rand_fr(cname, n, seed=172, mont=True)
+    point = util.rand_fr(cname, 1, seed=173, mont=True)[0]
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PCGPU_IPA_GLV", flag)
+        outs.append(ipa_pc.open_rounds(eng, C.id, key, coeffs, point, h_prime, 3))
+    for a, b in zip(outs[0]["l_vec"] + outs[0]["r_vec"], outs[1]["l_vec"] + outs[1]["r_vec"]):
+        assert (a == b).all()
+    assert (outs[0]["final_comm_key"] == outs[1]["final_comm_key"]).all()
+    # and against the oracle on a key without the identity (the oracle's affine key has no encoding for it)
+    key = util.random_points(cname, n, seed=174)
+    monkeypatch.setenv("PCGPU_IPA_GLV", "1")
+    got = ipa_pc.open_rounds(eng, C.id, key, coeffs, point, h_prime, 3)
+    exp = oracle_ipa_rounds(cname, key, coeffs, point, h_prime, 3)
+    assert (got["final_comm_key"] == exp["final_comm_key"]).all() and (got["c"] == exp["c"]).all()

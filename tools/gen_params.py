@@ -88,6 +88,44 @@ def sqrt_consts(p):
     return dict(ts=1, s=s, exp=(t - 1) // 2, root=pow(g, t, p))
 
 
+def glv_consts(c):
+    """GLV data for y^2 = x^3 + b: phi(x, y) = (zeta x, y) acts as multiplication by lambda on the order-r group.
+    Returns zeta (mod p), lambda (mod r) and a reduced lattice basis (a1, b1), (a2, b2) of {(a, b): a + b lambda = 0 mod r}
+    with a1 b2 - a2 b1 = +r (extended Euclid on (r, lambda), stopped around sqrt(r))."""
+    p, r = c["p"], c["r"]
+    G = (c["gx"] % p, c["gy"] % p)
+    g = 2
+    while pow(g, (p - 1) // 3, p) == 1:
+        g += 1
+    z0 = pow(g, (p - 1) // 3, p)
+    l0 = pow(c["fr_gen"], (r - 1) // 3, r)
+    assert l0 != 1 and pow(l0, 3, r) == 1
+    pick = None
+    for zeta in (z0, z0 * z0 % p):
+        for lam in (l0, l0 * l0 % r):
+            if ec_mul(lam, G, p) == (zeta * G[0] % p, G[1]):
+                pick = (zeta, lam)
+    assert pick is not None
+    zeta, lam = pick
+    # r_i = s_i r + t_i lam
+    rows = [(r, 1, 0), (lam, 0, 1)]
+    while rows[-1][0] != 0:
+        q = rows[-2][0] // rows[-1][0]
+        rows.append(tuple(x - q * y for x, y in zip(rows[-2], rows[-1])))
+    sq = int(r ** 0.5)
+    l = max(i for i, row in enumerate(rows) if row[0] >= sq)
+    v1 = (rows[l + 1][0], -rows[l + 1][2])
+    cand = [(rows[l][0], -rows[l][2]), (rows[l + 2][0], -rows[l + 2][2])]
+    v2 = min(cand, key=lambda v: v[0] * v[0] + v[1] * v[1])
+    for a, b in (v1, v2):
+        assert (a + b * lam) % r == 0
+    det = v1[0] * v2[1] - v2[0] * v1[1]
+    if det < 0:
+        v2 = (-v2[0], -v2[1]); det = -det
+    assert det == r and max(abs(x) for x in v1 + v2) < 1 << 128
+    return dict(zeta=zeta, lam=lam, v1=v1, v2=v2)
+
+
 BLS_X = 0xd201000000010000          # |z| of BLS12-381 (z is negative); ark-bls12-381 `Config::X`
 
 
@@ -161,6 +199,12 @@ def main():
             extra_q += arrq("beta", 0) + "  static constexpr unsigned long long SUBGROUP_X = 0ull;\n  static constexpr int COFACTOR_ONE = 1;\n"
         nr = fr["n32"]
         extra_r = arrq("root_of_unity", root * Rr % r, nr) + f"  static constexpr int TWO_ADICITY = {c['two_adicity']};\n"
+        gl = glv_consts(c)
+        extra_q += "  // GLV endomorphism phi(x, y) = (glv_zeta x, y) = [glv_lambda] (x, y)  (ipa.cuh key folding)\n" + arrq("glv_zeta", gl["zeta"] * Rq % p)
+        extra_r += "  // GLV: lambda (Montgomery) and the lattice basis |a1|, |b1|, |a2|, |b2| (128-bit magnitudes) with their signs\n"
+        extra_r += arrq("glv_lambda", gl["lam"] * Rr % r, nr)
+        for nm, v in (("glv_a1", gl["v1"][0]), ("glv_b1", gl["v1"][1]), ("glv_a2", gl["v2"][0]), ("glv_b2", gl["v2"][1])):
+            extra_r += arrq(nm, abs(v), 4) + f"  static constexpr int {nm.upper()}_NEG = {1 if v < 0 else 0};\n"
         cuh.append(cuh_field(f"{CN}Fq", fq, extra_q))
         cuh.append(cuh_field(f"{CN}Fr", fr, extra_r))
         U = cname.upper()
