@@ -216,30 +216,30 @@ def main():
     import torch
     import pkgload
     pc = pkgload.load()
-    from oracle import orc, pyref  # cpu_baseline leg + SRS scalar powers only
-    from tests import util
+    from poly_commit_b200 import params  # the oracle is imported by the cpu_baseline leg only (cpu_port_run)
 
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     eng = pc.Engine(local_rank)  # raises without the CUDA library / an sm_100 device
-    C = pyref.Curve(CURVE)
+    cid = pc.CURVES[CURVE]
     n = (1 << log_deg) + 1
 
-    # ---- synthetic SRS on the device: P_i = beta^i G (KZG10::setup), then window-folded tables
-    beta = util.rand_fr(CURVE, 1, 1001, mont=True)[0]
-    pows = torch.from_numpy(orc.fr_powers_canonical(C.id, beta, n).view(np.int64)).cuda()
+    # ---- synthetic SRS on the device: P_i = k_i G for seeded random k_i (g.batch_mul, kzg10/mod.rs:76, with random
+    # scalars in place of the powers of beta: the commit / open kernels do not depend on the structure of the bases), then
+    # window-folded tables
+    pows = torch.from_numpy(params.random_fr(cid, n, 1001).view(np.int64)).cuda()
     d_bases = torch.empty((n, 12), dtype=torch.int64, device="cuda")
-    eng.fixed_base_mul(C.id, orc.g1_generator(C.id), pows.data_ptr(), n=n, flags=pc.DEVICE_PTRS, out=d_bases.data_ptr())
-    srs = eng.srs_register(C.id, d_bases.data_ptr(), n=n, flags=pc.DEVICE_PTRS | pc.SRS_PRECOMPUTE)
+    eng.fixed_base_mul(cid, params.g1_generator(cid), pows.data_ptr(), n=n, flags=pc.DEVICE_PTRS, out=d_bases.data_ptr())
+    srs = eng.srs_register(cid, d_bases.data_ptr(), n=n, flags=pc.DEVICE_PTRS | pc.SRS_PRECOMPUTE)
     del pows
 
     # ---- polynomials: distinct per rank and per step (rotating), pinned host copies + device copies
     n_polys = 4
-    host_polys = [torch.from_numpy(util.rand_fr_fast(CURVE, n, 100 + rank * n_polys + i).view(np.int64)).pin_memory() for i in range(n_polys)]
+    host_polys = [torch.from_numpy(params.random_fr(cid, n, 100 + rank * n_polys + i).view(np.int64)).pin_memory() for i in range(n_polys)]
     dev_polys = [h.cuda() for h in host_polys]
-    z = util.rand_fr(CURVE, 1, seed=4, mont=True)[0]
+    z = params.random_fr(cid, 1, 4)[0]
     # `inflight` independent polynomials are processed concurrently, each on its own context (own stream + workspace),
     # sharing the read-only SRS tables: the latency-bound tails of one MSM overlap the multiply-bound phase of another.
     import threading

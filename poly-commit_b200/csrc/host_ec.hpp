@@ -25,7 +25,9 @@ template <class P>
 struct HFp {
   static constexpr int N = P::N / 2;
   uint64_t l[N];
-  static uint64_t mod(int i) { return (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32); }
+  struct ModTab { uint64_t v[P::N / 2]; ModTab() { for (int i = 0; i < P::N / 2; i++) v[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32); } };
+  static const uint64_t *modv() { static const ModTab t; return t.v; }
+  static uint64_t mod(int i) { return modv()[i]; }
   static uint64_t m0() {  // -p^-1 mod 2^64 by Newton iteration
     uint64_t p0 = mod(0), inv = 1;
     for (int i = 0; i < 7; i++) inv *= 2 - p0 * inv;
@@ -58,22 +60,30 @@ template <class P> inline HFp<P> sub(const HFp<P> &a, const HFp<P> &b) {
   return r;
 }
 template <class P> inline HFp<P> mul(const HFp<P> &a, const HFp<P> &b) {
+  // CIOS with the two carry chains interleaved ("no-carry" variant: valid because the top bit of every modulus word N-1 is
+  // clear, so t never needs an (N+1)-th word)
   constexpr int N = HFp<P>::N;
   static const uint64_t M0 = HFp<P>::m0();
-  uint64_t t[N + 2];
-  memset(t, 0, sizeof t);
+  const uint64_t *q = HFp<P>::modv();
+  uint64_t t[N];
+  for (int j = 0; j < N; j++) t[j] = 0;
   for (int i = 0; i < N; i++) {
-    uint64_t c = 0;
-    for (int j = 0; j < N; j++) { u128 s = (u128)a.l[j] * b.l[i] + t[j] + c; t[j] = (uint64_t)s; c = (uint64_t)(s >> 64); }
-    u128 s = (u128)t[N] + c; t[N] = (uint64_t)s; t[N + 1] = (uint64_t)(s >> 64);
-    uint64_t m = t[0] * M0;
-    s = (u128)m * HFp<P>::mod(0) + t[0]; c = (uint64_t)(s >> 64);
-    for (int j = 1; j < N; j++) { s = (u128)m * HFp<P>::mod(j) + t[j] + c; t[j - 1] = (uint64_t)s; c = (uint64_t)(s >> 64); }
-    s = (u128)t[N] + c; t[N - 1] = (uint64_t)s; t[N] = t[N + 1] + (uint64_t)(s >> 64);
+    const uint64_t bi = b.l[i];
+    u128 s = (u128)a.l[0] * bi + t[0];
+    uint64_t A = (uint64_t)(s >> 64), lo = (uint64_t)s;
+    const uint64_t m = lo * M0;
+    u128 r = (u128)m * q[0] + lo;
+    uint64_t Cc = (uint64_t)(r >> 64);
+    for (int j = 1; j < N; j++) {
+      s = (u128)a.l[j] * bi + t[j] + A; A = (uint64_t)(s >> 64);
+      r = (u128)m * q[j] + (uint64_t)s + Cc; Cc = (uint64_t)(r >> 64);
+      t[j - 1] = (uint64_t)r;
+    }
+    t[N - 1] = Cc + A;
   }
-  if (t[N] || geq_mod<P>(t)) sub_mod<P>(t);
-  HFp<P> r; memcpy(r.l, t, sizeof r.l);
-  return r;
+  if (geq_mod<P>(t)) sub_mod<P>(t);
+  HFp<P> rr; memcpy(rr.l, t, sizeof rr.l);
+  return rr;
 }
 template <class P> inline HFp<P> sqr(const HFp<P> &a) { return mul<P>(a, a); }
 template <class P> inline HFp<P> dbl(const HFp<P> &a) { return add<P>(a, a); }

@@ -12,19 +12,9 @@ All field elements are (.., 4) uint64 Montgomery Fr; points are Montgomery x||y 
 """
 import numpy as np
 
-from .binding import BLS12_381, BN254, PALLAS, SCALARS_MONT, fq_limbs
+from .binding import SCALARS_MONT, fq_limbs
 
-# public curve parameters (scalar-field and base-field moduli), needed for negation on the host
-FR_MODULUS = {
-    BLS12_381: 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001,
-    BN254: 21888242871839275222246405745257275088548364400416034343698204186575808495617,
-    PALLAS: 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001,
-}
-FQ_MODULUS = {
-    BLS12_381: 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab,
-    BN254: 21888242871839275222246405745257275088696311157297823662689037894645226208583,
-    PALLAS: 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001,
-}
+from .params import FQ_MODULUS, FR_MODULUS
 
 
 def _neg_limbs(limbs, mod):

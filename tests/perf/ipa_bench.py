@@ -2,7 +2,7 @@
 """Wall-clock of the InnerProductArgPC::open halving loop (cfg3: Pallas, 2^18) through the device-resident round API,
 with a per-phase split (l/r MSMs + inner products vs folds)."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import pkgload

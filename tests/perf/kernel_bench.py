@@ -3,12 +3,12 @@
 working sets larger than L2 or rotated) for the members of the path other than the headline step:
 the HBM-bound Fr kernels, the NTT, the MSM variants and the Hyrax / IPA batches.  Prints one JSON line per
 kernel with the algorithmic bytes of SURVEY.md section 8d and the achieved fraction of the measured HBM peak.
-Run on the GPU box:  python tools/kernel_bench.py > gpurun_out/kernel_bench.jsonl"""
+Run on the GPU box:  python tests/perf/kernel_bench.py > gpurun_out/kernel_bench.jsonl"""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

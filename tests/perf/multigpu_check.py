@@ -1,13 +1,13 @@
 #!/usr/bin/env python3
 """Run under torchrun on N GPUs (NCCL): index-range-sharded MSM with the NCCL all_gather point-sum
 (SURVEY.md 8e partitioning B) against the oracle, at 2^16 (direct) and 2^20 (vs the single-GPU result of rank 0).
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multigpu_check.py"""
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/perf/multigpu_check.py"""
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

@@ -2,7 +2,7 @@
 """Where does a small MSM spend its time?  Wall clock per call and the per-stage device times (pcgpu_profile_get)
 for n = 2^8 .. 2^14, raw bases (no window folding) -- the shape of IPA's late rounds and of cfg1 (degree 2^10)."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import pkgload

@@ -1,13 +1,13 @@
 #!/usr/bin/env python3
 """SRS ingestion timing on one GPU: pcgpu_g1_deserialize / pcgpu_g1_serialize at 2^20 points (BLS12-381, BN254, Pallas),
 host buffers (copies inside the timed region) and device pointers (kernel + status read only).
-  python tools/wire_bench.py > gpurun_out/wire_bench.json"""
+  python tests/perf/wire_bench.py > gpurun_out/wire_bench.json"""
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch
