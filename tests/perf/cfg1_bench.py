@@ -28,8 +28,10 @@ def main():
     for _ in range(reps):
         comm = eng.kzg_commit(srs, poly); w = eng.kzg_open(srs, poly, z)
     gpu = (time.perf_counter() - t0) / reps
-    ec = orc.kzg_commit(C.id, bases, poly)
-    assert (ec[0] == comm[0]).all()
+    rc, exy, einf = orc.kzg_commit(C.id, bases, poly)
+    assert rc == 0 and (exy == comm[0]).all()
+    rc, wxy, winf, _ = orc.kzg_open(C.id, bases, poly, z)
+    assert rc == 0 and (wxy == w[0]).all()
     creps = 20
     t0 = time.perf_counter()
     for _ in range(creps):
