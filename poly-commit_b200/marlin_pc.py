@@ -91,3 +91,31 @@ def open(ck, polynomials, point, challenges):
     a = eng.msm_partial(ck.powers, eng.fr_div_linear(cid, p, point)[0], flags=SCALARS_MONT)
     b = eng.msm_partial(ck.shifted, shifted_w[: _degree(shifted_w) + 1], flags=SCALARS_MONT)
     return eng.g1_sum_xyzz(cid, np.concatenate([a, b]))
+
+
+def accumulate_commitments_and_values(eng, curve, commitments, values, challenges, shift_powers=None):
+    """Marlin::accumulate_commitments_and_values (marlin/mod.rs:109-148), the verifier-side combination:
+         combined_comm  = sum_i challenge_i * comm_i + challenge_i' * (shifted_comm_i - value_i * shift_power(bound_i))
+         combined_value = sum_i challenge_i * value_i
+    commitments: list of (comm_xy, shifted_comm_xy or None, degree_bound or None); values: (m, 4) Montgomery Fr;
+    challenges: iterator of Montgomery Fr in the order the sponge yields them (:123, :129-130); shift_powers: {bound: point}
+    (VerifierKey::get_shift_power).  One MSM over the commitments (pcgpu_msm_bases); returns ((xy, is_identity), value)."""
+    from .kzg10 import _neg_limbs
+    from .params import FR_MODULUS
+    ch = iter(challenges)
+    values = np.asarray(values, dtype=np.uint64).reshape(-1, 4)
+    bases, scalars, ch_plain = [], [], []
+    for (comm, shifted, bound), v in zip(commitments, values):
+        if (bound is None) != (shifted is None):
+            raise ValueError("degree bound and shifted commitment must come together")      # assert_eq!, :119
+        c = np.asarray(next(ch), dtype=np.uint64).reshape(4)
+        bases.append(np.asarray(comm, dtype=np.uint64).reshape(-1)); scalars.append(c); ch_plain.append(c)
+        if bound is not None:
+            if shift_powers is None or bound not in shift_powers:
+                raise ValueError("UnsupportedDegreeBound")                                  # :136
+            c1 = np.asarray(next(ch), dtype=np.uint64).reshape(4)
+            c1v = eng.fr_mul(curve, c1.reshape(1, 4), v.reshape(1, 4))[0]
+            bases += [np.asarray(shifted, dtype=np.uint64).reshape(-1), np.asarray(shift_powers[bound], dtype=np.uint64).reshape(-1)]
+            scalars += [c1, _neg_limbs(c1v, FR_MODULUS[curve])]
+    combined_value = eng.fr_inner_product(curve, np.stack(ch_plain), values[: len(ch_plain)])
+    return eng.msm_bases(curve, np.stack(bases), np.stack(scalars), flags=SCALARS_MONT), combined_value

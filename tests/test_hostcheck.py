@@ -302,6 +302,23 @@ def test_marlin_pc_host_mirror(eng, pc):
     assert rc == 0 and rc2 == 0 and (w[0] == exp).all()
     with pytest.raises(ValueError):
         marlin_pc.commit(ck, [(polys[2][0], 20)])                            # bound below the degree
+    # verifier side: Marlin::accumulate_commitments_and_values (marlin/mod.rs:109-148) on these commitments
+    vals_int = [pyref.poly_eval(C.fr_from_limbs(c, True), C.fr_from_limbs(point, True)[0], C.r) for c, _ in polys]
+    vals = C.fr_to_limbs(vals_int, True)
+    shift_powers = {b: pp[max_degree - b] for b in bounds}                  # beta^(max_degree - bound) G
+    triples = [(comm[0], None if sh is None else sh[0], bound) for (_, bound), (comm, sh) in zip(polys, coms)]
+    (acc, ainf), cval = marlin_pc.accumulate_commitments_and_values(eng, C.id, triples, vals, list(chals), shift_powers)
+    ch_int = C.fr_from_limbs(chals, True)
+    exp_pt, exp_val, ci = None, 0, 0
+    for (coeffs, bound), (comm, sh), v in zip(polys, coms, vals_int):
+        cp = C.points_from_limbs(comm[0].reshape(1, -1))[0]
+        exp_pt = C.add(exp_pt, C.mul(ch_int[ci], cp)); exp_val = (exp_val + ch_int[ci] * v) % C.r; ci += 1
+        if bound is not None:
+            sp = C.points_from_limbs(sh[0].reshape(1, -1))[0]
+            shp = C.points_from_limbs(shift_powers[bound].reshape(1, -1))[0]
+            exp_pt = C.add(exp_pt, C.mul(ch_int[ci], C.add(sp, C.neg(C.mul(v, shp))))); ci += 1
+    ex, _ = C.points_to_limbs([exp_pt])
+    assert not ainf and (acc == ex[0]).all() and C.fr_from_limbs(cval, True)[0] == exp_val
 
 
 def test_hyrax_host_mirror(eng, pc):
