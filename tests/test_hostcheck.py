@@ -887,3 +887,19 @@ def test_ipa_fold_glv_equals_plain_ladder(eng, pc, cname, n, monkeypatch):
     got = ipa_pc.open_rounds(eng, C.id, key, coeffs, point, h_prime, 3)
     exp = oracle_ipa_rounds(cname, key, coeffs, point, h_prime, 3)
     assert (got["final_comm_key"] == exp["final_comm_key"]).all() and (got["c"] == exp["c"]).all()
+
+
+def test_empty_inputs_on_the_widened_entry_points(eng, pc):
+    """n = 0 everywhere: the identity / empty arrays, no error (msm_bigint of nothing is zero; an empty Vec serializes to its
+    length prefix only)."""
+    from poly_commit_b200 import wire
+    cid = pc.BN254
+    xy, inf = eng.msm_bases(cid, np.zeros((0, 8), dtype=np.uint64), np.zeros((0, 4), dtype=np.uint64))
+    assert inf and not xy.any()
+    assert eng.g1_serialize(cid, np.zeros((0, 8), dtype=np.uint64)).shape == (0, 32)
+    assert eng.g1_deserialize(cid, b"", 0)[0].shape == (0, 8)
+    assert eng.ntt_batch(cid, np.zeros((0, 4, 4), dtype=np.uint64), 3).shape == (0, 8, 4)
+    blob = wire.powers_serialize(eng, cid, np.zeros((0, 8), dtype=np.uint64), np.zeros((0, 8), dtype=np.uint64))
+    assert blob == bytes(16)
+    (g, _), (h, _) = wire.powers_deserialize(eng, cid, blob)
+    assert g.shape[0] == 0 and h.shape[0] == 0
