@@ -80,6 +80,11 @@ def main():
         assert (pyref.poly_eval(poly, beta, C.r) - pyref.poly_eval(poly, zz, C.r)) % C.r == (beta - zz) * pyref.poly_eval(wq, beta, C.r) % C.r
         cur["kzg"] = {"powers": [[hx(b[0]), hx(b[1])] for b in powers], "poly": [hx(c) for c in poly], "z": hx(zz),
                       "commitment": [hx(comm[0]), hx(comm[1])], "witness": [hx(wit[0]), hx(wit[1])]}
+        # G1 wire formats (ark-serialize restatement, oracle/pyref.py): the multiples above, compressed and uncompressed.
+        # Only the BLS12-381 generator's compressed form is a published vector; the rest pins the restatement against drift.
+        wpts = [None if m["point"] is None else (int(m["point"][0], 16), int(m["point"][1], 16)) for m in cur["multiples"]] + [None]
+        cur["wire"] = {"compressed": pyref.g1_serialize(C, wpts, True).hex(), "uncompressed": pyref.g1_serialize(C, wpts, False).hex(),
+                       "count": len(wpts)}
         out["curves"][name] = cur
     out["reference_kats"] = {"row_mul": {"source": "poly-commit/src/utils.rs:274-286", "rows": [[10, 100, 4], [23, 1, 0], [55, 58, 9]],
                                          "v": [12, 41, 55], "result": [4088, 4431, 543]}}

@@ -101,6 +101,30 @@ def check_engine(eng, cname):
             assert (eng.ntt(C.id, _fr(C, t["coeffs"], True), t["logn"]) == _fr(C, t["evals"], True)).all()
 
 
+def wire_points(cname):
+    C = pyref.Curve(cname)
+    g = golden()["curves"][cname]
+    pts = [None if m["point"] is None else (int(m["point"][0], 16), int(m["point"][1], 16)) for m in g["multiples"]] + [None]
+    return C, g["wire"], pts
+
+
+def check_wire_oracle(cname):
+    C, w, pts = wire_points(cname)
+    assert w["count"] == len(pts)
+    for compressed, key in ((True, "compressed"), (False, "uncompressed")):
+        assert pyref.g1_serialize(C, pts, compressed).hex() == w[key]
+        assert pyref.g1_deserialize(C, bytes.fromhex(w[key]), len(pts), compressed) == pts
+
+
+def check_wire_engine(eng, cname):
+    C, w, pts = wire_points(cname)
+    xy, inf = C.points_to_limbs(pts)
+    for compressed, key in ((True, "compressed"), (False, "uncompressed")):
+        assert eng.g1_serialize(C.id, xy, inf, compressed).tobytes().hex() == w[key]
+        bxy, binf = eng.g1_deserialize(C.id, bytes.fromhex(w[key]), len(pts), compressed)
+        assert (bxy == xy).all() and (binf == inf).all()
+
+
 def check_row_mul_kat(eng):
     """utils.rs:274-286 test_row_mul, verbatim numbers, on every curve's Fr."""
     kat = golden()["reference_kats"]["row_mul"]

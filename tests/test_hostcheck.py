@@ -411,6 +411,7 @@ def test_row_mul_reference_kat(eng):
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
 def test_golden_vectors(eng, cname, msm_path):
     golden_cases.check_engine(eng, cname)
+    golden_cases.check_wire_engine(eng, cname)
 
 
 def oracle_ipa_rounds(cname, comm_key, coeffs, point, h_prime, round_challenge):
