@@ -904,3 +904,64 @@ def test_empty_inputs_on_the_widened_entry_points(eng, pc):
     assert blob == bytes(16)
     (g, _), (h, _) = wire.powers_deserialize(eng, cid, blob)
     assert g.shape[0] == 0 and h.shape[0] == 0
+
+
+@pytest.mark.parametrize("cname", ["bls12_381", "bn254", "pallas"])
+@pytest.mark.parametrize("compressed", [True, False])
+def test_wire_decode_fuzz_agrees_with_the_oracle(eng, pc, cname, compressed):
+    """random byte strings, and valid encodings with single random bit flips: the device decoder and the Python restatement
+    accept / reject the same inputs (same first offending index and reason) and decode accepted ones to the same points."""
+    C = pyref.Curve(cname)
+    sz = pyref.wire_size(C, compressed)
+    g = np.random.default_rng(77 + sz)
+    pts = C.points_from_limbs(util.random_points(cname, 6, seed=180))
+    good = bytearray(pyref.g1_serialize(C, pts, compressed))
+    cases = []
+    for _ in range(60):                                   # bit flips in otherwise valid data
+        b = bytearray(good)
+        k = int(g.integers(0, len(b)))
+        b[k] ^= 1 << int(g.integers(0, 8))
+        cases.append(bytes(b))
+    for _ in range(40):                                   # random blobs of 3 elements (flag bytes drawn from the interesting set)
+        b = bytearray(g.integers(0, 256, size=3 * sz, dtype=np.uint8).tobytes())
+        for e in range(3):
+            pos = e * sz if cname == "bls12_381" else (e + 1) * sz - 1
+            b[pos] = int(g.choice([0x00, 0x01, 0x20, 0x40, 0x80, 0x9f, 0xa0, 0xc0, 0xe0, 0x3f, 0x7f]))
+        cases.append(bytes(b))
+    accepted = 0
+    for data in cases:
+        n = len(data) // sz
+        for validate in (True, False):
+            try:
+                exp, exp_err = pyref.g1_deserialize(C, data, n, compressed, validate), None
+            except pyref.WireError as e:
+                exp, exp_err = None, (e.index, e.reason)
+            try:
+                got, got_err = eng.g1_deserialize(C.id, data, n, compressed, validate), None
+            except pc.binding.WireError as e:
+                got, got_err = None, (e.index, e.reason)
+            assert got_err == exp_err, (cname, compressed, validate, data.hex())
+            if exp is not None:
+                ex, ei = C.points_to_limbs(exp)
+                assert (got[0] == ex).all() and (got[1] == ei).all()
+                accepted += 1
+    assert accepted > 0
+
+
+@pytest.mark.parametrize("cname,n", [("bn254", 511), ("bn254", 512), ("pallas", 513), ("bls12_381", 1030)])
+def test_msm_small_split_boundaries(eng, pc, cname, n):
+    """the one-launch path around the size where a window's terms are divided among three blocks (512), with an identity
+    base, repeated scalars and Montgomery input."""
+    C = pyref.Curve(cname)
+    bases = util.random_points(cname, n, seed=190)
+    inf = np.zeros(n, dtype=np.uint8); inf[n // 2] = 1
+    sc = util.rand_fr(cname, n, seed=191, mont=False)
+    sc[10:40] = sc[10]
+    sc[n - 1] = C.fr_to_limbs([C.r - 1], False)[0]
+    srs = eng.srs_register(C.id, bases, inf=inf)
+    exp = orc.msm(C.id, bases, sc, inf=inf)
+    got = eng.msm(srs, sc)
+    assert got[1] == exp[1] and (got[0] == exp[0]).all()
+    scm = orc.field_unop("orc_fr_to_mont", C.id, sc)
+    got = eng.msm(srs, scm, flags=pc.SCALARS_MONT)
+    assert (got[0] == exp[0]).all()
