@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def _newest_source():
     srcs = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
-        [os.path.join(HERE, "..", "include", "pcgpu.h")]
+        glob.glob(os.path.join(CSRC, "*.hpp")) + [os.path.join(HERE, "..", "include", "pcgpu.h")]
     return max(os.path.getmtime(s) for s in srcs)
 
 
