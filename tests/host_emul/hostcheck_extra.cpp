@@ -62,3 +62,27 @@ extern "C" int hostcheck_glv(int curve, const uint64_t *k, uint32_t *out) {
   out[10] = g.neg1; out[11] = g.neg2; out[12] = g.nbits; out[13] = g.ok ? 1 : 0;
   return 0;
 }
+
+// host_ec.hpp's 64-bit Montgomery product (the MSM tail's arithmetic): out[i] = a[i] * b[i] / R, n elements of N64 limbs.
+// field ids as in hostcheck_field_op.
+template <class P>
+static void host_mul_many(const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+  constexpr int N = host::HFp<P>::N;
+  for (size_t i = 0; i < n; i++) {
+    host::HFp<P> x, y;
+    memcpy(x.l, a + i * N, sizeof x.l); memcpy(y.l, b + i * N, sizeof y.l);
+    host::HFp<P> r = host::mul<P>(x, y);
+    memcpy(out + i * N, r.l, sizeof r.l);
+  }
+}
+extern "C" int hostcheck_hostfield_mul(int field, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+  switch (field) {
+    case 0: host_mul_many<Bls12381Fq>(a, b, out, n); return 0;
+    case 1: host_mul_many<Bls12381Fr>(a, b, out, n); return 0;
+    case 2: host_mul_many<Bn254Fq>(a, b, out, n); return 0;
+    case 3: host_mul_many<Bn254Fr>(a, b, out, n); return 0;
+    case 4: host_mul_many<PallasFq>(a, b, out, n); return 0;
+    case 5: host_mul_many<PallasFr>(a, b, out, n); return 0;
+    default: return -1;
+  }
+}

@@ -965,3 +965,27 @@ def test_msm_small_split_boundaries(eng, pc, cname, n):
     scm = orc.field_unop("orc_fr_to_mont", C.id, sc)
     got = eng.msm(srs, scm, flags=pc.SCALARS_MONT)
     assert (got[0] == exp[0]).all()
+
+
+@pytest.mark.parametrize("cname,which,fid", FIELDS)
+def test_host_tail_field_product_vs_bigint(hostcheck_path, cname, which, fid):
+    """host_ec.hpp's 64-bit Montgomery product (interleaved-carry CIOS, used by the MSM tail, to_affine and the GLV check) on
+    edge values -- 0, 1, p-1, R, values with all-ones limbs -- and random ones, against Python integers."""
+    lib = ctypes.CDLL(hostcheck_path)
+    C = pyref.Curve(cname)
+    mod = getattr(C, which)
+    n64 = (mod.bit_length() + 63) // 64
+    R = (1 << (64 * n64)) % mod
+    Rinv = pow(R, -1, mod)
+    g = np.random.default_rng(40 + fid)
+    edge = [0, 1, 2, mod - 1, mod - 2, R, R * R % mod, mod >> 1, (mod >> 1) + 1, (1 << 64) - 1, ((1 << (64 * n64 - 2)) - 1) % mod,
+            ((1 << (64 * (n64 - 1))) - 1), (mod - 1) ^ ((1 << 64) - 1) if mod > 1 << 64 else 3]
+    edge = [e % mod for e in edge]
+    rnd = [int.from_bytes(g.bytes(8 * n64), "little") % mod for _ in range(2000)]
+    va = [a for a in edge for _ in edge] + rnd
+    vb = [b for _ in edge for b in edge] + rnd[::-1]
+    A, B = _tol(va, n64), _tol(vb, n64)
+    out = np.zeros_like(A)
+    vp = ctypes.c_void_p
+    assert lib.hostcheck_hostfield_mul(fid, A.ctypes.data_as(vp), B.ctypes.data_as(vp), out.ctypes.data_as(vp), ctypes.c_size_t(len(va))) == 0
+    assert (out == _tol([a * b * Rinv % mod for a, b in zip(va, vb)], n64)).all()
