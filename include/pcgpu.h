@@ -178,6 +178,15 @@ int pcgpu_ntt_split(uint32_t logn, uint32_t *m1, uint32_t *m2);
 int pcgpu_ntt_pass(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, int which, size_t lo, size_t count,
                    const void *in, size_t n_in, void *out);
 
+/* Pass 1 with the all-to-all fused into its stores: element k1 of column n2 is written straight into the row buffer of the
+ * rank that owns row k1, dst[k1 / rows][(k1 % rows) * N2 + n2] with rows = N1 / world.  dst[0 .. world) are device pointers
+ * valid on THIS device: the local row buffer and peer-mapped ones (cudaDeviceEnablePeerAccess / cudaIpcOpenMemHandle); each
+ * holds rows * N2 elements.  After a barrier every rank runs pcgpu_ntt_pass(which = 2, lo = rank * rows, count = rows) on its
+ * own buffer.  (Round-1 status: kernel and host logic verified under emulation with in-process "ranks"; the NVLink run is
+ * scheduled for the next round) */
+int pcgpu_ntt_pass1_peer(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, size_t lo, size_t count, const void *in, size_t n_in,
+                         void *const *dst, uint32_t world);
+
 /* ---- InnerProductArgPC::open halving loop, device-resident (ipa_pc/mod.rs:636-711) ------------------------- */
 typedef struct pcgpu_ipa pcgpu_ipa;
 /* Upload the committer key (n = d+1 affine points, n a power of two) and the combined polynomial's coefficients

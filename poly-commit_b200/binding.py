@@ -89,6 +89,8 @@ def _load(path):
                                  ctypes.POINTER(ctypes.c_int)],
         "pcgpu_ntt_split": [ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)],
         "pcgpu_ntt_pass": [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, _sz, _sz, _vp, _sz, _vp],
+        "pcgpu_ntt_pass1_peer": [_vp, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, _sz, _sz, _vp, _sz, ctypes.POINTER(_vp),
+                                 ctypes.c_uint32],
         "pcgpu_ntt_batch": [_vp, ctypes.c_int, _vp, _sz, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
         "pcgpu_ntt": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vp],
         "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
@@ -351,6 +353,12 @@ class Engine:
             raise WireError(rc, self.lib.pcgpu_strerror(rc).decode(), int(bad.value), int(reason.value))
         self._ck(rc)
         return xy, inf
+
+    def ntt_pass1_peer(self, curve, logn, lo, count, in_ptr, n_in, dst_ptrs, inverse=False):
+        """pass 1 on columns [lo, lo+count) storing straight into the row buffers dst_ptrs[rank] (device pointers as ints)"""
+        arr = (_vp * len(dst_ptrs))(*[ctypes.c_void_p(int(p)) for p in dst_ptrs])
+        self._ck(self.lib.pcgpu_ntt_pass1_peer(self.ctx, curve, logn, NTT_INVERSE if inverse else 0, lo, count, _ptr(in_ptr), n_in, arr,
+                                               len(dst_ptrs)))
 
     def ntt_batch(self, curve, rows, logn, inverse=False):
         """(count, n_in, 4) rows -> (count, 2^logn, 4): every row zero-padded and transformed (Ligero row encoding)"""

@@ -782,6 +782,31 @@ int ntt_impl(pcgpu_ctx *ctx, const void *in, size_t n_in, uint32_t logn, uint32_
 }
 
 template <class C>
+int ntt_pass1_peer_impl(pcgpu_ctx *ctx, uint32_t logn, uint32_t flags, size_t lo, size_t count, const void *in, size_t n_in,
+                        void *const *dst, uint32_t world) {
+  using R = typename C::Fr;
+  if (!ntt_supported(logn) || logn > (uint32_t)R::TWO_ADICITY || world == 0 || world > NTT_MAX_PEERS) return PCGPU_E_BADARG;
+  uint32_t m1, m2;
+  ntt_split(logn, &m1, &m2);
+  if (m2 == 0 || (((size_t)1 << m1) % world) != 0) return PCGPU_E_BADARG;
+  const size_t N2 = (size_t)1 << m2;
+  if (lo > N2 || count > N2 - lo) return PCGPU_E_LEN;
+  for (uint32_t d = 0; d < world; d++) if (!dst[d]) return PCGPU_E_BADARG;
+  rt::stream_t st = ctx->stream;
+  int rc, inverse = (flags & PCGPU_NTT_INVERSE) ? 1 : 0;
+  const NttPlan *plan = nullptr;
+  for (const NttPlan &p : ctx->ntt_plans) if (p.curve == C::ID && p.logn == logn && p.inverse == inverse) plan = &p;
+  if (!plan) {
+    NttPlan p;
+    if ((rc = ntt_build_plan<R>(p, C::ID, logn, inverse, st))) return rc;
+    ctx->ntt_plans.push_back(p);
+    plan = &ctx->ntt_plans.back();
+  }
+  if (count && (rc = ntt_run_pass1_peer<R>(*plan, lo, count, (const uint32_t *)in, n_in, (uint32_t *const *)dst, world, st))) return rc;
+  return rt::stream_sync(st);
+}
+
+template <class C>
 int ntt_batch_impl(pcgpu_ctx *ctx, const void *in, size_t n_in, size_t count, uint32_t logn, uint32_t flags, void *out) {
   using R = typename C::Fr;
   if (!ntt_supported(logn) || logn > (uint32_t)R::TWO_ADICITY) return PCGPU_E_BADARG;
@@ -1036,4 +1061,5 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int g1_serialize_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, uint8_t *); \
   EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *); \
   EXT template int fr_mul_impl<C>(pcgpu_ctx *, const void *, const void *, void *, size_t, uint32_t); \
-  EXT template int ntt_batch_impl<C>(pcgpu_ctx *, const void *, size_t, size_t, uint32_t, uint32_t, void *);
+  EXT template int ntt_batch_impl<C>(pcgpu_ctx *, const void *, size_t, size_t, uint32_t, uint32_t, void *); \
+  EXT template int ntt_pass1_peer_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, size_t, size_t, const void *, size_t, void *const *, uint32_t);

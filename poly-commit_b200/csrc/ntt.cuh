@@ -119,6 +119,57 @@ struct NttBlockBody {
   }
 };
 
+// Pass 1 of the sharded four-step transform with the all-to-all FUSED into its stores: the block that
+// transforms column n2 writes element k1 straight into the row buffer of the rank that owns row k1,
+//   dst[k1 / rows][(k1 % rows) * N2 + n2],   rows = N1 / world,
+// where dst[] are peer-mapped device pointers (NVLink P2P stores; plain pointers of one process under host emulation).
+// The exchange then overlaps the butterflies column by column and pass 2 starts after one barrier -- no staging buffer, no
+// separate collective.  Same arithmetic as NttBlockBody with step2 = 1 (kept separate so the validated kernel is untouched).
+enum { NTT_MAX_PEERS = 16 };
+template <class R>
+struct NttBlockPeerBody {
+  const uint32_t *in; uint32_t *dst[NTT_MAX_PEERS];
+  uint32_t m;                                // N1 = 2^m
+  uint64_t N2, n_valid, col_lo;              // this launch handles columns n2 = col_lo + batch
+  uint32_t rows;                             // N1 / world
+  const uint32_t *tw, *lo, *hi;
+  PCGPU_KERNEL_DEV void operator()(size_t batch, uint32_t *smem) const {
+    const uint32_t M = 1u << m;
+    const uint64_t n2 = col_lo + batch;
+    PCGPU_BLOCK_FOR(i, M) {
+      uint64_t idx = n2 + (uint64_t)i * N2;
+      Fp<R> v = idx < n_valid ? load_fr<R>(in, idx) : Fp<R>::zero();
+      uint32_t r = bitrev32(i, m);
+#pragma unroll
+      for (int l = 0; l < 8; l++) smem[l * M + r] = v.l[l];
+    }
+    PCGPU_BLOCK_SYNC();
+    for (uint32_t s = 0; s < m; s++) {
+      const uint32_t half = 1u << s;
+      PCGPU_BLOCK_FOR(b, M / 2) {
+        uint32_t pos = b & (half - 1);
+        uint32_t i0 = ((b >> s) << (s + 1)) + pos, i1 = i0 + half;
+        Fp<R> a, t;
+#pragma unroll
+        for (int l = 0; l < 8; l++) { a.l[l] = smem[l * M + i0]; t.l[l] = smem[l * M + i1]; }
+        if (s) t = fp_mul<R>(t, load_fr<R>(tw, (size_t)pos << (m - 1 - s)));
+        Fp<R> x = fp_add<R>(a, t), y = fp_sub<R>(a, t);
+#pragma unroll
+        for (int l = 0; l < 8; l++) { smem[l * M + i0] = x.l[l]; smem[l * M + i1] = y.l[l]; }
+      }
+      PCGPU_BLOCK_SYNC();
+    }
+    PCGPU_BLOCK_FOR(i, M) {
+      Fp<R> v;
+#pragma unroll
+      for (int l = 0; l < 8; l++) v.l[l] = smem[l * M + i];
+      uint64_t e = (uint64_t)i * n2;
+      if (e) v = fp_mul<R>(v, fp_mul<R>(load_fr<R>(hi, e >> NTT_LO_BITS), load_fr<R>(lo, e & ((1u << NTT_LO_BITS) - 1))));
+      store_fr<R>(dst[i / rows], (uint64_t)(i % rows) * N2 + n2, v);
+    }
+  }
+};
+
 inline void ntt_split(uint32_t logn, uint32_t *m1, uint32_t *m2) {
   if (logn <= NTT_MAX_LOG_BLOCK) { *m1 = logn; *m2 = 0; }
   else { *m1 = (logn + 1) / 2; *m2 = logn - *m1; }
@@ -174,6 +225,18 @@ inline int ntt_run_pass(const NttPlan &p, int which, uint64_t lo, uint64_t count
   }
   NttBlockBody<R> b{in, out, p.m2, 1, N2, count, 1, count * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0, ~0u};
   return rt::launch_blocks<256>(b, count, (size_t)N2 * 32, st);
+}
+
+template <class R>
+inline int ntt_run_pass1_peer(const NttPlan &p, uint64_t lo, uint64_t count, const uint32_t *in, size_t n_in, uint32_t *const *dst,
+                              uint32_t world, rt::stream_t st) {
+  const uint64_t N1 = (uint64_t)1 << p.m1, N2 = (uint64_t)1 << p.m2;
+  NttBlockPeerBody<R> b;
+  b.in = in;
+  for (uint32_t d = 0; d < NTT_MAX_PEERS; d++) b.dst[d] = d < world ? dst[d] : nullptr;
+  b.m = p.m1; b.N2 = N2; b.n_valid = n_in; b.col_lo = lo; b.rows = (uint32_t)(N1 / world);
+  b.tw = p.tw1; b.lo = p.lo; b.hi = p.hi;
+  return rt::launch_blocks<256>(b, count, (size_t)N1 * 32, st);
 }
 
 // `count` independent transforms of rows laid out back to back (row r = in[r * n_in .. (r+1) * n_in), zero-padded to N) --

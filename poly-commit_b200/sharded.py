@@ -101,3 +101,36 @@ class ShardedNtt:
         self.dist.all_gather(gathered, out_local)
         full = torch.stack(gathered, dim=0).permute(1, 0, 2, 3).contiguous()            # [k2][r][k1_local] = natural order
         return full.reshape(N1 * N2, 4).cpu().numpy().view(np.uint64)
+
+
+class PeerNtt:
+    """Four-step NTT over the GPUs of ONE process with the exchange fused into pass 1's stores (`pcgpu_ntt_pass1_peer`):
+    engine g runs on device g, owns `rows = N1 / world` rows, and every pass-1 block writes its column's elements straight
+    into the owners' row buffers over NVLink peer mappings -- no staging buffer and no separate all-to-all; pass 2 starts
+    after one device-wide synchronisation.  `alloc(rank, nbytes)` returns a device pointer on device `rank` that every other
+    device can store to (the caller enables peer access, e.g. torch tensors after `cudaDeviceEnablePeerAccess`); `engines`
+    are `Engine` objects, one per device.  Under host emulation all "devices" are the host and the pointers are numpy buffers
+    (tests/test_hostcheck.py::test_ntt_pass1_with_fused_exchange).  STATUS: the kernel and this host logic are verified under
+    emulation only; the multi-GPU run over NVLink is the first item of the next round."""
+
+    def __init__(self, engines, curve, logn):
+        self.engines, self.curve, self.logn = engines, curve, logn
+        self.world = len(engines)
+        self.m1, self.m2 = engines[0].ntt_split(logn)
+        if self.m2 == 0:
+            raise ValueError("transform too small to shard (single block pass)")
+        self.N1, self.N2 = 1 << self.m1, 1 << self.m2
+        if self.N1 % self.world or self.N2 % self.world:
+            raise ValueError("world size must divide both factors")
+
+    def forward(self, in_ptrs, n_in, row_ptrs, out_ptrs, inverse=False, sync=None):
+        """in_ptrs[g]: the (zero-padded at n_in) input on device g; row_ptrs[g]: rows*N2-element exchange buffer on device g,
+        writable from every device; out_ptrs[g]: N2*rows-element result slice [k2][k1_local] on device g.  `sync()` must drain
+        all devices (between the passes every buffer has to be complete)."""
+        rows, cols = self.N1 // self.world, self.N2 // self.world
+        for g, e in enumerate(self.engines):
+            e.ntt_pass1_peer(self.curve, self.logn, g * cols, cols, in_ptrs[g], n_in, row_ptrs, inverse=inverse)
+        if sync is not None:
+            sync()
+        for g, e in enumerate(self.engines):
+            e.ntt_pass(self.curve, self.logn, 2, g * rows, rows, row_ptrs[g], rows * self.N2, out_ptrs[g], inverse=inverse)

@@ -989,3 +989,39 @@ def test_host_tail_field_product_vs_bigint(hostcheck_path, cname, which, fid):
     vp = ctypes.c_void_p
     assert lib.hostcheck_hostfield_mul(fid, A.ctypes.data_as(vp), B.ctypes.data_as(vp), out.ctypes.data_as(vp), ctypes.c_size_t(len(va))) == 0
     assert (out == _tol([a * b * Rinv % mod for a, b in zip(va, vb)], n64)).all()
+
+
+@pytest.mark.parametrize("cname,logn,world", [("bls12_381", 12, 2), ("bn254", 13, 4), ("pallas", 14, 8)])
+def test_ntt_pass1_with_fused_exchange(eng, cname, logn, world):
+    """pcgpu_ntt_pass1_peer: every "rank" transforms its columns and stores straight into the owners' row buffers (the fused
+    all-to-all); pass 2 on each buffer then yields the same transform as the single call.  Ranks are simulated in-process:
+    under emulation a device pointer is a host pointer, so the peer table is just the list of buffers."""
+    C = pyref.Curve(cname)
+    m1, m2 = eng.ntt_split(logn)
+    N1, N2 = 1 << m1, 1 << m2
+    rows, cols = N1 // world, N2 // world
+    n_in = (1 << logn) - 5
+    x = util.rand_fr(cname, n_in, seed=200 + logn, mont=True)
+    for inverse in (False, True):
+        rowbufs = [np.zeros((rows, N2, 4), dtype=np.uint64) for _ in range(world)]
+        ptrs = [b.ctypes.data for b in rowbufs]
+        for r in range(world):
+            eng.ntt_pass1_peer(C.id, logn, r * cols, cols, x.ctypes.data, n_in, ptrs, inverse=inverse)
+        outs = []
+        for r in range(world):
+            o = np.zeros((N2, rows, 4), dtype=np.uint64)
+            eng.ntt_pass(C.id, logn, 2, r * rows, rows, rowbufs[r].ctypes.data, rows * N2, o.ctypes.data, inverse=inverse)
+            outs.append(o)
+        got = np.stack(outs, 0).transpose(1, 0, 2, 3).reshape(-1, 4)
+        assert (got == eng.ntt(C.id, x, logn, inverse=inverse)).all()
+    # the host-side driver (one engine per "device")
+    from poly_commit_b200 import sharded
+    pn = sharded.PeerNtt([eng] * world, C.id, logn)
+    rowbufs = [np.zeros((rows, N2, 4), dtype=np.uint64) for _ in range(world)]
+    outs = [np.zeros((N2, rows, 4), dtype=np.uint64) for _ in range(world)]
+    pn.forward([x.ctypes.data] * world, n_in, [b.ctypes.data for b in rowbufs], [o.ctypes.data for o in outs])
+    assert (np.stack(outs, 0).transpose(1, 0, 2, 3).reshape(-1, 4) == eng.ntt(C.id, x, logn)).all()
+    with pytest.raises(Exception):
+        eng.ntt_pass1_peer(C.id, logn, 0, cols, x.ctypes.data, n_in, [ptrs[0]] * 3)        # 3 ranks do not divide N1
+    with pytest.raises(Exception):
+        eng.ntt_pass1_peer(C.id, logn, N2 - 1, 2, x.ctypes.data, n_in, ptrs)                # columns out of range
