@@ -18,7 +18,7 @@ from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_
                                   test_row_mul_reference_kat, test_golden_vectors, test_ntt_vs_oracle, test_msm_batch_shared_bases, test_ipa_open_rounds, test_msm_batched_affine_rounds, test_hyrax_host_mirror, test_marlin_pc_host_mirror, test_kzg_commit_batch, test_msm_two_level_reduction, test_msm_heavy_buckets,
                                   test_wire_roundtrip_vs_oracle, test_wire_bls12_381_generator_known_answer,
                                   test_wire_rejects_like_the_oracle, test_wire_kzg_containers, test_msm_bases_unregistered,
-                                  test_kzg10_batch_check_combination, test_ligero_reed_solomon_like_the_reference, test_msm_small_path_limits, test_ipa_fold_glv_equals_plain_ladder,
+                                  test_kzg10_batch_check_combination, test_ligero_reed_solomon_like_the_reference, test_msm_small_path_limits, test_ipa_fold_glv_equals_plain_ladder, test_sonic_pc_host_mirror,
                                   test_ligero_compute_matrices)
 
 pytestmark = pytest.mark.gpu

@@ -1025,3 +1025,41 @@ def test_ntt_pass1_with_fused_exchange(eng, cname, logn, world):
         eng.ntt_pass1_peer(C.id, logn, 0, cols, x.ctypes.data, n_in, [ptrs[0]] * 3)        # 3 ranks do not divide N1
     with pytest.raises(Exception):
         eng.ntt_pass1_peer(C.id, logn, N2 - 1, 2, x.ctypes.data, n_in, ptrs)                # columns out of range
+
+
+def test_sonic_pc_host_mirror(eng, pc):
+    """sonic_pc.commit / open (mirror of sonic_pc/mod.rs:274-382) vs the oracle composed the same way: a bounded polynomial is
+    committed against shifted_powers(bound) only, and the opening is ONE KZG10 proof of the challenge-weighted combination."""
+    from poly_commit_b200 import sonic_pc
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    max_degree, bounds = 40, [20, 33]
+    pp = util.synthetic_srs(cname, max_degree + 1, seed=8)
+    supported = 36
+    powers = pp[: supported + 1]
+    shifted = pp[max_degree - bounds[-1]:]                                   # trim(): powers_of_g[lowest_shift_degree..]
+    ck = sonic_pc.CommitterKey(eng, C.id, powers, shifted, bounds)
+    polys = [(util.rand_fr(cname, 30, seed=210, mont=True), None), (util.rand_fr(cname, 18, seed=211, mont=True), 20),
+             (util.rand_fr(cname, 34, seed=212, mont=True), 33)]
+    coms = sonic_pc.commit(ck, polys)
+    for (coeffs, bound), comm in zip(polys, coms):
+        key = powers if bound is None else shifted[bounds[-1] - bound:]
+        rc, exy, einf = orc.kzg_commit(C.id, key, coeffs)
+        assert rc == 0 and (comm[0] == exy).all() and comm[1] == einf
+    # a bounded commitment is beta^(max_degree - bound) times the plain one: the relation the Sonic verifier's pairing checks
+    beta = C.fr_from_limbs(util.rand_fr(cname, 1, 1000 + 8, mont=True), True)[0]
+    plain = eng.kzg_commit(ck.powers, polys[1][0])
+    shifted_pt = C.points_from_limbs(coms[1][0].reshape(1, -1))[0]
+    assert C.mul(pow(beta, max_degree - 20, C.r), C.points_from_limbs(plain[0].reshape(1, -1))[0]) == shifted_pt
+    point = util.rand_fr(cname, 1, seed=213, mont=True)[0]
+    chals = util.rand_fr(cname, 3, seed=214, mont=True)
+    w = sonic_pc.open(ck, polys, point, list(chals))
+    p = np.zeros((34, 4), dtype=np.uint64)
+    for (coeffs, _), c in zip(polys, chals):
+        p[: len(coeffs)] = orc.fr_axpy(C.id, p[: len(coeffs)], c, coeffs)
+    rc, w0, winf, _ = orc.kzg_open(C.id, powers, p, point)
+    assert rc == 0 and (w[0] == w0).all() and w[1] == winf
+    with pytest.raises(ValueError):
+        sonic_pc.commit(ck, [(polys[2][0], 20)])                              # bound below the degree
+    with pytest.raises(ValueError):
+        sonic_pc.commit(ck, [(polys[1][0], 21)])                              # bound that was not enforced at trim
