@@ -40,7 +40,7 @@ def main():
     cid = pc.BLS12_381
     res = {"world": world}
     engines = [pc.Engine(g) for g in range(world)]
-    for logn in (16, 22, 24):
+    for logn in (16, 20, 22):
         n_in = (1 << logn) - 3
         x = params.random_fr(cid, n_in, 5)
         pn = sharded.PeerNtt(engines, cid, logn)
