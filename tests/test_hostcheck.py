@@ -1063,3 +1063,35 @@ def test_sonic_pc_host_mirror(eng, pc):
         sonic_pc.commit(ck, [(polys[2][0], 20)])                              # bound below the degree
     with pytest.raises(ValueError):
         sonic_pc.commit(ck, [(polys[1][0], 21)])                              # bound that was not enforced at trim
+
+
+@pytest.mark.parametrize("cname", ["pallas", "bn254"])
+def test_ipa_fold_special_challenges(eng, pc, cname, monkeypatch):
+    """the key fold key_l + c * key_r (ipa_pc/mod.rs:699-701) for challenges that stress the GLV split -- 1, r-1, the
+    eigenvalue lambda itself and its square (k1 = 0 or k2 = 0), powers of two around 2^128 -- with identity points in both
+    halves: GLV ladder == 256-step ladder == the definition in Python integers."""
+    from poly_commit_b200 import params
+    C = pyref.Curve(cname)
+    r = C.r
+    lam = [l for l in (pow(g, (r - 1) // 3, r) for g in range(2, 12)) if l != 1][0]
+    chals = [1, 2, r - 1, lam, lam * lam % r, (lam + 1) % r, 1 << 127, 1 << 128, (1 << 129) + 1, (r - 1) // 2, (lam << 64) % r]
+    m = 4
+    key = util.random_points(cname, 2 * m, seed=400)
+    key[m + 1] = 0
+    key[2] = 0
+    inf = np.array([0 if k.any() else 1 for k in key], dtype=np.uint8)
+    coeffs, z = util.rand_fr(cname, 2 * m, seed=1, mont=True), util.rand_fr(cname, 1, seed=2, mont=True)[0]
+    for c in chals:
+        outs = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("PCGPU_IPA_GLV", flag)
+            st = eng.ipa_begin(C.id, key, coeffs, z)
+            while eng.ipa_len(st) > 1:
+                eng.ipa_round_fold(st, params.fr_mont(C.id, c), params.fr_mont(C.id, pow(c, -1, r)))
+            outs.append(eng.ipa_finish(C.id, st)[0].copy())
+        pts = C.points_from_limbs(key, inf=inf)
+        while len(pts) > 1:
+            h = len(pts) // 2
+            pts = [C.add(pts[i], C.mul(c, pts[h + i])) for i in range(h)]
+        ex, _ = C.points_to_limbs(pts)
+        assert (outs[0] == outs[1]).all() and (outs[0].reshape(-1) == ex[0]).all(), hex(c)
