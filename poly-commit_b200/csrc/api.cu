@@ -14,7 +14,7 @@ extern "C" const char *pcgpu_strerror(int code) {
     case PCGPU_E_CUDA: return "CUDA failure or no usable sm_100 device";
     case PCGPU_E_OOM: return "device memory allocation failed";
     case PCGPU_E_BADARG: return "bad argument";
-    case PCGPU_E_LEN: return "base_offset + n exceeds the registered bases";
+    case PCGPU_E_LEN: return "length out of range (base_offset + n exceeds the registered bases, or the input is longer than the transform / slice)";
     case PCGPU_E_RANGE: return "canonical scalar out of range (not a reduced field element)";
     case PCGPU_E_DEGREE: return "TooManyCoefficients: polynomial degree too large for the powers";
     case PCGPU_E_HIDING: return "HidingBoundToolarge: blinding polynomial too large for powers_of_gamma_g";
