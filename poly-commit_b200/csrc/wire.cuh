@@ -169,7 +169,14 @@ struct G1DecodeBody {
       const bool fc = (f & 0x80) != 0;
       is_inf = (f & 0x40) != 0; y_flag = (f & 0x20) != 0;
       if (fc != (compressed != 0)) { finish(WIRE_BAD_FLAGS, false, x, y); return; }
+      // EncodingFlags::get_flags (ark-bls12-381 curves/util.rs): the sort flag is only legal on a compressed finite point
+      if (y_flag && (!fc || is_inf)) { finish(WIRE_BAD_FLAGS, false, x, y); return; }
       buf[0] &= 0x1f;
+      if (is_inf) {   // read_g1_{compressed,uncompressed}: the payload of the identity must be all zero (canonical encoding only)
+        uint8_t any = 0;
+        for (int k = 0; k < sz; k++) any |= buf[k];
+        if (any) { finish(WIRE_NOT_CANONICAL, false, x, y); return; }
+      }
     } else {
       // flags sit in the last byte of the flagged element (x when compressed, y otherwise)
       uint8_t &last = buf[sz - 1];
@@ -181,15 +188,14 @@ struct G1DecodeBody {
     if (is_inf && BE) { finish(WIRE_OK, true, x, y); return; }
     uint32_t xl[N], yl[N];
     limbs_from_bytes<Q>(buf, compressed ? XF : XP, BE, xl);
-    // the generic form carries one byte beyond the limbs when bits + 2 > 8 * 4N' (Pallas: 33 bytes); it must be zero
-    bool extra = false;
-    for (int k = 4 * N; k < (compressed ? XF : XP); k++) extra |= buf[k] != 0;
-    if (extra || limbs_ge_mod<Q>(xl)) { finish(WIRE_NOT_CANONICAL, false, x, y); return; }
+    // the generic form carries one byte beyond the limbs when bits + 2 > 8 * 4N' (Pallas: 33 bytes).  ark-ff's
+    // deserialize_with_flags strips the flag bits from that byte and then converts only the 8N'-byte limb buffer
+    // (SerBuffer::to_bigint), so its six low bits are IGNORED, not checked -- mirrored here (limbs_from_bytes stops at 4N bytes).
+    if (limbs_ge_mod<Q>(xl)) { finish(WIRE_NOT_CANONICAL, false, x, y); return; }
     if (!compressed) {
       const uint8_t *yb = buf + XP;
       limbs_from_bytes<Q>(yb, BE ? XP : XF, BE, yl);
-      for (int k = 4 * N; k < (BE ? XP : XF); k++) extra |= yb[k] != 0;
-      if (extra || limbs_ge_mod<Q>(yl)) { finish(WIRE_NOT_CANONICAL, false, x, y); return; }
+      if (limbs_ge_mod<Q>(yl)) { finish(WIRE_NOT_CANONICAL, false, x, y); return; }
     }
     if (is_inf) { finish(WIRE_OK, true, x, y); return; }
     for (int j = 0; j < N; j++) x.l[j] = xl[j];
