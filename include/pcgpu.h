@@ -47,7 +47,8 @@ enum {
   PCGPU_E_RANGE = -5,  /* a canonical scalar is >= 2^255 (2^254 for BN254): not a reduced field element */
   PCGPU_E_DEGREE = -6, /* Error::TooManyCoefficients, kzg10/mod.rs:392-402 */
   PCGPU_E_HIDING = -7, /* Error::HidingBoundToolarge, kzg10/mod.rs:404-422 */
-  PCGPU_E_INVALID = -8 /* SerializationError::{InvalidData, UnexpectedFlags}: a wire-format element failed to decode / validate */
+  PCGPU_E_INVALID = -8, /* SerializationError::{InvalidData, UnexpectedFlags}: a wire-format element failed to decode / validate */
+  PCGPU_E_PEER = -9     /* multi-GPU exchange: a peer did not signal within the wait budget, or its record is malformed */
 };
 
 /* flags */
@@ -182,10 +183,36 @@ int pcgpu_ntt_pass(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, int
  * rank that owns row k1, dst[k1 / rows][(k1 % rows) * N2 + n2] with rows = N1 / world.  dst[0 .. world) are device pointers
  * valid on THIS device: the local row buffer and peer-mapped ones (cudaDeviceEnablePeerAccess / cudaIpcOpenMemHandle); each
  * holds rows * N2 elements.  After a barrier every rank runs pcgpu_ntt_pass(which = 2, lo = rank * rows, count = rows) on its
- * own buffer.  (Round-1 status: kernel and host logic verified under emulation with in-process "ranks"; the NVLink run is
- * scheduled for the next round) */
+ * own buffer (pcgpu_peer_signal / pcgpu_peer_wait below are that barrier when the ranks are separate processes). */
 int pcgpu_ntt_pass1_peer(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, size_t lo, size_t count, const void *in, size_t n_in,
                          void *const *dst, uint32_t world);
+
+/* ---- multi-GPU over NVLink peer memory -------------------------------------------------------
+ * One process per GPU.  Every rank allocates ONE window (pcgpu_peer_window_bytes() bytes, zero-filled) with pcgpu_peer_alloc,
+ * the ranks exchange the 64-byte handles out of band (torch.distributed all_gather in poly_commit_b200.sharded.PeerGroup;
+ * MPI / a socket in a Rust host) and map each other's windows with pcgpu_peer_open (cudaIpcOpenMemHandle; NVLink P2P).
+ * win[0 .. world) below are the window pointers valid in THIS process: win[rank] is the local allocation, the others are
+ * the mapped peers.  Epochs are caller-chosen, strictly increasing per channel (flags are never reset).
+ *
+ * pcgpu_msm_peer: "MSM shards by scalar/base pair across the GPUs with a final point-sum over NVLink" (BASELINE.json
+ *   north_star; the reference computes the same sum in one msm_bigint call, kzg10/mod.rs:175-178): every rank calls it with
+ *   ITS slice of the scalars and an SRS holding ITS slice of the bases; the last kernel of the rank's Pippenger pipeline
+ *   stores the rank's bit-plane sums (~3 KB) into slot [rank] of every peer's window and raises a flag, a bounded spin on
+ *   the local window's flags follows on the same stream, and one device-to-host copy returns all records: every rank
+ *   obtains the full sum, affine, with no collective call.  flags: PCGPU_SCALARS_MONT, PCGPU_DEVICE_PTRS (scalars).
+ * pcgpu_peer_signal / pcgpu_peer_wait: raise flag [rank] of `channel` (0..7; channel 0 is used by pcgpu_msm_peer) in every
+ *   window / wait (bounded, PCGPU_E_PEER on expiry) until every flag of the local window reached `epoch` -- the barrier
+ *   between pcgpu_ntt_pass1_peer and pass 2 of the sharded NTT. */
+#define PCGPU_IPC_HANDLE_BYTES 64
+size_t pcgpu_peer_window_bytes(void);
+int pcgpu_peer_alloc(pcgpu_ctx *ctx, size_t bytes, void **out_ptr, uint8_t *handle /* PCGPU_IPC_HANDLE_BYTES */);
+int pcgpu_peer_open(pcgpu_ctx *ctx, const uint8_t *handle, void **out_ptr);
+int pcgpu_peer_close(pcgpu_ctx *ctx, void *mapped_ptr);
+int pcgpu_peer_free(pcgpu_ctx *ctx, void *ptr);
+int pcgpu_peer_signal(pcgpu_ctx *ctx, void *const *win, uint32_t rank, uint32_t world, uint32_t channel, uint64_t epoch);
+int pcgpu_peer_wait(pcgpu_ctx *ctx, void *local_win, uint32_t world, uint32_t channel, uint64_t epoch);
+int pcgpu_msm_peer(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n, uint32_t flags,
+                   void *const *win, uint32_t rank, uint32_t world, uint64_t epoch, void *out_xy, uint8_t *out_inf);
 
 /* ---- InnerProductArgPC::open halving loop, device-resident (ipa_pc/mod.rs:636-711) ------------------------- */
 typedef struct pcgpu_ipa pcgpu_ipa;

@@ -57,6 +57,8 @@ def _load(path):
     lib.pcgpu_g1_wire_size.argtypes = [ctypes.c_int, ctypes.c_uint32]
     lib.pcgpu_launch_count.restype = ctypes.c_uint64
     lib.pcgpu_launch_count.argtypes = []
+    lib.pcgpu_peer_window_bytes.restype = _sz
+    lib.pcgpu_peer_window_bytes.argtypes = []
     sigs = {
         "pcgpu_init": [ctypes.c_int, ctypes.POINTER(_vp)],
         "pcgpu_destroy": [_vp],
@@ -96,6 +98,14 @@ def _load(path):
         "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
+        "pcgpu_peer_alloc": [_vp, _sz, ctypes.POINTER(_vp), _vp],
+        "pcgpu_peer_open": [_vp, _vp, ctypes.POINTER(_vp)],
+        "pcgpu_peer_close": [_vp, _vp],
+        "pcgpu_peer_free": [_vp, _vp],
+        "pcgpu_peer_signal": [_vp, ctypes.POINTER(_vp), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64],
+        "pcgpu_peer_wait": [_vp, _vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64],
+        "pcgpu_msm_peer": [_vp, _vp, _sz, _vp, _sz, ctypes.c_uint32, ctypes.POINTER(_vp), ctypes.c_uint32, ctypes.c_uint32,
+                           ctypes.c_uint64, _vp, _vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -377,6 +387,46 @@ class Engine:
         """one four-step pass on a slice of its batches; in_ptr / out_ptr are DEVICE pointers (ints)"""
         self._ck(self.lib.pcgpu_ntt_pass(self.ctx, curve, logn, NTT_INVERSE if inverse else 0, which, lo, count, _ptr(in_ptr), n_in,
                                          _ptr(out_ptr)))
+
+    # ---- multi-GPU over NVLink peer memory ----
+    def peer_window_bytes(self):
+        return int(self.lib.pcgpu_peer_window_bytes())
+
+    def peer_alloc(self, nbytes):
+        """zero-filled device buffer other processes can map -> (device pointer, 64-byte IPC handle)"""
+        p, h = _vp(), np.zeros(64, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_peer_alloc(self.ctx, nbytes, ctypes.byref(p), _ptr(h)))
+        return int(p.value), h
+
+    def peer_open(self, handle):
+        p, h = _vp(), np.ascontiguousarray(handle, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_peer_open(self.ctx, _ptr(h), ctypes.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, ptr):
+        self._ck(self.lib.pcgpu_peer_close(self.ctx, _vp(ptr)))
+
+    def peer_free(self, ptr):
+        self._ck(self.lib.pcgpu_peer_free(self.ctx, _vp(ptr)))
+
+    def peer_signal(self, win, rank, channel, epoch):
+        arr = (_vp * len(win))(*[ctypes.c_void_p(int(p)) for p in win])
+        self._ck(self.lib.pcgpu_peer_signal(self.ctx, arr, rank, len(win), channel, epoch))
+
+    def peer_wait(self, local_win, world, channel, epoch):
+        self._ck(self.lib.pcgpu_peer_wait(self.ctx, _vp(int(local_win)), world, channel, epoch))
+
+    def msm_peer(self, srs, scalars, win, rank, epoch, n=None, base_offset=0, flags=0):
+        """this rank's slice of an index-sharded MSM; the point-sum over all ranks is fused into the call -> (xy, is_identity)"""
+        scalars = _u64(scalars)
+        if n is None:
+            n = scalars.size // 4
+        arr = (_vp * len(win))(*[ctypes.c_void_p(int(p)) for p in win])
+        out = np.zeros(2 * fq_limbs(srs.curve), dtype=np.uint64)
+        inf = np.zeros(1, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_msm_peer(self.ctx, srs.handle, base_offset, _ptr(scalars), n, flags, arr, rank, len(win), epoch,
+                                         _ptr(out), _ptr(inf)))
+        return out, int(inf[0])
 
     # ---- IPA halving loop (device-resident state) ----
     def ipa_begin(self, curve, comm_key_xy, coeffs, point, n=None, flags=0):

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Builds poly-commit_b200/libpcgpu.so: nvcc, sm_100a only, one translation unit per curve in parallel.
+"""Builds poly-commit_b200/libpcgpu.so: nvcc, sm_100a only, one translation unit per (curve, kernel group) in parallel.
 No GPU is needed to build (nvcc cross-compiles).  Re-builds only when a source is newer than the library."""
 import concurrent.futures
 import glob
@@ -11,7 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpcgpu.so")
-UNITS = ["api", "inst_bls12_381", "inst_bn254", "inst_pallas"]
+CURVES = ["Bls12381", "Bn254", "Pallas"]
+GROUPS = [1, 2, 3, 4, 5]   # inst_unit.cu: Pippenger pipeline | small MSM | SRS + MSM entry points | Fr / NTT | IPA + wire
+# heaviest first so the thread pool keeps every core busy to the end
+UNITS = [("inst_unit", c, g) for g in GROUPS for c in CURVES] + [("api", None, None)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -22,10 +25,13 @@ def _newest_source():
 
 
 def _compile(unit, extra):
-    out = os.path.join(OBJ, unit + ".o")
-    cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, unit + ".cu"), "-o", out]
+    src, curve, group = unit
+    name = src if curve is None else f"{src}_{curve.lower()}_{group}"
+    out = os.path.join(OBJ, name + ".o")
+    defs = [] if curve is None else [f"-DPCGPU_UNIT_CURVE={curve}", f"-DPCGPU_UNIT_GROUP={group}"]
+    cmd = ["nvcc"] + NVCC_FLAGS + defs + extra + ["-c", os.path.join(CSRC, src + ".cu"), "-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    return unit, r.returncode, r.stdout + r.stderr, out
+    return name, r.returncode, r.stdout + r.stderr, out
 
 
 def build(force=False, verbose=False, extra=()):
@@ -33,7 +39,7 @@ def build(force=False, verbose=False, extra=()):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     extra = list(extra) + (["-Xptxas", "-v"] if verbose else [])
-    with concurrent.futures.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+    with concurrent.futures.ThreadPoolExecutor(max_workers=max(2, min(len(UNITS), os.cpu_count() or 4))) as ex:
         results = list(ex.map(lambda u: _compile(u, extra), UNITS))
     objs = []
     for unit, rc, log, out in results:

@@ -19,6 +19,7 @@ extern "C" const char *pcgpu_strerror(int code) {
     case PCGPU_E_DEGREE: return "TooManyCoefficients: polynomial degree too large for the powers";
     case PCGPU_E_HIDING: return "HidingBoundToolarge: blinding polynomial too large for powers_of_gamma_g";
     case PCGPU_E_INVALID: return "SerializationError: wire-format element failed to decode or validate";
+    case PCGPU_E_PEER: return "multi-GPU exchange failed: a peer did not signal in time, or sent a malformed record";
     default: return "unknown error";
   }
 }
@@ -425,4 +426,109 @@ extern "C" int pcgpu_ntt_pass1_peer(pcgpu_ctx *ctx, int curve, uint32_t logn, ui
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return ntt_pass1_peer_impl<C>(ctx, logn, flags, lo, count, in, n_in, dst, world));
+}
+
+// ---- multi-GPU over NVLink peer memory (peer.cuh) ---------------------------------------------------------------------
+extern "C" size_t pcgpu_peer_window_bytes(void) { return (size_t)PEER_WINDOW_BYTES; }
+
+extern "C" int pcgpu_peer_alloc(pcgpu_ctx *ctx, size_t bytes, void **out_ptr, uint8_t *handle) {
+  if (!ctx || !out_ptr || !handle || bytes == 0) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  void *p = nullptr;
+  int rc = rt::dev_malloc(&p, bytes);
+  if (rc) return rc;
+  memset(handle, 0, PCGPU_IPC_HANDLE_BYTES);
+#ifndef PCGPU_EMUL
+  if (cudaMemset(p, 0, bytes) != cudaSuccess) { rt::dev_free(p); return PCGPU_E_CUDA; }
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) <= PCGPU_IPC_HANDLE_BYTES, "IPC handle larger than the ABI's handle");
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { rt::dev_free(p); return PCGPU_E_CUDA; }
+  memcpy(handle, &h, sizeof h);
+#else
+  memset(p, 0, bytes);
+  memcpy(handle, &p, sizeof p);   // emulation: every "rank" lives in this process
+#endif
+  *out_ptr = p;
+  return PCGPU_OK;
+}
+
+extern "C" int pcgpu_peer_open(pcgpu_ctx *ctx, const uint8_t *handle, void **out_ptr) {
+  if (!ctx || !handle || !out_ptr) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+#ifndef PCGPU_EMUL
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  void *p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return PCGPU_E_CUDA; }
+  *out_ptr = p;
+#else
+  memcpy(out_ptr, handle, sizeof(void *));
+#endif
+  return PCGPU_OK;
+}
+
+extern "C" int pcgpu_peer_close(pcgpu_ctx *ctx, void *mapped) {
+  if (!ctx || !mapped) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+#ifndef PCGPU_EMUL
+  cudaStreamSynchronize(ctx->stream);
+  if (cudaIpcCloseMemHandle(mapped) != cudaSuccess) return PCGPU_E_CUDA;
+#endif
+  return PCGPU_OK;
+}
+
+extern "C" int pcgpu_peer_free(pcgpu_ctx *ctx, void *ptr) {
+  if (!ctx || !ptr) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+#ifndef PCGPU_EMUL
+  cudaStreamSynchronize(ctx->stream);
+#endif
+  rt::dev_free(ptr);
+  return PCGPU_OK;
+}
+
+static int peer_args_ok(void *const *win, uint32_t rank, uint32_t world) {
+  if (!win || world == 0 || world > (uint32_t)PEER_MAX_WORLD || rank >= world) return 0;
+  for (uint32_t d = 0; d < world; d++) if (!win[d]) return 0;
+  return 1;
+}
+
+extern "C" int pcgpu_peer_signal(pcgpu_ctx *ctx, void *const *win, uint32_t rank, uint32_t world, uint32_t channel, uint64_t epoch) {
+  if (!ctx || !peer_args_ok(win, rank, world) || channel >= 8) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  PeerSignalBody b;
+  memset(&b, 0, sizeof b);
+  for (uint32_t d = 0; d < world; d++) b.win[d] = (char *)win[d];
+  b.rank = rank; b.world = world; b.flag_off = (uint32_t)PEER_FLAG_OFFSET + 256u * channel; b.epoch = epoch;
+  int rc = rt::launch<32>(b, world, ctx->stream);
+  if (rc) return rc;
+  return rt::stream_sync(ctx->stream);
+}
+
+extern "C" int pcgpu_peer_wait(pcgpu_ctx *ctx, void *local_win, uint32_t world, uint32_t channel, uint64_t epoch) {
+  if (!ctx || !local_win || world == 0 || world > (uint32_t)PEER_MAX_WORLD || channel >= 8) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  rt::stream_t st = ctx->stream;
+  uint32_t *d_timeout = (uint32_t *)((char *)ctx->d_slots + SLOT_BYTES * NSLOTS);
+  int rc;
+  if ((rc = rt::dev_memset(d_timeout, 0, 4, st))) return rc;
+  if ((rc = rt::launch<32>(PeerWaitBody{(const char *)local_win, world, (uint32_t)PEER_FLAG_OFFSET + 256u * channel, epoch, PEER_WAIT_CYCLES, d_timeout}, world, st))) return rc;
+  uint32_t t = 0;
+  if ((rc = rt::copy_d2h(&t, d_timeout, 4, st))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  return t ? PCGPU_E_PEER : PCGPU_OK;
+}
+
+extern "C" int pcgpu_msm_peer(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n, uint32_t flags,
+                              void *const *win, uint32_t rank, uint32_t world, uint64_t epoch, void *out_xy, uint8_t *out_inf) {
+  if (!ctx || !srs || (n && !scalars) || !out_xy || !peer_args_ok(win, rank, world) || epoch == 0) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(srs->curve, return msm_peer_impl<C>(ctx, srs, base_offset, scalars, n, flags, win, rank, world, epoch, out_xy, out_inf));
 }

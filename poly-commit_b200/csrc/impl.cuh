@@ -5,6 +5,7 @@
 // g++ with -DPCGPU_EMUL into tests/host_emul/libpcgpu_hostcheck.so, a unit-test harness that runs
 // the kernel bodies serially; the package never loads that library.
 #pragma once
+#include <memory>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -20,6 +21,7 @@
 #include "srs.cuh"
 #include "wire.cuh"
 #include "msm_small.cuh"
+#include "peer.cuh"
 
 using namespace pcgpu;
 
@@ -82,6 +84,7 @@ struct pcgpu_ctx {
 };
 
 static const size_t SLOT_BYTES = 256;  // >= sizeof(XYZZ<Bls12381>) = 192
+enum { PCGPU_MAX_PLANES = 512 };  // S * c of any geometry msm_geometry produces (W <= 32 windows of <= 22 bits, S <= W)
 static const int NSLOTS = 8;
 
 #ifndef PCGPU_EMUL
@@ -152,7 +155,7 @@ inline bool msm_small_enabled() {
   return !(e && e[0] == '0');
 }
 template <class C>
-static int msm_small_to_host(pcgpu_ctx *ctx, const MsmSmallProblem<C> *probs, uint32_t nprob, bool mont, host::HXYZZ<C> *out) {
+int msm_small_to_host(pcgpu_ctx *ctx, const MsmSmallProblem<C> *probs, uint32_t nprob, bool mont, host::HXYZZ<C> *out) {
   using R = typename C::Fr;
   constexpr uint32_t W = small_windows<R>();
   rt::stream_t st = ctx->stream;
@@ -195,18 +198,12 @@ static int msm_small_to_host(pcgpu_ctx *ctx, const MsmSmallProblem<C> *probs, ui
   return PCGPU_OK;
 }
 
-// One MSM: device pipeline, then the S*c bit-plane sums come back to the host, which combines them
-// (host_ec.hpp).  d_scalars: device, n x 8 u32.  Synchronises the stream.
+// Device half of one bucket-pipeline MSM (n > SMALL_MAX_N or the small path disabled): picks the geometry, runs msm_run on
+// the context's stream and returns (asynchronously) the compact S*c bit-plane sums and the error word.
 template <class C>
-static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const uint32_t *d_scalars, size_t n,
-                       bool mont, host::HXYZZ<C> *out) {
+int msm_device_planes(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const uint32_t *d_scalars, size_t n,
+                             bool mont, MsmGeom *g_out, const XYZZ<C> **d_planes, size_t *stride, uint32_t **d_err) {
   rt::stream_t st = ctx->stream;
-  *out = host::HXYZZ<C>::inf();
-  if (n == 0) return PCGPU_OK;
-  if (n <= SMALL_MAX_N && msm_small_enabled()) {
-    MsmSmallProblem<C> pr{(const Affine<C> *)srs->d_tables + base_offset, d_scalars, nullptr, nullptr, (uint32_t)n};
-    return msm_small_to_host<C>(ctx, &pr, 1, mont, out);
-  }
   uint32_t c, groups;
   const uint32_t *tables = (const uint32_t *)srs->d_tables;
   uint32_t pt_words = 2 * C::Fq::N, y_words = C::Fq::N;
@@ -235,22 +232,39 @@ static int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset,
     if ((rc = rt::dev_malloc((void **)&ctx->d_pow2[C::ID], (size_t)(64 * QP::N + 1) * QP::N * 4))) return rc;
     if ((rc = rt::launch<32>(Pow2TableBody<QP>{ctx->d_pow2[C::ID]}, 1, st))) return rc;
   }
+  *g_out = g;
+  return msm_run<C>(tables, g, d_scalars, ctx->msm_arena, d_planes, stride, d_err, st, ctx->prof, ctx->d_pow2[C::ID]);
+}
+
+// One MSM: device pipeline, then the S*c bit-plane sums come back to the host, which combines them
+// (host_ec.hpp).  d_scalars: device, n x 8 u32.  Synchronises the stream.
+template <class C>
+int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const uint32_t *d_scalars, size_t n,
+                       bool mont, host::HXYZZ<C> *out) {
+  rt::stream_t st = ctx->stream;
+  *out = host::HXYZZ<C>::inf();
+  if (n == 0) return PCGPU_OK;
+  if (n <= SMALL_MAX_N && msm_small_enabled()) {
+    MsmSmallProblem<C> pr{(const Affine<C> *)srs->d_tables + base_offset, d_scalars, nullptr, nullptr, (uint32_t)n};
+    return msm_small_to_host<C>(ctx, &pr, 1, mont, out);
+  }
+  MsmGeom g;
   const XYZZ<C> *d_planes = nullptr; size_t stride = 0; uint32_t *d_err = nullptr;
-  rc = msm_run<C>(tables, g, d_scalars, ctx->msm_arena, &d_planes, &stride, &d_err, st, ctx->prof,
-                  ctx->d_pow2[C::ID]);
+  int rc = msm_device_planes<C>(ctx, srs, base_offset, d_scalars, n, mont, &g, &d_planes, &stride, &d_err);
   if (rc) return rc;
   size_t np = (size_t)g.S * g.c;   // one-level: c planes per set; two-level: (h+1) + (c-1-h) = c planes per set as well
-  std::vector<host::HXYZZ<C>> planes(np);
   static_assert(sizeof(host::HXYZZ<C>) == sizeof(XYZZ<C>), "host/device point layouts must agree");
+  host::HXYZZ<C> planes[PCGPU_MAX_PLANES];
+  if (np > PCGPU_MAX_PLANES) return PCGPU_E_BADARG;
   uint32_t herr = 0;
-  if ((rc = rt::copy_d2h_2d(planes.data(), sizeof(XYZZ<C>), d_planes, stride * sizeof(XYZZ<C>), sizeof(XYZZ<C>), np, st))) return rc;
+  if ((rc = rt::copy_d2h_2d(planes, sizeof(XYZZ<C>), d_planes, stride * sizeof(XYZZ<C>), sizeof(XYZZ<C>), np, st))) return rc;
   if ((rc = rt::copy_d2h(&herr, d_err, sizeof herr, st))) return rc;
   if ((rc = rt::stream_sync(st))) return rc;
   ctx->prof.collect();
   if (herr) return PCGPU_E_RANGE;
   auto t0 = std::chrono::steady_clock::now();
-  *out = g.h_split ? host::combine_bit_planes_2level<C>(planes.data(), g.S, g.c, g.h_split)
-                   : host::combine_bit_planes<C>(planes.data(), g.S, g.c);
+  *out = g.h_split ? host::combine_bit_planes_2level<C>(planes, g.S, g.c, g.h_split)
+                   : host::combine_bit_planes<C>(planes, g.S, g.c);
   if (ctx->prof.on) {
     ctx->prof.ms[6] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     ctx->prof.cnt[6]++;
@@ -286,6 +300,83 @@ int msm_impl(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const voi
   if ((rc = msm_to_host<C>(ctx, srs, base_offset, d_scalars, n, (flags & PCGPU_SCALARS_MONT) != 0, &r))) return rc;
   if (out_xyzz) { memcpy(out_xyzz, &r, sizeof r); return PCGPU_OK; }
   host::to_affine<C>(r, out_xy, out_inf);
+  return PCGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// index-range-sharded MSM with the point-sum fused into the pipeline tail (peer.cuh; SURVEY.md 8e partitioning B)
+// ---------------------------------------------------------------------------------------------
+static const long long PEER_WAIT_CYCLES = 6000000000ll;   // ~3 s at 1.9 GHz: a missing peer becomes PCGPU_E_PEER, not a hang
+
+template <class C>
+int msm_peer_impl(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n, uint32_t flags,
+                  void *const *win, uint32_t rank, uint32_t world, uint64_t epoch, void *out_xy, uint8_t *out_inf) {
+  if (base_offset > srs->n || n > srs->n - base_offset) return PCGPU_E_LEN;
+  rt::stream_t st = ctx->stream;
+  const bool mont = (flags & PCGPU_SCALARS_MONT) != 0;
+  int rc;
+  const uint32_t *d_scalars = nullptr;
+  if (n) {
+    if (!(flags & PCGPU_DEVICE_PTRS)) {
+      if ((rc = ctx->stage.reserve(rt::Arena::pad(n * 32) + 4096))) return rc;
+    }
+    uint32_t *buf = (flags & PCGPU_DEVICE_PTRS) ? nullptr : ctx->stage.take<uint32_t>(n * 8);
+    if ((rc = stage_words(ctx, scalars, n * 32, flags, &d_scalars, buf))) return rc;
+  }
+  MsmPeerPushBody push;
+  memset(&push, 0, sizeof push);
+  for (uint32_t d = 0; d < world; d++) push.win[d] = (char *)win[d];
+  push.rank = rank; push.world = world; push.epoch = epoch;
+  uint32_t *d_timeout = (uint32_t *)((char *)ctx->d_slots + SLOT_BYTES * NSLOTS);
+  bool pipeline = n > SMALL_MAX_N || (n > 0 && !msm_small_enabled());
+  MsmGeom g;
+  if (pipeline) {
+    const XYZZ<C> *d_planes = nullptr; size_t stride = 0; uint32_t *d_err = nullptr;
+    if ((rc = msm_device_planes<C>(ctx, srs, base_offset, d_scalars, n, mont, &g, &d_planes, &stride, &d_err))) return rc;
+    const size_t np = (size_t)g.S * g.c;
+    if (sizeof(PeerRecordHeader) + np * sizeof(XYZZ<C>) <= (size_t)PEER_RECORD_BYTES && stride == 1) {
+      push.planes = (const uint32_t *)d_planes; push.plane_words = (uint32_t)(np * sizeof(XYZZ<C>) / 4);
+      push.hdr.np = (uint32_t)np; push.hdr.S = g.S; push.hdr.c = g.c; push.hdr.h_split = g.h_split; push.d_err = d_err;
+    } else {
+      pipeline = false;   // record too large for a slot (no window folding): send the combined partial instead
+    }
+  }
+  if (!pipeline) {
+    // small or unfolded MSM: this rank's partial is finished on the host and pushed as a one-plane record
+    host::HXYZZ<C> part;
+    if ((rc = msm_to_host<C>(ctx, srs, base_offset, d_scalars, n, mont, &part))) return rc;
+    XYZZ<C> *d_one = (XYZZ<C> *)ctx->d_slots;
+    if ((rc = rt::copy_h2d(d_one, &part, sizeof part, st))) return rc;
+    push.planes = (const uint32_t *)d_one; push.plane_words = sizeof(XYZZ<C>) / 4;
+    push.hdr.np = 1; push.hdr.S = 1; push.hdr.c = 1; push.hdr.h_split = 0; push.d_err = nullptr;
+  }
+  if ((rc = rt::dev_memset(d_timeout, 0, 4, st))) return rc;
+  ctx->prof.begin(13, st);
+  if ((rc = rt::launch_blocks<128>(push, world, 0, st))) return rc;
+  if ((rc = rt::launch<32>(PeerWaitBody{(const char *)win[rank], world, (uint32_t)PEER_FLAG_OFFSET, epoch, PEER_WAIT_CYCLES, d_timeout}, world, st))) return rc;
+  ctx->prof.end(13, st);
+  // ONE copy brings every rank's record back
+  std::unique_ptr<char[]> rec(new (std::nothrow) char[(size_t)world * PEER_RECORD_BYTES]);
+  if (!rec) return PCGPU_E_OOM;
+  uint32_t timed_out = 0;
+  if ((rc = rt::copy_d2h(rec.get(), win[rank], (size_t)world * PEER_RECORD_BYTES, st))) return rc;
+  if ((rc = rt::copy_d2h(&timed_out, d_timeout, 4, st))) return rc;
+  if ((rc = rt::stream_sync(st))) return rc;
+  ctx->prof.collect();
+  if (timed_out) return PCGPU_E_PEER;
+  host::HXYZZ<C> acc = host::HXYZZ<C>::inf();
+  for (uint32_t r = 0; r < world; r++) {
+    const char *p = rec.get() + (size_t)r * PEER_RECORD_BYTES;
+    PeerRecordHeader h;
+    memcpy(&h, p, sizeof h);
+    if (h.err) return PCGPU_E_RANGE;
+    if (h.np == 0 || h.np > PCGPU_MAX_PLANES || sizeof h + (size_t)h.np * sizeof(XYZZ<C>) > (size_t)PEER_RECORD_BYTES || h.np != h.S * h.c) return PCGPU_E_PEER;
+    host::HXYZZ<C> planes[PEER_RECORD_BYTES / sizeof(XYZZ<C>) + 1];
+    memcpy(planes, p + sizeof h, (size_t)h.np * sizeof(XYZZ<C>));
+    acc = host::padd<C>(acc, h.h_split ? host::combine_bit_planes_2level<C>(planes, h.S, h.c, h.h_split)
+                                       : host::combine_bit_planes<C>(planes, h.S, h.c));
+  }
+  host::to_affine<C>(acc, out_xy, out_inf);
   return PCGPU_OK;
 }
 
@@ -1034,32 +1125,45 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
 #endif
 }
 
-// Explicit instantiation list: `PCGPU_INSTANTIATE(Curve, extern)` declares, `PCGPU_INSTANTIATE(Curve, )` defines.
-#define PCGPU_INSTANTIATE(C, EXT)                                                                                          \
+// Explicit instantiation lists, one per translation-unit group so that the heavy kernels of one curve compile in parallel
+// (inst_unit.cu is built once per (curve, group); `EXT` = extern declares, empty defines).  The three msm_* helpers are
+// instantiated in ONE group and only declared elsewhere, so the Pippenger kernels are compiled exactly once per curve.
+#define PCGPU_INST_PIPE(C, EXT)                                                                                            \
+  EXT template int msm_device_planes<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const uint32_t *, size_t, bool, MsmGeom *, \
+                                        const XYZZ<C> **, size_t *, uint32_t **);                                          \
+  EXT template int msm_to_host<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const uint32_t *, size_t, bool, host::HXYZZ<C> *);
+#define PCGPU_INST_SMALL(C, EXT)                                                                                           \
+  EXT template int msm_small_to_host<C>(pcgpu_ctx *, const MsmSmallProblem<C> *, uint32_t, bool, host::HXYZZ<C> *);
+#define PCGPU_INST_SRS(C, EXT)                                                                                             \
   EXT template int srs_register_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, pcgpu_srs *);        \
   EXT template int msm_impl<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const void *, size_t, uint32_t, void *, uint8_t *, void *); \
   EXT template int g1_sum_impl<C>(pcgpu_ctx *, const void *, size_t, void *, uint8_t *);                                   \
   EXT template int fixed_base_impl<C>(pcgpu_ctx *, const void *, const void *, size_t, uint32_t, void *);                  \
+  EXT template int kzg_commit_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const pcgpu_srs *, const void *, \
+                                      size_t, uint32_t, void *, uint8_t *);                                                \
+  EXT template int kzg_open_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const void *, const pcgpu_srs *, \
+                                    const void *, size_t, uint32_t, void *, uint8_t *, void *); \
+  EXT template int msm_batch_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, size_t, uint32_t, void *, uint8_t *); \
+  EXT template int msm_peer_impl<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const void *, size_t, uint32_t, void *const *, uint32_t, uint32_t, uint64_t, void *, uint8_t *);
+#define PCGPU_INST_FR(C, EXT)                                                                                              \
   EXT template int fr_from_mont_impl<C>(pcgpu_ctx *, const void *, void *, size_t, uint32_t);                              \
   EXT template int fr_axpy_impl<C>(pcgpu_ctx *, void *, const void *, const void *, size_t, uint32_t);                     \
   EXT template int fr_div_impl<C>(pcgpu_ctx *, const void *, size_t, const void *, void *, void *, uint32_t);              \
   EXT template int fr_ip_impl<C>(pcgpu_ctx *, const void *, const void *, size_t, void *, uint32_t);                       \
   EXT template int fr_row_mul_impl<C>(pcgpu_ctx *, const void *, const void *, size_t, size_t, void *, uint32_t);          \
-  EXT template int kzg_commit_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const pcgpu_srs *, const void *, \
-                                      size_t, uint32_t, void *, uint8_t *);                                                \
-  EXT template int kzg_open_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const void *, const pcgpu_srs *, \
-                                    const void *, size_t, uint32_t, void *, uint8_t *, void *); \
+  EXT template int fr_mul_impl<C>(pcgpu_ctx *, const void *, const void *, void *, size_t, uint32_t); \
   EXT template int selftest_field_impl<C>(pcgpu_ctx *, uint64_t, size_t, uint64_t *); \
   EXT template int ntt_impl<C>(pcgpu_ctx *, const void *, size_t, uint32_t, uint32_t, void *); \
-  EXT template int msm_batch_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, size_t, uint32_t, void *, uint8_t *); \
+  EXT template int ntt_pass_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, int, size_t, size_t, const void *, size_t, void *); \
+  EXT template int ntt_batch_impl<C>(pcgpu_ctx *, const void *, size_t, size_t, uint32_t, uint32_t, void *); \
+  EXT template int ntt_pass1_peer_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, size_t, size_t, const void *, size_t, void *const *, uint32_t);
+#define PCGPU_INST_IPA(C, EXT)                                                                                             \
   EXT template int ipa_begin_impl<C>(pcgpu_ctx *, const void *, size_t, const void *, size_t, const void *, uint32_t, pcgpu_ipa *); \
   EXT template int ipa_round_lr_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, void *, uint8_t *, void *, uint8_t *); \
   EXT template int ipa_round_fold_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, const void *); \
   EXT template int ipa_finish_impl<C>(pcgpu_ctx *, pcgpu_ipa *, void *, void *); \
   EXT template int ipa_check_final_key_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, uint32_t, void *, uint8_t *); \
-  EXT template int ntt_pass_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, int, size_t, size_t, const void *, size_t, void *); \
   EXT template int g1_serialize_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, uint8_t *); \
-  EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *); \
-  EXT template int fr_mul_impl<C>(pcgpu_ctx *, const void *, const void *, void *, size_t, uint32_t); \
-  EXT template int ntt_batch_impl<C>(pcgpu_ctx *, const void *, size_t, size_t, uint32_t, uint32_t, void *); \
-  EXT template int ntt_pass1_peer_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, size_t, size_t, const void *, size_t, void *const *, uint32_t);
+  EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *);
+#define PCGPU_INSTANTIATE(C, EXT) \
+  PCGPU_INST_PIPE(C, EXT) PCGPU_INST_SMALL(C, EXT) PCGPU_INST_SRS(C, EXT) PCGPU_INST_FR(C, EXT) PCGPU_INST_IPA(C, EXT)
