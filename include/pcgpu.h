@@ -70,7 +70,8 @@ const char *pcgpu_strerror(int code);
 int pcgpu_set_stream(pcgpu_ctx *ctx, void *cuda_stream);
 /* Per-stage device timings (CUDA events on the launching stream).  stage: 0 digits/count, 1 scan,
  * 2 scatter, 3 tasks, 4 bucket accumulate (XYZZ), 5 bucket reduce, 6 final (host tail, wall clock), 7 fr division,
- * 8 fr axpy, 9 ntt, 10 comb batch, 11 affine pair rounds (all), 12 affine pair round 0 kernel alone.
+ * 8 fr axpy, 9 ntt, 10 comb batch, 11 affine pair rounds (all), 12 affine pair round 0 kernel alone, 13 peer push + wait,
+ * 14 column hashes + Merkle tree.
  * enable=1 starts recording; get returns accumulated milliseconds and launch count since enable. */
 int pcgpu_profile_enable(pcgpu_ctx *ctx, int enable);
 int pcgpu_profile_get(pcgpu_ctx *ctx, int stage, double *ms, uint64_t *count);
@@ -186,6 +187,29 @@ int pcgpu_ntt_pass(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, int
  * own buffer (pcgpu_peer_signal / pcgpu_peer_wait below are that barrier when the ranks are separate processes). */
 int pcgpu_ntt_pass1_peer(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, size_t lo, size_t count, const void *in, size_t n_in,
                          void *const *dst, uint32_t world);
+
+/* ---- linear-code commitments: column hashes + Merkle tree ---------------------------------
+ * LinearCodePCS::commit steps 2-3, linear_codes/mod.rs:253-275, for the hashers the reference's tests and benches
+ * instantiate (linear_codes/{ligero,multilinear_ligero,brakedown}/tests.rs; bench-templates/src/lib.rs):
+ *   column hash   FieldToBytesColHasher<F, D> (linear_codes/utils.rs:208-236): D(u64 LE length || n_rows canonical 32-byte
+ *                 LE field elements), D = BLAKE2s-256 (PCGPU_HASH_BLAKE2S) or SHA-256 (PCGPU_HASH_SHA256)
+ *   Merkle tree   Leaf = Vec<u8> with LeafIdentityHasher, TwoToOneHash = ark-crypto-primitives sha256 (SHA-256(left || right)),
+ *                 ByteDigestConverter at the leaf level (each leaf digest is prefixed with its u64 length), leaves padded to
+ *                 a power of two with empty leaves (create_merkle_tree, linear_codes/mod.rs:507-523)
+ * pcgpu_lincode_hash_columns: ext_mat is n_rows x n_cols Montgomery Fr, row-major (Matrix<F>, utils.rs:49-53); out_leaves
+ *   receives n_cols x 32 bytes.  The matrix is read in place (one thread per column, rows coalesced across the warp).
+ * pcgpu_merkle_tree: n_leaves >= 2 digests of 32 bytes -> the P - 1 inner nodes (P = next power of two) in heap order
+ *   (node 0 = root, children of i are 2i+1, 2i+2 -- MerkleTree::non_leaf_nodes) and the 32-byte root (host pointer).
+ * pcgpu_lincode_commit: the whole commit of one polynomial matrix without leaving the device: every row of `mat`
+ *   (n_rows x n_cols) through reed_solomon to 2^log_ext_cols evaluations (compute_matrices, linear_codes/mod.rs:118-138),
+ *   column hashes, tree.  out_ext_mat (n_rows x 2^log_ext_cols), out_leaves, out_nodes may be NULL; out_root: host.
+ * With PCGPU_DEVICE_PTRS the matrix / leaves / nodes arguments are device pointers. */
+enum { PCGPU_HASH_BLAKE2S = 0, PCGPU_HASH_SHA256 = 1 };
+int pcgpu_lincode_hash_columns(pcgpu_ctx *ctx, int curve, const void *ext_mat, size_t n_rows, size_t n_cols, int hash, uint32_t flags,
+                               uint8_t *out_leaves);
+int pcgpu_merkle_tree(pcgpu_ctx *ctx, const uint8_t *leaves, size_t n_leaves, uint32_t flags, uint8_t *out_nodes, uint8_t *out_root);
+int pcgpu_lincode_commit(pcgpu_ctx *ctx, int curve, const void *mat, size_t n_rows, size_t n_cols, uint32_t log_ext_cols, int hash,
+                         uint32_t flags, void *out_ext_mat, uint8_t *out_leaves, uint8_t *out_nodes, uint8_t *out_root);
 
 /* ---- multi-GPU over NVLink peer memory -------------------------------------------------------
  * One process per GPU.  Every rank allocates ONE window (pcgpu_peer_window_bytes() bytes, zero-filled) with pcgpu_peer_alloc,

@@ -98,6 +98,9 @@ def _load(path):
         "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
+        "pcgpu_lincode_hash_columns": [_vp, ctypes.c_int, _vp, _sz, _sz, ctypes.c_int, ctypes.c_uint32, _vp],
+        "pcgpu_merkle_tree": [_vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
+        "pcgpu_lincode_commit": [_vp, ctypes.c_int, _vp, _sz, _sz, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, _vp, _vp, _vp, _vp],
         "pcgpu_peer_alloc": [_vp, _sz, ctypes.POINTER(_vp), _vp],
         "pcgpu_peer_open": [_vp, _vp, ctypes.POINTER(_vp)],
         "pcgpu_peer_close": [_vp, _vp],
@@ -387,6 +390,45 @@ class Engine:
         """one four-step pass on a slice of its batches; in_ptr / out_ptr are DEVICE pointers (ints)"""
         self._ck(self.lib.pcgpu_ntt_pass(self.ctx, curve, logn, NTT_INVERSE if inverse else 0, which, lo, count, _ptr(in_ptr), n_in,
                                          _ptr(out_ptr)))
+
+    # ---- linear-code commitments: column hashes + Merkle tree ----
+    def lincode_hash_columns(self, curve, ext_mat, n_rows=None, n_cols=None, hash=0, flags=0, out=None):
+        """leaves[j] = D(to_bytes!(column j)) for a row-major (n_rows, n_cols, 4) Montgomery matrix -> (n_cols, 32) uint8"""
+        ext_mat = _u64(ext_mat)
+        if n_rows is None:
+            n_rows, n_cols = ext_mat.shape[0], ext_mat.shape[1]
+        if out is None:
+            out = np.zeros((n_cols, 32), dtype=np.uint8)
+        self._ck(self.lib.pcgpu_lincode_hash_columns(self.ctx, curve, _ptr(ext_mat), n_rows, n_cols, hash, flags, _ptr(out)))
+        return out
+
+    def merkle_tree(self, leaves, n_leaves=None, flags=0, nodes=None):
+        """(n, 32) uint8 leaf digests -> (inner nodes (P - 1, 32) in heap order, root (32,))"""
+        if not isinstance(leaves, (int, np.integer)):
+            leaves = np.ascontiguousarray(leaves, dtype=np.uint8)
+            n_leaves = leaves.shape[0]
+        P = 1 << max(1, (n_leaves - 1).bit_length())
+        if nodes is None:
+            nodes = np.zeros((P - 1, 32), dtype=np.uint8)
+        root = np.zeros(32, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_merkle_tree(self.ctx, _ptr(leaves), n_leaves, flags, _ptr(nodes), _ptr(root)))
+        return nodes, root
+
+    def lincode_commit(self, curve, mat, log_ext_cols, n_rows=None, n_cols=None, hash=0, flags=0, want=("ext", "leaves", "nodes"),
+                       out_ext=None, out_leaves=None, out_nodes=None):
+        """row encoding + column hashes + Merkle tree in one device-resident call -> dict(root, ext?, leaves?, nodes?)"""
+        mat = _u64(mat)
+        if n_rows is None:
+            n_rows, n_cols = mat.shape[0], mat.shape[1]
+        N = 1 << log_ext_cols
+        if not (flags & DEVICE_PTRS):
+            out_ext = np.zeros((n_rows, N, 4), dtype=np.uint64) if "ext" in want else None
+            out_leaves = np.zeros((N, 32), dtype=np.uint8) if "leaves" in want else None
+            out_nodes = np.zeros((N - 1, 32), dtype=np.uint8) if "nodes" in want else None
+        root = np.zeros(32, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_lincode_commit(self.ctx, curve, _ptr(mat), n_rows, n_cols, log_ext_cols, hash, flags, _ptr(out_ext),
+                                               _ptr(out_leaves), _ptr(out_nodes), _ptr(root)))
+        return dict(root=root, ext=out_ext, leaves=out_leaves, nodes=out_nodes)
 
     # ---- multi-GPU over NVLink peer memory ----
     def peer_window_bytes(self):

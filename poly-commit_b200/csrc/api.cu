@@ -532,3 +532,30 @@ extern "C" int pcgpu_msm_peer(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_
   SET_DEVICE(ctx);
   DISPATCH_CURVE(srs->curve, return msm_peer_impl<C>(ctx, srs, base_offset, scalars, n, flags, win, rank, world, epoch, out_xy, out_inf));
 }
+
+// ---- linear-code commitments (hash.cuh) ---------------------------------------------------------------------------------
+extern "C" int pcgpu_lincode_hash_columns(pcgpu_ctx *ctx, int curve, const void *ext_mat, size_t n_rows, size_t n_cols, int hash,
+                                          uint32_t flags, uint8_t *out_leaves) {
+  if (!ctx || (n_cols && !out_leaves) || (n_rows && n_cols && !ext_mat)) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(curve, return lincode_hash_columns_impl<C>(ctx, ext_mat, n_rows, n_cols, hash, flags, out_leaves));
+}
+
+extern "C" int pcgpu_merkle_tree(pcgpu_ctx *ctx, const uint8_t *leaves, size_t n_leaves, uint32_t flags, uint8_t *out_nodes,
+                                 uint8_t *out_root) {
+  if (!ctx || !leaves) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  return merkle_tree_impl(ctx, leaves, n_leaves, flags, out_nodes, out_root);
+}
+
+extern "C" int pcgpu_lincode_commit(pcgpu_ctx *ctx, int curve, const void *mat, size_t n_rows, size_t n_cols, uint32_t log_ext_cols,
+                                    int hash, uint32_t flags, void *out_ext_mat, uint8_t *out_leaves, uint8_t *out_nodes,
+                                    uint8_t *out_root) {
+  if (!ctx || (n_rows && n_cols && !mat)) return PCGPU_E_BADARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  SET_DEVICE(ctx);
+  DISPATCH_CURVE(curve, return lincode_commit_impl<C>(ctx, mat, n_rows, n_cols, log_ext_cols, hash, flags, out_ext_mat, out_leaves,
+                                                      out_nodes, out_root));
+}

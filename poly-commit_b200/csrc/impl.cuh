@@ -22,6 +22,7 @@
 #include "wire.cuh"
 #include "msm_small.cuh"
 #include "peer.cuh"
+#include "hash.cuh"
 
 using namespace pcgpu;
 
@@ -959,6 +960,111 @@ int ntt_pass_impl(pcgpu_ctx *ctx, uint32_t logn, uint32_t flags, int which, size
 }
 
 // ---------------------------------------------------------------------------------------------
+// linear-code commitments: column hashes + Merkle tree (hash.cuh), fused behind the row encoding
+// ---------------------------------------------------------------------------------------------
+static inline uint64_t next_pow2_u64(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
+
+template <class C>
+static int hash_columns_device(const uint32_t *d_mat, size_t n_rows, size_t n_cols, int hash, bool mont, uint32_t *d_leaves, rt::stream_t st) {
+  using R = typename C::Fr;
+  if (hash == HASH_BLAKE2S) return rt::launch<64>(ColumnHashBody<R, Blake2s>{d_mat, n_rows, n_cols, d_leaves, mont ? 1 : 0}, n_cols, st);
+  if (hash == HASH_SHA256) return rt::launch<64>(ColumnHashBody<R, Sha256>{d_mat, n_rows, n_cols, d_leaves, mont ? 1 : 0}, n_cols, st);
+  return PCGPU_E_BADARG;
+}
+
+template <class C>
+int lincode_hash_columns_impl(pcgpu_ctx *ctx, const void *mat, size_t n_rows, size_t n_cols, int hash, uint32_t flags, uint8_t *out_leaves) {
+  rt::stream_t st = ctx->stream;
+  const bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  int rc;
+  if (n_cols == 0) return PCGPU_OK;
+  if (dev) {
+    if ((rc = hash_columns_device<C>((const uint32_t *)mat, n_rows, n_cols, hash, true, (uint32_t *)out_leaves, st))) return rc;
+    return rt::stream_sync(st);
+  }
+  if ((rc = ctx->stage.reserve(rt::Arena::pad(n_rows * n_cols * 32 + 32) + rt::Arena::pad(n_cols * 32) + 4096))) return rc;
+  uint32_t *d_m = ctx->stage.take<uint32_t>(n_rows * n_cols * 8 + 8), *d_l = ctx->stage.take<uint32_t>(n_cols * 8);
+  if (n_rows && (rc = rt::copy_h2d(d_m, mat, n_rows * n_cols * 32, st))) return rc;
+  if ((rc = hash_columns_device<C>(d_m, n_rows, n_cols, hash, true, d_l, st))) return rc;
+  if ((rc = rt::copy_d2h(out_leaves, d_l, n_cols * 32, st))) return rc;
+  return rt::stream_sync(st);
+}
+
+inline int merkle_tree_impl(pcgpu_ctx *ctx, const uint8_t *leaves, size_t n_leaves, uint32_t flags, uint8_t *out_nodes, uint8_t *out_root) {
+  rt::stream_t st = ctx->stream;
+  const bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  if (n_leaves < 2) return PCGPU_E_BADARG;          // ark-crypto-primitives' MerkleTree::new needs at least two leaves
+  const uint64_t P = next_pow2_u64(n_leaves);
+  int rc;
+  if ((rc = ctx->stage.reserve((dev ? 0 : rt::Arena::pad(n_leaves * 32)) + rt::Arena::pad((P - 1) * 32) + 4096))) return rc;
+  uint32_t *d_nodes = (dev && out_nodes) ? (uint32_t *)out_nodes : ctx->stage.take<uint32_t>((P - 1) * 8);
+  const uint32_t *d_leaves = (const uint32_t *)leaves;
+  if (!dev) {
+    uint32_t *t = ctx->stage.take<uint32_t>(n_leaves * 8);
+    if ((rc = rt::copy_h2d(t, leaves, n_leaves * 32, st))) return rc;
+    d_leaves = t;
+  }
+  if ((rc = merkle_build(d_leaves, n_leaves, P, d_nodes, st))) return rc;
+  if (!dev && out_nodes && (rc = rt::copy_d2h(out_nodes, d_nodes, (P - 1) * 32, st))) return rc;
+  if (out_root && (rc = rt::copy_d2h(out_root, d_nodes, 32, st))) return rc;
+  return rt::stream_sync(st);
+}
+
+// compute_matrices' row encoding + column hashes + Merkle tree without leaving the device (linear_codes/mod.rs:247-275)
+template <class C>
+int lincode_commit_impl(pcgpu_ctx *ctx, const void *mat, size_t n_rows, size_t n_cols, uint32_t log_ext, int hash, uint32_t flags,
+                        void *out_ext, uint8_t *out_leaves, uint8_t *out_nodes, uint8_t *out_root) {
+  using R = typename C::Fr;
+  if (!ntt_supported(log_ext) || log_ext > (uint32_t)R::TWO_ADICITY) return PCGPU_E_BADARG;
+  const size_t N = (size_t)1 << log_ext;
+  if (n_cols > N) return PCGPU_E_LEN;
+  if (N < 2 || n_rows == 0) return PCGPU_E_BADARG;
+  if (n_rows > ((size_t)1 << 40) / N) return PCGPU_E_BADARG;
+  rt::stream_t st = ctx->stream;
+  const bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  int rc;
+  const NttPlan *plan = nullptr;
+  for (const NttPlan &p : ctx->ntt_plans) if (p.curve == C::ID && p.logn == log_ext && p.inverse == 0) plan = &p;
+  if (!plan) {
+    NttPlan p;
+    if ((rc = ntt_build_plan<R>(p, C::ID, log_ext, 0, st))) return rc;
+    ctx->ntt_plans.push_back(p);
+    plan = &ctx->ntt_plans.back();
+  }
+  const uint64_t P = N;   // the extended width is a power of two already
+  size_t need = rt::Arena::pad(N * 32) + rt::Arena::pad(N * 32) + rt::Arena::pad((P - 1) * 32) + 4096;
+  if (!dev) need += rt::Arena::pad(n_rows * (n_cols ? n_cols : 1) * 32);
+  if (!(dev && out_ext)) need += rt::Arena::pad(n_rows * N * 32);
+  if ((rc = ctx->stage.reserve(need))) return rc;
+  uint32_t *tmp = ctx->stage.take<uint32_t>(N * 8);
+  uint32_t *d_leaves = (dev && out_leaves) ? (uint32_t *)out_leaves : ctx->stage.take<uint32_t>(N * 8);
+  uint32_t *d_nodes = (dev && out_nodes) ? (uint32_t *)out_nodes : ctx->stage.take<uint32_t>((P - 1) * 8);
+  uint32_t *d_ext = (dev && out_ext) ? (uint32_t *)out_ext : ctx->stage.take<uint32_t>(n_rows * N * 8);
+  const uint32_t *d_in = (const uint32_t *)mat;
+  if (!dev) {
+    uint32_t *ti = ctx->stage.take<uint32_t>(n_rows * (n_cols ? n_cols : 1) * 8);
+    if (n_cols && (rc = rt::copy_h2d(ti, mat, n_rows * n_cols * 32, st))) return rc;
+    d_in = ti;
+  }
+  ctx->prof.begin(9, st);
+  if ((rc = ntt_run_batch<R>(*plan, d_in, n_cols, n_rows, d_ext, tmp, st))) return rc;
+  ctx->prof.end(9, st);
+  ctx->prof.begin(14, st);
+  if ((rc = hash_columns_device<C>(d_ext, n_rows, N, hash, true, d_leaves, st))) return rc;
+  if ((rc = merkle_build(d_leaves, N, P, d_nodes, st))) return rc;
+  ctx->prof.end(14, st);
+  if (!dev) {
+    if (out_ext && (rc = rt::copy_d2h(out_ext, d_ext, n_rows * N * 32, st))) return rc;
+    if (out_leaves && (rc = rt::copy_d2h(out_leaves, d_leaves, N * 32, st))) return rc;
+    if (out_nodes && (rc = rt::copy_d2h(out_nodes, d_nodes, (P - 1) * 32, st))) return rc;
+  }
+  if (out_root && (rc = rt::copy_d2h(out_root, d_nodes, 32, st))) return rc;
+  rc = rt::stream_sync(st);
+  ctx->prof.collect();
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // G1 wire formats (wire.cuh)
 // ---------------------------------------------------------------------------------------------
 template <class C>
@@ -1156,7 +1262,9 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int ntt_impl<C>(pcgpu_ctx *, const void *, size_t, uint32_t, uint32_t, void *); \
   EXT template int ntt_pass_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, int, size_t, size_t, const void *, size_t, void *); \
   EXT template int ntt_batch_impl<C>(pcgpu_ctx *, const void *, size_t, size_t, uint32_t, uint32_t, void *); \
-  EXT template int ntt_pass1_peer_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, size_t, size_t, const void *, size_t, void *const *, uint32_t);
+  EXT template int ntt_pass1_peer_impl<C>(pcgpu_ctx *, uint32_t, uint32_t, size_t, size_t, const void *, size_t, void *const *, uint32_t); \
+  EXT template int lincode_hash_columns_impl<C>(pcgpu_ctx *, const void *, size_t, size_t, int, uint32_t, uint8_t *); \
+  EXT template int lincode_commit_impl<C>(pcgpu_ctx *, const void *, size_t, size_t, uint32_t, int, uint32_t, void *, uint8_t *, uint8_t *, uint8_t *);
 #define PCGPU_INST_IPA(C, EXT)                                                                                             \
   EXT template int ipa_begin_impl<C>(pcgpu_ctx *, const void *, size_t, const void *, size_t, const void *, uint32_t, pcgpu_ipa *); \
   EXT template int ipa_round_lr_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, void *, uint8_t *, void *, uint8_t *); \

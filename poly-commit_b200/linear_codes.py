@@ -8,8 +8,10 @@ rank 4: the one place the reference exercises the NTT.
   compute_matrices       linear_codes/mod.rs:118-138     -> Engine.ntt_batch over all rows (one launch up to 2^11 columns)
   b^T . M                linear_codes/mod.rs:? (open) via Matrix::row_mul, utils.rs:127-146  -> Engine.fr_row_mul
 
-Column hashing and the Merkle tree (linear_codes/mod.rs:255-275) use ark-crypto-primitives hashers and stay on the host
-(out of scope).
+  commit steps 2-3       linear_codes/mod.rs:253-275: column hashes (FieldToBytesColHasher<F, Blake2s256>) and the Merkle tree
+                         (LeafIdentityHasher + SHA-256 two-to-one, the configuration of the reference's tests and benches) run on
+                         the device behind Engine.lincode_commit; `commit` below is LinearCodePCS::commit for one polynomial and
+                         `merkle_path` is MerkleTree::generate_proof (used by generate_proof, linear_codes/mod.rs:553-558).
 """
 import math
 
@@ -63,3 +65,38 @@ def compute_matrices(eng, curve, coeffs, n_rows, n_cols, rho_inv):
     flat[:coeffs.shape[0]] = coeffs
     mat = flat.reshape(n_rows, n_cols, 4)
     return mat, eng.ntt_batch(curve, mat, _domain_log(n_cols * rho_inv))
+
+
+BLAKE2S, SHA256 = 0, 1
+
+
+def commit(eng, curve, coeffs, sec_param=128, rho_inv=4, hash=BLAKE2S):
+    """LinearCodePCS::commit for one polynomial given as its coefficient vector (linear_codes/mod.rs:228-298) ->
+    (commitment dict(metadata=(n_rows, n_cols, n_ext_cols), root=bytes), state dict(mat, ext_mat, leaves, nodes)).
+    Row encoding, column hashing and the tree run in ONE device-resident call."""
+    coeffs = np.asarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+    n_rows, n_cols = compute_dimensions(curve, sec_param, rho_inv, coeffs.shape[0])
+    flat = np.zeros((n_rows * n_cols, 4), dtype=np.uint64)
+    flat[:coeffs.shape[0]] = coeffs
+    mat = flat.reshape(n_rows, n_cols, 4)
+    log_ext = _domain_log(n_cols * rho_inv)
+    r = eng.lincode_commit(curve, mat, log_ext, hash=hash)
+    n_ext = 1 << log_ext
+    return (dict(metadata=(n_rows, n_cols, n_ext), root=r["root"].tobytes()),
+            dict(mat=mat, ext_mat=r["ext"], leaves=r["leaves"], nodes=r["nodes"]))
+
+
+def merkle_path(state, index):
+    """MerkleTree::generate_proof(index) over the state's tree -> dict(leaf_sibling_hash, auth_path (root's children first, as
+    ark-crypto-primitives stores it), leaf_index).  The padding leaves are empty (Vec::default())."""
+    leaves, nodes = state["leaves"], state["nodes"]
+    P = nodes.shape[0] + 1
+    sib = index ^ 1
+    leaf_sibling = leaves[sib].tobytes() if sib < leaves.shape[0] else b""
+    node = P // 2 - 1 + index // 2                    # heap index of the leaf pair's parent
+    path = []
+    while node > 0:
+        sibling = node + 1 if node % 2 == 1 else node - 1
+        path.append(nodes[sibling].tobytes())
+        node = (node - 1) // 2
+    return dict(leaf_sibling_hash=leaf_sibling, auth_path=path[::-1], leaf_index=index)
