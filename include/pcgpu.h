@@ -286,6 +286,19 @@ int pcgpu_kzg_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coe
                    const pcgpu_srs *powers_of_gamma_g, const void *blind, size_t n_blind, uint32_t flags,
                    void *out_w_xy, uint8_t *out_w_inf, void *out_random_v);
 
+/* KZG10::commit followed by KZG10::open of the same polynomial at z -- what a Marlin prover does per polynomial
+ * (MarlinKZG10::commit, marlin_pc/mod.rs:192-241, then ::open, :245-336) -- as ONE call: the coefficients are uploaded once,
+ * the commitment MSM (kzg10/mod.rs:175-178) and the witness division + MSM (:222-226, :255-258) run concurrently on two
+ * streams of the same device.  Non-hiding path (hiding_bound = None, the benchmark protocol of bench-templates/src/lib.rs:79);
+ * with blinding polynomials call pcgpu_kzg_commit and pcgpu_kzg_open.  flags: PCGPU_DEVICE_PTRS (coeffs).
+ * pcgpu_kzg_commit_open_batch: `count` polynomials opened at the same point z (the query set of one Marlin opening), two
+ * polynomials in flight; coeffs[i] / n[i] as in pcgpu_kzg_commit_batch, outputs are `count` points / flags each. */
+int pcgpu_kzg_commit_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coeffs, size_t n, const void *z, uint32_t flags,
+                          void *out_comm_xy, uint8_t *out_comm_inf, void *out_w_xy, uint8_t *out_w_inf);
+int pcgpu_kzg_commit_open_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *const *coeffs, const size_t *n, size_t count,
+                                const void *z, uint32_t flags, void *out_comm_xy, uint8_t *out_comm_inf, void *out_w_xy,
+                                uint8_t *out_w_inf);
+
 /* ---- diagnostics -------------------------------------------------------------------------------- */
 /* Device self-test of the field layer: n pseudo-random pairs per field (Fq and Fr of `curve`), production
  * multiplier (carry-chained mad.lo/mad.hi schedule) against the plain 64-bit-accumulate multiplier compiled into

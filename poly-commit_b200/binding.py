@@ -98,6 +98,8 @@ def _load(path):
         "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
+        "pcgpu_kzg_commit_open": [_vp, _vp, _vp, _sz, _vp, ctypes.c_uint32, _vp, _vp, _vp, _vp],
+        "pcgpu_kzg_commit_open_batch": [_vp, _vp, _vp, _vp, _sz, _vp, ctypes.c_uint32, _vp, _vp, _vp, _vp],
         "pcgpu_lincode_hash_columns": [_vp, ctypes.c_int, _vp, _sz, _sz, ctypes.c_int, ctypes.c_uint32, _vp],
         "pcgpu_merkle_tree": [_vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_lincode_commit": [_vp, ctypes.c_int, _vp, _sz, _sz, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32, _vp, _vp, _vp, _vp],
@@ -111,7 +113,9 @@ def _load(path):
                            ctypes.c_uint64, _vp, _vp],
     }
     for name, args in sigs.items():
-        fn = getattr(lib, name)
+        fn = getattr(lib, name, None)
+        if fn is None:      # a library older than this binding: only the calls that need the symbol fail (AttributeError)
+            continue
         fn.argtypes = args
         fn.restype = None if name in ("pcgpu_destroy", "pcgpu_srs_release") else ctypes.c_int
     return lib
@@ -536,6 +540,37 @@ class Engine:
         inf = np.zeros(count, dtype=np.uint8)
         self._ck(self.lib.pcgpu_kzg_commit_batch(self.ctx, powers_of_g.handle, ptrs, lens, count, flags, _ptr(out), _ptr(inf)))
         return out, inf
+
+    def kzg_commit_open(self, powers_of_g, coeffs, z, n=None, flags=0):
+        """KZG10::commit + KZG10::open of one polynomial in one call (coefficients uploaded once, the two MSMs overlapped)
+        -> ((comm_xy, comm_is_identity), (w_xy, w_is_identity))"""
+        coeffs, z = _u64(coeffs), _u64(z)
+        if n is None:
+            n = coeffs.size // 4
+        nq = 2 * fq_limbs(powers_of_g.curve)
+        c, w = np.zeros(nq, dtype=np.uint64), np.zeros(nq, dtype=np.uint64)
+        ci, wi = np.zeros(1, dtype=np.uint8), np.zeros(1, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_kzg_commit_open(self.ctx, powers_of_g.handle, _ptr(coeffs), n, _ptr(z), flags, _ptr(c), _ptr(ci),
+                                                _ptr(w), _ptr(wi)))
+        return (c, int(ci[0])), (w, int(wi[0]))
+
+    def kzg_commit_open_batch(self, powers_of_g, polys, z, flags=0):
+        """commit + open of `count` polynomials at the same point (list of arrays, or (device_ptr, n) tuples with
+        DEVICE_PTRS) -> (comm (count, 2*limbs), comm_inf (count,), w (count, 2*limbs), w_inf (count,))"""
+        count = len(polys)
+        ptrs, lens, keep = (ctypes.c_void_p * count)(), (_sz * count)(), []
+        for i, p in enumerate(polys):
+            if isinstance(p, tuple):
+                ptrs[i], lens[i] = int(p[0]), int(p[1])
+            else:
+                a = _u64(p); keep.append(a)
+                ptrs[i], lens[i] = a.ctypes.data, a.size // 4
+        nq = 2 * fq_limbs(powers_of_g.curve)
+        c, w = np.zeros((count, nq), dtype=np.uint64), np.zeros((count, nq), dtype=np.uint64)
+        ci, wi = np.zeros(count, dtype=np.uint8), np.zeros(count, dtype=np.uint8)
+        self._ck(self.lib.pcgpu_kzg_commit_open_batch(self.ctx, powers_of_g.handle, ptrs, lens, count, _ptr(_u64(z)), flags, _ptr(c),
+                                                      _ptr(ci), _ptr(w), _ptr(wi)))
+        return c, ci, w, wi
 
     def kzg_open(self, powers_of_g, coeffs, z, n=None, powers_of_gamma_g=None, blind=None, flags=0):
         coeffs, blind, z = _u64(coeffs), _u64(blind), _u64(z)

@@ -6,6 +6,7 @@ import glob
 import os
 import subprocess
 import sys
+import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -30,8 +31,9 @@ def _compile(unit, extra):
     out = os.path.join(OBJ, name + ".o")
     defs = [] if curve is None else [f"-DPCGPU_UNIT_CURVE={curve}", f"-DPCGPU_UNIT_GROUP={group}"]
     cmd = ["nvcc"] + NVCC_FLAGS + defs + extra + ["-c", os.path.join(CSRC, src + ".cu"), "-o", out]
+    t0 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)
-    return name, r.returncode, r.stdout + r.stderr, out
+    return name, r.returncode, r.stdout + r.stderr + f"[build] {name}: {time.time() - t0:.0f} s\n", out
 
 
 def build(force=False, verbose=False, extra=()):
@@ -45,6 +47,8 @@ def build(force=False, verbose=False, extra=()):
     for unit, rc, log, out in results:
         if verbose or rc:
             sys.stderr.write(log)
+        elif os.environ.get("PCGPU_BUILD_TIMES"):
+            sys.stderr.write(log.splitlines()[-1] + "\n")
         if rc:
             raise RuntimeError(f"nvcc failed on {unit}.cu")
         objs.append(out)

@@ -46,6 +46,7 @@ extern "C" int pcgpu_init(int device, pcgpu_ctx **out) {
   ctx->stream = ctx->own_stream;
   int rc = rt::dev_malloc(&ctx->d_slots, SLOT_BYTES * (NSLOTS + 2));
   if (rc) { delete ctx; return rc; }
+  if ((rc = rt::host_alloc_pinned(&ctx->h_pinned, PINNED_BYTES))) { rt::dev_free(ctx->d_slots); delete ctx; return rc; }
   *out = ctx;
   return PCGPU_OK;
 }
@@ -63,6 +64,8 @@ extern "C" void pcgpu_destroy(pcgpu_ctx *ctx) {
   ctx->msm_arena.release();
   ctx->stage.release();
   rt::dev_free(ctx->d_slots);
+  rt::host_free_pinned(ctx->h_pinned);
+  if (ctx->ev_ok) rt::event_destroy(ctx->ev_upload);
 #ifndef PCGPU_EMUL
   cudaStreamDestroy(ctx->own_stream);
 #endif
@@ -558,4 +561,63 @@ extern "C" int pcgpu_lincode_commit(pcgpu_ctx *ctx, int curve, const void *mat, 
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return lincode_commit_impl<C>(ctx, mat, n_rows, n_cols, log_ext_cols, hash, flags, out_ext_mat, out_leaves,
                                                       out_nodes, out_root));
+}
+
+// ---- fused KZG10 commit + open ------------------------------------------------------------------------------------------
+static int ensure_siblings(pcgpu_ctx *ctx, size_t count) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  while (ctx->siblings.size() < count) {
+    pcgpu_ctx *s = nullptr;
+    int rc = pcgpu_init(ctx->device, &s);
+    if (rc) return rc;
+    ctx->siblings.push_back(s);
+  }
+  return PCGPU_OK;
+}
+
+// one polynomial on the context pair (a, b); both mutexes are taken in a fixed order (a is never somebody's b)
+static int commit_open_pair(pcgpu_ctx *a, pcgpu_ctx *b, const pcgpu_srs *pg, const void *coeffs, size_t n, const void *z, uint32_t flags,
+                            void *out_c_xy, uint8_t *out_c_inf, void *out_w_xy, uint8_t *out_w_inf) {
+  std::lock_guard<std::mutex> la(a->mu);
+  std::lock_guard<std::mutex> lb(b->mu);
+  SET_DEVICE(a);
+  DISPATCH_CURVE(pg->curve, return kzg_commit_open_impl<C>(a, b, pg, coeffs, n, z, flags, out_c_xy, out_c_inf, out_w_xy, out_w_inf));
+}
+
+extern "C" int pcgpu_kzg_commit_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coeffs, size_t n, const void *z,
+                                     uint32_t flags, void *out_comm_xy, uint8_t *out_comm_inf, void *out_w_xy, uint8_t *out_w_inf) {
+  if (!ctx || !powers_of_g || !z || (n && !coeffs) || !out_comm_xy || !out_w_xy) return PCGPU_E_BADARG;
+  int rc = ensure_siblings(ctx, 1);
+  if (rc) return rc;
+  return commit_open_pair(ctx, ctx->siblings[0], powers_of_g, coeffs, n, z, flags, out_comm_xy, out_comm_inf, out_w_xy, out_w_inf);
+}
+
+enum { PCGPU_COMMIT_OPEN_WAYS = 2 };   // polynomials in flight (two MSM pipelines each)
+
+extern "C" int pcgpu_kzg_commit_open_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *const *coeffs, const size_t *n,
+                                           size_t count, const void *z, uint32_t flags, void *out_comm_xy, uint8_t *out_comm_inf,
+                                           void *out_w_xy, uint8_t *out_w_inf) {
+  if (!ctx || !powers_of_g || !z || (count && (!coeffs || !n || !out_comm_xy || !out_w_xy))) return PCGPU_E_BADARG;
+  const size_t ways = count < (size_t)PCGPU_COMMIT_OPEN_WAYS ? count : (size_t)PCGPU_COMMIT_OPEN_WAYS;
+  if (ways == 0) return PCGPU_OK;
+  int rc = ensure_siblings(ctx, 2 * ways - 1);   // way 0: (ctx, sib[0]); way w >= 1: (sib[2w-1], sib[2w])
+  if (rc) return rc;
+  const size_t psz = (powers_of_g->curve == PCGPU_BLS12_381 ? 6 : 4) * 16;
+  int rcs[PCGPU_COMMIT_OPEN_WAYS] = {PCGPU_OK, PCGPU_OK};
+  auto work = [&](size_t w) {
+    pcgpu_ctx *a = w == 0 ? ctx : ctx->siblings[2 * w - 1], *b = ctx->siblings[w == 0 ? 0 : 2 * w];
+    for (size_t i = w; i < count; i += ways) {
+      int r = commit_open_pair(a, b, powers_of_g, coeffs[i], n[i], (const char *)z, flags, (char *)out_comm_xy + i * psz,
+                               out_comm_inf ? out_comm_inf + i : nullptr, (char *)out_w_xy + i * psz, out_w_inf ? out_w_inf + i : nullptr);
+      if (r) { rcs[w] = r; return; }
+    }
+  };
+  try {
+    std::vector<std::thread> th;
+    for (size_t w = 1; w < ways; w++) th.emplace_back(work, w);
+    work(0);
+    for (auto &t : th) t.join();
+  } catch (...) { return PCGPU_E_OOM; }
+  for (size_t w = 0; w < ways; w++) if (rcs[w]) return rcs[w];
+  return PCGPU_OK;
 }

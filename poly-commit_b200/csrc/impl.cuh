@@ -81,8 +81,12 @@ struct pcgpu_ctx {
   uint32_t *d_pow2[3] = {nullptr, nullptr, nullptr};  // fp_inv_gcd tables (Fq), per curve
   std::vector<pcgpu_ctx *> siblings;  // extra contexts on the same device for pcgpu_kzg_commit_batch
   std::vector<NttPlan> ntt_plans;  // twiddle tables, cached per (curve, logn, direction)
+  void *h_pinned = nullptr;        // page-locked landing zone of the asynchronous plane / error-word copies (PINNED_BYTES)
+  rt::event_t ev_upload;           // "inputs are on the device": lets a sibling context's stream start on them
+  bool ev_ok = false;
   std::mutex mu;
 };
+static const size_t PINNED_BYTES = 512 * 192 + 256;   // PCGPU_MAX_PLANES XYZZ<Bls12381> points + the error word
 
 static const size_t SLOT_BYTES = 256;  // >= sizeof(XYZZ<Bls12381>) = 192
 enum { PCGPU_MAX_PLANES = 512 };  // S * c of any geometry msm_geometry produces (W <= 32 windows of <= 22 bits, S <= W)
@@ -237,40 +241,72 @@ int msm_device_planes(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, 
   return msm_run<C>(tables, g, d_scalars, ctx->msm_arena, d_planes, stride, d_err, st, ctx->prof, ctx->d_pow2[C::ID]);
 }
 
-// One MSM: device pipeline, then the S*c bit-plane sums come back to the host, which combines them
-// (host_ec.hpp).  d_scalars: device, n x 8 u32.  Synchronises the stream.
+// One MSM in two halves so that a caller can keep several pipelines in flight from one host thread:
+//   msm_issue    launches the device pipeline on the context's stream and queues the copy of the S*c bit-plane sums (and the
+//                error word) into the context's pinned buffer -- returns without waiting
+//   msm_collect  waits for that stream and combines the planes on the host (host_ec.hpp)
+// MSMs below the small-path threshold complete inside msm_issue.
 template <class C>
-int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const uint32_t *d_scalars, size_t n,
-                       bool mont, host::HXYZZ<C> *out) {
+struct MsmPending {
+  bool done = true;            // result already in `ready`
+  host::HXYZZ<C> ready;
+  MsmGeom g;
+  size_t np = 0;
+};
+
+template <class C>
+int msm_issue(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const uint32_t *d_scalars, size_t n, bool mont,
+              MsmPending<C> *p) {
   rt::stream_t st = ctx->stream;
-  *out = host::HXYZZ<C>::inf();
+  p->done = true; p->ready = host::HXYZZ<C>::inf(); p->np = 0;
   if (n == 0) return PCGPU_OK;
   if (n <= SMALL_MAX_N && msm_small_enabled()) {
     MsmSmallProblem<C> pr{(const Affine<C> *)srs->d_tables + base_offset, d_scalars, nullptr, nullptr, (uint32_t)n};
-    return msm_small_to_host<C>(ctx, &pr, 1, mont, out);
+    return msm_small_to_host<C>(ctx, &pr, 1, mont, &p->ready);
   }
-  MsmGeom g;
   const XYZZ<C> *d_planes = nullptr; size_t stride = 0; uint32_t *d_err = nullptr;
-  int rc = msm_device_planes<C>(ctx, srs, base_offset, d_scalars, n, mont, &g, &d_planes, &stride, &d_err);
+  int rc = msm_device_planes<C>(ctx, srs, base_offset, d_scalars, n, mont, &p->g, &d_planes, &stride, &d_err);
   if (rc) return rc;
-  size_t np = (size_t)g.S * g.c;   // one-level: c planes per set; two-level: (h+1) + (c-1-h) = c planes per set as well
+  p->np = (size_t)p->g.S * p->g.c;   // one-level: c planes per set; two-level: (h+1) + (c-1-h) = c planes per set as well
   static_assert(sizeof(host::HXYZZ<C>) == sizeof(XYZZ<C>), "host/device point layouts must agree");
-  host::HXYZZ<C> planes[PCGPU_MAX_PLANES];
-  if (np > PCGPU_MAX_PLANES) return PCGPU_E_BADARG;
-  uint32_t herr = 0;
-  if ((rc = rt::copy_d2h_2d(planes, sizeof(XYZZ<C>), d_planes, stride * sizeof(XYZZ<C>), sizeof(XYZZ<C>), np, st))) return rc;
-  if ((rc = rt::copy_d2h(&herr, d_err, sizeof herr, st))) return rc;
-  if ((rc = rt::stream_sync(st))) return rc;
+  if (p->np > PCGPU_MAX_PLANES || !ctx->h_pinned) return PCGPU_E_BADARG;
+  char *hp = (char *)ctx->h_pinned;
+  if ((rc = rt::copy_d2h_2d(hp, sizeof(XYZZ<C>), d_planes, stride * sizeof(XYZZ<C>), sizeof(XYZZ<C>), p->np, st))) return rc;
+  if ((rc = rt::copy_d2h(hp + PINNED_BYTES - 64, d_err, sizeof(uint32_t), st))) return rc;
+  p->done = false;
+  return PCGPU_OK;
+}
+
+template <class C>
+int msm_collect(pcgpu_ctx *ctx, MsmPending<C> *p, host::HXYZZ<C> *out) {
+  if (p->done) { *out = p->ready; return PCGPU_OK; }
+  int rc = rt::stream_sync(ctx->stream);
+  if (rc) return rc;
   ctx->prof.collect();
+  const char *hp = (const char *)ctx->h_pinned;
+  uint32_t herr;
+  memcpy(&herr, hp + PINNED_BYTES - 64, sizeof herr);
   if (herr) return PCGPU_E_RANGE;
   auto t0 = std::chrono::steady_clock::now();
-  *out = g.h_split ? host::combine_bit_planes_2level<C>(planes, g.S, g.c, g.h_split)
-                   : host::combine_bit_planes<C>(planes, g.S, g.c);
+  const host::HXYZZ<C> *planes = (const host::HXYZZ<C> *)hp;
+  *out = p->g.h_split ? host::combine_bit_planes_2level<C>(planes, p->g.S, p->g.c, p->g.h_split)
+                      : host::combine_bit_planes<C>(planes, p->g.S, p->g.c);
   if (ctx->prof.on) {
     ctx->prof.ms[6] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     ctx->prof.cnt[6]++;
   }
+  p->done = true; p->ready = *out;
   return PCGPU_OK;
+}
+
+// One MSM, synchronous.  d_scalars: device, n x 8 u32.
+template <class C>
+int msm_to_host(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const uint32_t *d_scalars, size_t n,
+                bool mont, host::HXYZZ<C> *out) {
+  MsmPending<C> p;
+  int rc = msm_issue<C>(ctx, srs, base_offset, d_scalars, n, mont, &p);
+  if (rc) return rc;
+  return msm_collect<C>(ctx, &p, out);
 }
 
 // copies scalars (n x 32 bytes) to the staging arena unless they already live on the device
@@ -616,6 +652,7 @@ int fr_row_mul_impl(pcgpu_ctx *ctx, const void *v, const void *m, size_t rows, s
 // ---------------------------------------------------------------------------------------------
 // KZG10 fused calls
 // ---------------------------------------------------------------------------------------------
+static int device_trim_trailing_zeros(pcgpu_ctx *ctx, const void *d_coeffs, size_t *n);
 static size_t trim_trailing_zeros(const void *coeffs, size_t n) {
   const uint64_t *c = (const uint64_t *)coeffs;
   while (n > 0 && !(c[4 * (n - 1)] | c[4 * (n - 1) + 1] | c[4 * (n - 1) + 2] | c[4 * (n - 1) + 3])) n--;
@@ -627,6 +664,7 @@ int kzg_commit_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, siz
                            const void *blind, size_t n_blind, uint32_t flags, void *out_xy, uint8_t *out_inf) {
   bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
   if (!dev) { n = trim_trailing_zeros(coeffs, n); n_blind = trim_trailing_zeros(blind, n_blind); }
+  else { int trc; if ((trc = device_trim_trailing_zeros(ctx, coeffs, &n)) || (trc = device_trim_trailing_zeros(ctx, blind, &n_blind))) return trc; }
   if (n > pg->n) return PCGPU_E_DEGREE;                      // check_degree_is_too_large, kzg10/mod.rs:163
   if (n_blind && (!gamma || n_blind > gamma->n)) return PCGPU_E_HIDING;  // check_hiding_bound, :190-193
   rt::stream_t st = ctx->stream;
@@ -657,6 +695,7 @@ int kzg_open_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, size_
   using R = typename C::Fr;
   bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
   if (!dev) { n = trim_trailing_zeros(coeffs, n); n_blind = trim_trailing_zeros(blind, n_blind); }
+  else { int trc; if ((trc = device_trim_trailing_zeros(ctx, coeffs, &n)) || (trc = device_trim_trailing_zeros(ctx, blind, &n_blind))) return trc; }
   if (n > pg->n) return PCGPU_E_DEGREE;  // kzg10/mod.rs:292
   if (n_blind && (!gamma || n_blind - 1 > gamma->n)) return PCGPU_E_HIDING;
   rt::stream_t st = ctx->stream;
@@ -695,6 +734,89 @@ int kzg_open_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, size_
 }
 
 
+
+// length of the polynomial without its trailing zero coefficients, for coefficients that live on the device
+// (DensePolynomial truncates them; the host path does the same scan in trim_trailing_zeros).  One 32-byte read in the common
+// case of a non-zero leading coefficient, otherwise a scan kernel.
+struct FrLastNonzeroBody {
+  const uint32_t *v; size_t n; unsigned long long *last_plus_one;
+  PCGPU_KERNEL_DEV void operator()(size_t i) const {
+    const uint32_t *e = v + 8 * i;
+    uint32_t o = 0;
+    for (int l = 0; l < 8; l++) o |= e[l];
+    if (o) {
+#ifdef __CUDA_ARCH__
+      atomicMax(last_plus_one, (unsigned long long)(i + 1));
+#else
+      if (*last_plus_one < i + 1) *last_plus_one = i + 1;
+#endif
+    }
+  }
+};
+static int device_trim_trailing_zeros(pcgpu_ctx *ctx, const void *d_coeffs, size_t *n) {
+  rt::stream_t st = ctx->stream;
+  int rc;
+  while (*n > 0) {
+    uint64_t top[4];
+    if ((rc = rt::copy_d2h(top, (const char *)d_coeffs + (*n - 1) * 32, 32, st))) return rc;
+    if ((rc = rt::stream_sync(st))) return rc;
+    if (top[0] | top[1] | top[2] | top[3]) return PCGPU_OK;
+    unsigned long long *d_last = (unsigned long long *)((char *)ctx->d_slots + SLOT_BYTES * NSLOTS + 64);
+    if ((rc = rt::dev_memset(d_last, 0, 8, st))) return rc;
+    if ((rc = rt::launch<256>(FrLastNonzeroBody{(const uint32_t *)d_coeffs, *n, d_last}, *n, st))) return rc;
+    unsigned long long h = 0;
+    if ((rc = rt::copy_d2h(&h, d_last, 8, st))) return rc;
+    if ((rc = rt::stream_sync(st))) return rc;
+    *n = (size_t)h;
+    return PCGPU_OK;
+  }
+  return PCGPU_OK;
+}
+
+// KZG10::commit followed by KZG10::open of the SAME polynomial (what a Marlin prover does per polynomial: commit,
+// marlin_pc/mod.rs:192-241, then open, :245-336) in one call: the coefficients are uploaded ONCE, the commitment MSM runs
+// on `ctx`'s stream while the witness division and the witness MSM run on the sibling context `sib`'s stream, so the
+// latency-bound stages of one pipeline hide under the multiply-bound stages of the other.  Non-hiding path only (the caller
+// falls back to the two separate calls when blinding polynomials are present).
+template <class C>
+int kzg_commit_open_impl(pcgpu_ctx *ctx, pcgpu_ctx *sib, const pcgpu_srs *pg, const void *coeffs, size_t n, const void *z,
+                         uint32_t flags, void *out_c_xy, uint8_t *out_c_inf, void *out_w_xy, uint8_t *out_w_inf) {
+  using R = typename C::Fr;
+  const bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  int rc;
+  if (!dev) n = trim_trailing_zeros(coeffs, n);
+  else if ((rc = device_trim_trailing_zeros(ctx, coeffs, &n))) return rc;
+  if (n > pg->n) return PCGPU_E_DEGREE;                      // kzg10/mod.rs:163, :292
+  rt::stream_t sa = ctx->stream, sb = sib->stream;
+  if ((rc = ctx->stage.reserve(dev ? 4096 : rt::Arena::pad(n * 32 + 32) + 4096))) return rc;
+  if ((rc = sib->stage.reserve(rt::Arena::pad(div_scratch_words(n) * 4) + rt::Arena::pad(n * 32 + 32) + 8192))) return rc;
+  const uint32_t *d_c = (const uint32_t *)coeffs;
+  if (!dev) {
+    uint32_t *tc = ctx->stage.take<uint32_t>(n * 8 + 8);
+    if (n && (rc = rt::copy_h2d(tc, coeffs, n * 32, sa))) return rc;
+    d_c = tc;
+  }
+  uint32_t *d_z = sib->stage.take<uint32_t>(8), *d_rem = sib->stage.take<uint32_t>(8);
+  uint32_t *scratch = sib->stage.take<uint32_t>(div_scratch_words(n));
+  uint32_t *d_q = sib->stage.take<uint32_t>(n * 8 + 8);
+  if ((rc = rt::copy_h2d(d_z, z, 32, sb))) return rc;
+  if (!ctx->ev_ok) { if ((rc = rt::event_create(&ctx->ev_upload))) return rc; ctx->ev_ok = true; }
+  if ((rc = rt::event_record(ctx->ev_upload, sa))) return rc;
+  if ((rc = rt::stream_wait_event(sb, ctx->ev_upload))) return rc;
+  MsmPending<C> pc, pw;
+  // witness side first: its division is short and its MSM then overlaps the commitment's
+  sib->prof.begin(7, sb);
+  if ((rc = fr_div_linear<R>(d_c, n, d_z, d_q, d_rem, scratch, sb))) return rc;      // kzg10/mod.rs:222-226
+  sib->prof.end(7, sb);
+  if ((rc = msm_issue<C>(ctx, pg, 0, d_c, n, true, &pc))) return rc;                 // :175-178
+  if ((rc = msm_issue<C>(sib, pg, 0, d_q, n ? n - 1 : 0, true, &pw))) return rc;     // :255-258
+  host::HXYZZ<C> comm, w;
+  if ((rc = msm_collect<C>(ctx, &pc, &comm))) return rc;
+  if ((rc = msm_collect<C>(sib, &pw, &w))) return rc;
+  host::to_affine<C>(comm, out_c_xy, out_c_inf);                                      // :209
+  host::to_affine<C>(w, out_w_xy, out_w_inf);                                         // :281
+  return PCGPU_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // IPA halving loop (device-resident)
@@ -1237,7 +1359,9 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
 #define PCGPU_INST_PIPE(C, EXT)                                                                                            \
   EXT template int msm_device_planes<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const uint32_t *, size_t, bool, MsmGeom *, \
                                         const XYZZ<C> **, size_t *, uint32_t **);                                          \
-  EXT template int msm_to_host<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const uint32_t *, size_t, bool, host::HXYZZ<C> *);
+  EXT template int msm_to_host<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const uint32_t *, size_t, bool, host::HXYZZ<C> *); \
+  EXT template int msm_issue<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const uint32_t *, size_t, bool, MsmPending<C> *);   \
+  EXT template int msm_collect<C>(pcgpu_ctx *, MsmPending<C> *, host::HXYZZ<C> *);
 #define PCGPU_INST_SMALL(C, EXT)                                                                                           \
   EXT template int msm_small_to_host<C>(pcgpu_ctx *, const MsmSmallProblem<C> *, uint32_t, bool, host::HXYZZ<C> *);
 #define PCGPU_INST_SRS(C, EXT)                                                                                             \
@@ -1250,6 +1374,7 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int kzg_open_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const void *, const pcgpu_srs *, \
                                     const void *, size_t, uint32_t, void *, uint8_t *, void *); \
   EXT template int msm_batch_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, size_t, uint32_t, void *, uint8_t *); \
+  EXT template int kzg_commit_open_impl<C>(pcgpu_ctx *, pcgpu_ctx *, const pcgpu_srs *, const void *, size_t, const void *, uint32_t, void *, uint8_t *, void *, uint8_t *); \
   EXT template int msm_peer_impl<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const void *, size_t, uint32_t, void *const *, uint32_t, uint32_t, uint64_t, void *, uint8_t *);
 #define PCGPU_INST_FR(C, EXT)                                                                                              \
   EXT template int fr_from_mont_impl<C>(pcgpu_ctx *, const void *, void *, size_t, uint32_t);                              \

@@ -161,11 +161,42 @@ struct ScanApplyBody {
   }
 };
 
+// One-launch variant for inputs up to SCAN_BLOCK_MAX elements (every histogram of a window-folded MSM): a single block,
+// each thread scans a contiguous slice, the slice totals are scanned in shared memory.
+enum { SCAN_BLOCK = 1024, SCAN_BLOCK_MAX = 1 << 17 };
+struct ScanBlockBody {
+  const uint32_t *in; size_t n; uint32_t *out;
+  PCGPU_KERNEL_DEV void operator()(size_t, uint32_t *smem) const {
+    const size_t per = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    PCGPU_BLOCK_FOR(t, SCAN_BLOCK) {
+      size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
+      uint32_t sum = 0;
+      for (size_t i = lo; i < hi; i++) sum += in[i];
+      smem[t] = sum;
+    }
+    PCGPU_BLOCK_SYNC();
+    // Hillis-Steele inclusive scan of the SCAN_BLOCK slice totals (double buffer)
+    uint32_t *a = smem, *b = smem + SCAN_BLOCK;
+    for (uint32_t d = 1; d < SCAN_BLOCK; d <<= 1) {
+      PCGPU_BLOCK_FOR(t, SCAN_BLOCK) { b[t] = a[t] + (t >= d ? a[t - d] : 0u); }
+      PCGPU_BLOCK_SYNC();
+      uint32_t *tmp = a; a = b; b = tmp;
+    }
+    PCGPU_BLOCK_FOR(t, SCAN_BLOCK) {
+      size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
+      uint32_t run = t ? a[t - 1] : 0u;
+      for (size_t i = lo; i < hi; i++) { uint32_t v = in[i]; out[i] = run; run += v; }
+      if (t == SCAN_BLOCK - 1) out[n] = a[SCAN_BLOCK - 1];
+    }
+  }
+};
+
 // scratch: (n/SCAN_CHUNK + 2) uint32
 inline size_t scan_scratch_words(size_t n) { return (n + SCAN_CHUNK - 1) / SCAN_CHUNK + 2; }
 inline int exclusive_scan_u32(const uint32_t *in, size_t n, uint32_t *out, uint32_t *scratch, rt::stream_t st) {
   size_t m = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
   if (m == 0) { return rt::dev_memset(out, 0, sizeof(uint32_t), st); }
+  if (n <= SCAN_BLOCK_MAX) return rt::launch_blocks<SCAN_BLOCK>(ScanBlockBody{in, n, out}, 1, 2 * SCAN_BLOCK * sizeof(uint32_t), st);
   int rc;
   if ((rc = rt::launch<128>(ScanChunkSumBody{in, n, scratch}, m, st))) return rc;
   if ((rc = rt::launch<32>(ScanPartialsBody{scratch, m}, 1, st))) return rc;
@@ -176,10 +207,13 @@ inline int exclusive_scan_u32(const uint32_t *in, size_t n, uint32_t *out, uint3
 // tasks
 // ---------------------------------------------------------------------------------------------
 struct TaskCountBody {
-  const uint32_t *offsets; uint32_t L; uint32_t *ntasks;
+  const uint32_t *offsets; uint32_t L; uint32_t *ntasks; uint32_t heavy_min; uint32_t *heavy_count; uint32_t *heavy_list;
   PCGPU_KERNEL_DEV void operator()(size_t b) const {
     uint32_t cnt = offsets[b + 1] - offsets[b];
-    ntasks[b] = (cnt + L - 1) / L;
+    uint32_t nt = (cnt + L - 1) / L;
+    ntasks[b] = nt;
+    // buckets with many task partials (repeated scalars, a short top window) are reduced by whole blocks before the row pass
+    if (nt > heavy_min) heavy_list[rt::atomic_add(heavy_count, 1u)] = (uint32_t)b;
   }
 };
 struct TaskFillBody {
@@ -304,28 +338,13 @@ struct MsmAccumulateBody {
 // (every stage is a plain sum, so the serial depth stays at chunk + log2(chunks) additions; the
 // c-term Horner combination  sum_j 2^j T[s][j]  and the final inversion run on the host, host_ec.hpp)
 // ---------------------------------------------------------------------------------------------
-enum { HEAVY_BUCKET_TASKS = 8, HEAVY_BLOCK = 128, HEAVY_GRID = 64 };
-
-// buckets[b] = sum of the bucket's task partials.  Buckets with more than HEAVY_BUCKET_TASKS partials (repeated scalars:
-// many coefficients equal to 1 or -1, or a short top window) are appended to a list and reduced by whole thread blocks.
-template <class C>
-struct MsmBucketSumBody {
-  const uint32_t *task_off; const XYZZ<C> *partial; XYZZ<C> *buckets; uint32_t *heavy_count; uint32_t *heavy_list;
-  PCGPU_KERNEL_DEV void operator()(size_t b) const {
-    uint32_t t0 = task_off[b], t1 = task_off[b + 1];
-    if (t1 - t0 > HEAVY_BUCKET_TASKS) { heavy_list[rt::atomic_add(heavy_count, 1u)] = (uint32_t)b; return; }
-    XYZZ<C> acc = XYZZ<C>::inf();
-    for (uint32_t q = t0; q < t1; q++) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add<C>(acc, p); }
-    store_xyzz<C>(buckets + b, acc);
-  }
-};
+enum { HEAVY_BUCKET_TASKS = 8, HEAVY_BLOCK = 128, HEAVY_GRID = 64, REDUCE_BLOCK = 128 };
 
 // one thread block per heavy bucket (grid-strided over the list): strided partial sums, then a shared-memory tree
 template <class C>
 struct MsmHeavyBucketBody {
   const uint32_t *task_off; const XYZZ<C> *partial; XYZZ<C> *buckets; const uint32_t *heavy_count; const uint32_t *heavy_list;
   PCGPU_KERNEL_DEV void operator()(size_t blk, uint32_t *smem) const {
-    constexpr uint32_t WORDS = sizeof(XYZZ<C>) / 4;
     XYZZ<C> *sh = reinterpret_cast<XYZZ<C> *>(smem);
     const uint32_t nheavy = *heavy_count;
     for (uint32_t hb = (uint32_t)blk; hb < nheavy; hb += HEAVY_GRID) {
@@ -343,66 +362,95 @@ struct MsmHeavyBucketBody {
       PCGPU_BLOCK_FOR(i, 1) { store_xyzz<C>(buckets + b, sh[0]); }
       PCGPU_BLOCK_SYNC();
     }
-    (void)WORDS;
   }
 };
 
-// planes[((s*nbits + j) * nseg) + q] = sum of vals[s*NBx + k], k in segment q, over the k whose weight (k + wofs) has bit j set
+// shared-memory tree over REDUCE_BLOCK per-thread values; the sum ends in sh[0]
 template <class C>
-struct MsmBitPlaneBody {
-  const XYZZ<C> *vals; XYZZ<C> *planes;
-  uint32_t NBx, nbits, wofs, seg_len, nseg;
-  PCGPU_KERNEL_DEV void operator()(size_t t) const {
-    uint32_t q = (uint32_t)(t % nseg);
-    uint32_t j = (uint32_t)((t / nseg) % nbits);
-    uint32_t s = (uint32_t)(t / ((size_t)nseg * nbits));
-    uint32_t lo = q * seg_len;
-    uint32_t hi = lo + seg_len < NBx ? lo + seg_len : NBx;
-    XYZZ<C> acc = XYZZ<C>::inf();
-    for (uint32_t k = lo; k < hi; k++) {
-      if (((k + wofs) >> j) & 1) { XYZZ<C> p = load_xyzz<C>(vals + (size_t)s * NBx + k); xyzz_add<C>(acc, p); }
+PCGPU_KERNEL_DEV void block_tree_sum(XYZZ<C> *sh) {
+  for (uint32_t half = REDUCE_BLOCK / 2; half >= 1; half >>= 1) {
+    PCGPU_BLOCK_FOR(i, half) { XYZZ<C> x = sh[i], y = sh[i + half]; xyzz_add<C>(x, y); sh[i] = x; }
+    PCGPU_BLOCK_SYNC();
+  }
+}
+
+// Bucket reduction in three block-cooperative launches.  Bucket k of a set is addressed as k = hi * cols + lo
+// (cols = 2^h_split); with row sums R_hi = sum_lo B and column sums C_lo = sum_hi B the weighted sum is
+//     sum_k (k + 1) B_k  =  2^h * sum_hi hi * R_hi  +  sum_lo (lo + 1) * C_lo ,
+// and each of the two short weighted sums is handed to the host as bit-plane sums (plain additions only; the O(c) Horner
+// combination and the inversion run in host_ec.hpp).  Serial depth: <= 8 (task partials) + 7 (row tree) | 7 | 7.
+//   rows pass : one block per (set, row): bucket sums from the task partials (kept in buckets[] for the column pass), row tree
+template <class C>
+struct MsmRowReduceBody {
+  const uint32_t *task_off; const XYZZ<C> *partial; XYZZ<C> *buckets; XYZZ<C> *Rv;
+  uint32_t NB, rows, cols;
+  PCGPU_KERNEL_DEV void operator()(size_t blk, uint32_t *smem) const {
+    XYZZ<C> *sh = reinterpret_cast<XYZZ<C> *>(smem);
+    const uint32_t s = (uint32_t)(blk / rows), hi = (uint32_t)(blk % rows);
+    PCGPU_BLOCK_FOR(t, REDUCE_BLOCK) {
+      XYZZ<C> acc = XYZZ<C>::inf();
+      for (uint32_t lo = t; lo < cols; lo += REDUCE_BLOCK) {
+        const size_t b = (size_t)s * NB + (size_t)hi * cols + lo;
+        const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+        XYZZ<C> bs;
+        if (t1 - t0 > HEAVY_BUCKET_TASKS) bs = load_xyzz<C>(buckets + b);          // written by MsmHeavyBucketBody
+        else {
+          bs = XYZZ<C>::inf();
+          for (uint32_t q = t0; q < t1; q++) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add<C>(bs, p); }
+          store_xyzz<C>(buckets + b, bs);
+        }
+        xyzz_add<C>(acc, bs);
+      }
+      sh[t] = acc;
     }
-    store_xyzz<C>(planes + t, acc);
+    PCGPU_BLOCK_SYNC();
+    block_tree_sum<C>(sh);
+    PCGPU_BLOCK_FOR(i, 1) { store_xyzz<C>(Rv + blk, sh[0]); }
   }
 };
-
-// part[(s*cnt + i)*nq + q] = sum_{e < len} in[s*NB + base_mul*i + (q*len + e)*stride]      (row sums: base_mul = row length,
-// stride = 1; column sums: base_mul = 1, stride = row length)
+//   columns pass : one block per (set, column)
 template <class C>
-struct MsmStrideSumBody {
-  const XYZZ<C> *in; XYZZ<C> *part;
-  uint32_t NB, cnt, per, base_mul, stride, len, nq;   // cnt outputs per set, `per` inputs per output
-  PCGPU_KERNEL_DEV void operator()(size_t t) const {
-    uint32_t q = (uint32_t)(t % nq);
-    uint32_t i = (uint32_t)((t / nq) % cnt);
-    uint32_t s = (uint32_t)(t / ((size_t)nq * cnt));
-    uint32_t e0 = q * len, e1 = e0 + len < per ? e0 + len : per;
-    XYZZ<C> acc = XYZZ<C>::inf();
-    for (uint32_t e = e0; e < e1; e++) {
-      XYZZ<C> p = load_xyzz<C>(in + (size_t)s * NB + (size_t)base_mul * i + (size_t)e * stride);
-      xyzz_add<C>(acc, p);
+struct MsmColReduceBody {
+  const XYZZ<C> *buckets; XYZZ<C> *Cv;
+  uint32_t NB, rows, cols;
+  PCGPU_KERNEL_DEV void operator()(size_t blk, uint32_t *smem) const {
+    XYZZ<C> *sh = reinterpret_cast<XYZZ<C> *>(smem);
+    const uint32_t s = (uint32_t)(blk / cols), lo = (uint32_t)(blk % cols);
+    PCGPU_BLOCK_FOR(t, REDUCE_BLOCK) {
+      XYZZ<C> acc = XYZZ<C>::inf();
+      for (uint32_t hi = t; hi < rows; hi += REDUCE_BLOCK) {
+        XYZZ<C> p = load_xyzz<C>(buckets + (size_t)s * NB + (size_t)hi * cols + lo);
+        xyzz_add<C>(acc, p);
+      }
+      sh[t] = acc;
     }
-    store_xyzz<C>(part + t, acc);
+    PCGPU_BLOCK_SYNC();
+    block_tree_sum<C>(sh);
+    PCGPU_BLOCK_FOR(i, 1) { store_xyzz<C>(Cv + blk, sh[0]); }
   }
 };
-
-// out[i] = in[i * stride]
+//   planes pass : one block per (set, plane): planes 0 .. bits_c-1 are sums of the C_lo whose weight lo + 1 has that bit set,
+//   planes bits_c .. are sums of the R_hi whose weight hi has bit (j - bits_c) set
 template <class C>
-struct XyzzGatherBody {
-  const XYZZ<C> *in; XYZZ<C> *out; uint32_t stride;
-  PCGPU_KERNEL_DEV void operator()(size_t i) const { store_xyzz<C>(out + i, load_xyzz<C>(in + i * (size_t)stride)); }
-};
-
-template <class C>
-struct MsmTreeAddBody {
-  XYZZ<C> *a; uint32_t stride; uint32_t m; uint32_t half;  // per row: a[i] += a[i+half] for i+half < m
-  PCGPU_KERNEL_DEV void operator()(size_t t) const {
-    uint32_t cnt = m - half;
-    uint32_t s = (uint32_t)(t / cnt), i = (uint32_t)(t % cnt);
-    XYZZ<C> *base = a + (size_t)s * stride;
-    XYZZ<C> x = load_xyzz<C>(base + i), y = load_xyzz<C>(base + i + half);
-    xyzz_add<C>(x, y);
-    store_xyzz<C>(base + i, x);
+struct MsmPlaneReduceBody {
+  const XYZZ<C> *Rv, *Cv; XYZZ<C> *plane_out;
+  uint32_t rows, cols, bits_c, bits_r;
+  PCGPU_KERNEL_DEV void operator()(size_t blk, uint32_t *smem) const {
+    XYZZ<C> *sh = reinterpret_cast<XYZZ<C> *>(smem);
+    const uint32_t per = bits_c + bits_r;
+    const uint32_t s = (uint32_t)(blk / per), j = (uint32_t)(blk % per);
+    const bool col = j < bits_c;
+    const XYZZ<C> *vals = col ? Cv + (size_t)s * cols : Rv + (size_t)s * rows;
+    const uint32_t cnt = col ? cols : rows, wofs = col ? 1u : 0u, bit = col ? j : j - bits_c;
+    PCGPU_BLOCK_FOR(t, REDUCE_BLOCK) {
+      XYZZ<C> acc = XYZZ<C>::inf();
+      for (uint32_t k = t; k < cnt; k += REDUCE_BLOCK)
+        if (((k + wofs) >> bit) & 1) { XYZZ<C> p = load_xyzz<C>(vals + k); xyzz_add<C>(acc, p); }
+      sh[t] = acc;
+    }
+    PCGPU_BLOCK_SYNC();
+    block_tree_sum<C>(sh);
+    PCGPU_BLOCK_FOR(i, 1) { store_xyzz<C>(plane_out + blk, sh[0]); }
   }
 };
 
@@ -440,19 +488,15 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
   g.scalar_bits = scalar_bits; g.scalars_mont = mont ? 1 : 0;
   g.table_stride = table_stride; g.base_off = base_off;
   g.affine_rounds = 0;
-  g.h_split = c > 17 ? (c - 1) / 2 : 0;
+  g.h_split = (c - 1) / 2;
   g.pt_words = 0; g.y_words = 0;  // set by the caller (table_layout)
   return g;
 }
 
-// XYZZ scratch elements of the reduction stage (bit planes, and for the two-level mode the row/column partial sums)
+// XYZZ scratch elements of the reduction stage: row sums and column sums of every set
 inline size_t msm_plane_scratch_elems(const MsmGeom &g) {
-  if (!g.h_split) return (size_t)g.S * g.c * g.nseg;
   size_t cols = (size_t)1 << g.h_split, rows = g.NB >> g.h_split;
-  size_t part = (size_t)g.S * (rows * ((cols + 15) / 16) + cols * ((rows + 15) / 16));     // partial sums
-  size_t rc = (size_t)g.S * (rows + cols);                                                  // compacted R and C
-  size_t planes = (size_t)g.S * 32 * ((rows + 15) / 16 + (cols + 15) / 16);                 // bit planes of R and C
-  return part + rc + planes;
+  return (size_t)g.S * (rows + cols);
 }
 
 template <class C>
@@ -566,7 +610,8 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
   }
 
   prof.begin(3, st);
-  if ((rc = rt::launch<256>(TaskCountBody{offsets, g.L, ntasks}, g.TB, st))) return rc;
+  if ((rc = rt::dev_memset(err + 12, 0, 4, st))) return rc;   // err[12]: number of heavy buckets; cursor[] is free again: heavy list
+  if ((rc = rt::launch<256>(TaskCountBody{offsets, g.L, ntasks, HEAVY_BUCKET_TASKS, err + 12, cursor}, g.TB, st))) return rc;
   if ((rc = exclusive_scan_u32(ntasks, g.TB, task_off, scratch, st))) return rc;
   if ((rc = rt::launch<256>(TaskFillBody{task_off, task_bucket}, g.TB, st))) return rc;
   prof.end(3, st);
@@ -576,43 +621,15 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
   prof.end(4, st);
 
   prof.begin(5, st);
-  if ((rc = rt::dev_memset(err + 12, 0, 4, st))) return rc;   // err[12]: number of heavy buckets
-  if ((rc = rt::launch<128>(MsmBucketSumBody<C>{task_off, partial, buckets, err + 12, cursor}, g.TB, st))) return rc;   // cursor[] is free again: heavy list
-  if ((rc = rt::launch_blocks<HEAVY_BLOCK>(MsmHeavyBucketBody<C>{task_off, partial, buckets, err + 12, cursor}, HEAVY_GRID,
-                                           HEAVY_BLOCK * sizeof(XYZZ<C>), st))) return rc;
-  // weighted sum of `cnt` values per set (weights index + wofs, `nbits` bits) -> nbits plane sums per set at dst[s*dst_stride + j]
-  auto reduce_planes = [&](const XYZZ<C> *vals, uint32_t cnt, uint32_t wofs, uint32_t nbits, XYZZ<C> *scratch, XYZZ<C> *dst,
-                           uint32_t dst_stride) -> int {
-    uint32_t seg_len = 16, nseg = (cnt + seg_len - 1) / seg_len;
-    int r2;
-    if ((r2 = rt::launch<128>(MsmBitPlaneBody<C>{vals, scratch, cnt, nbits, wofs, seg_len, nseg}, (size_t)g.S * nbits * nseg, st))) return r2;
-    for (uint32_t m = nseg; m > 1;) {
-      uint32_t half = (m + 1) / 2;
-      if ((r2 = rt::launch<128>(MsmTreeAddBody<C>{scratch, nseg, m, half}, (size_t)g.S * nbits * (m - half), st))) return r2;
-      m = half;
-    }
-    for (uint32_t sset = 0; sset < g.S; sset++)   // compact: plane (s, j) sits at scratch[(s*nbits + j) * nseg]
-      if ((r2 = rt::launch<32>(XyzzGatherBody<C>{scratch + (size_t)sset * nbits * nseg, dst + (size_t)sset * dst_stride, nseg}, nbits, st))) return r2;
-    return rt::OK;
-  };
-  if (!g.h_split) {
-    if ((rc = reduce_planes(buckets, g.NB, 1u, g.c, planes, plane_out, g.c))) return rc;
-  } else {
-    // two-level: bucket k = hi * 2^h + lo.  R_hi = sum_lo B, C_lo = sum_hi B (plain sums), then
-    //   sum_k (k+1) B_k = 2^h * sum_hi hi * R_hi + sum_lo (lo+1) * C_lo      -> planes of C first (h+1 bits), then of R
-    const uint32_t h = g.h_split, cols = 1u << h, rows = g.NB >> h;
-    const uint32_t nq_r = (cols + 15) / 16, nq_c = (rows + 15) / 16;
-    XYZZ<C> *part_r = planes, *part_c = part_r + (size_t)g.S * rows * nq_r;
-    XYZZ<C> *Rv = part_c + (size_t)g.S * cols * nq_c, *Cv = Rv + (size_t)g.S * rows, *pl = Cv + (size_t)g.S * cols;
-    if ((rc = rt::launch<128>(MsmStrideSumBody<C>{buckets, part_r, g.NB, rows, cols, cols, 1u, 16u, nq_r}, (size_t)g.S * rows * nq_r, st))) return rc;
-    if ((rc = rt::launch<128>(MsmStrideSumBody<C>{buckets, part_c, g.NB, cols, rows, 1u, cols, 16u, nq_c}, (size_t)g.S * cols * nq_c, st))) return rc;
-    for (uint32_t m = nq_r; m > 1;) { uint32_t half = (m + 1) / 2; if ((rc = rt::launch<128>(MsmTreeAddBody<C>{part_r, nq_r, m, half}, (size_t)g.S * rows * (m - half), st))) return rc; m = half; }
-    for (uint32_t m = nq_c; m > 1;) { uint32_t half = (m + 1) / 2; if ((rc = rt::launch<128>(MsmTreeAddBody<C>{part_c, nq_c, m, half}, (size_t)g.S * cols * (m - half), st))) return rc; m = half; }
-    if ((rc = rt::launch<128>(XyzzGatherBody<C>{part_r, Rv, nq_r}, (size_t)g.S * rows, st))) return rc;
-    if ((rc = rt::launch<128>(XyzzGatherBody<C>{part_c, Cv, nq_c}, (size_t)g.S * cols, st))) return rc;
-    const uint32_t bits_c = h + 1, bits_r = g.c - 1 - h;
-    if ((rc = reduce_planes(Cv, cols, 1u, bits_c, pl, plane_out, bits_c + bits_r))) return rc;
-    if ((rc = reduce_planes(Rv, rows, 0u, bits_r, pl, plane_out + bits_c, bits_c + bits_r))) return rc;
+  {
+    const uint32_t h = g.h_split, cols = 1u << h, rows = g.NB >> h, bits_c = h + 1, bits_r = g.c - 1 - h;
+    const size_t smem = REDUCE_BLOCK * sizeof(XYZZ<C>);
+    XYZZ<C> *Rv = planes, *Cv = planes + (size_t)g.S * rows;
+    if ((rc = rt::launch_blocks<HEAVY_BLOCK>(MsmHeavyBucketBody<C>{task_off, partial, buckets, err + 12, cursor}, HEAVY_GRID,
+                                             HEAVY_BLOCK * sizeof(XYZZ<C>), st))) return rc;
+    if ((rc = rt::launch_blocks<REDUCE_BLOCK>(MsmRowReduceBody<C>{task_off, partial, buckets, Rv, g.NB, rows, cols}, (size_t)g.S * rows, smem, st))) return rc;
+    if ((rc = rt::launch_blocks<REDUCE_BLOCK>(MsmColReduceBody<C>{buckets, Cv, g.NB, rows, cols}, (size_t)g.S * cols, smem, st))) return rc;
+    if ((rc = rt::launch_blocks<REDUCE_BLOCK>(MsmPlaneReduceBody<C>{Rv, Cv, plane_out, rows, cols, bits_c, bits_r}, (size_t)g.S * (bits_c + bits_r), smem, st))) return rc;
   }
   prof.end(5, st);
   return rt::OK;

@@ -49,6 +49,13 @@ inline int copy_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, siz
 }
 inline int stream_sync(stream_t) { return OK; }
 inline int last_error() { return OK; }
+typedef int event_t;
+inline int event_create(event_t *e) { *e = 0; return OK; }
+inline void event_destroy(event_t) {}
+inline int event_record(event_t, stream_t) { return OK; }
+inline int stream_wait_event(stream_t, event_t) { return OK; }
+inline int host_alloc_pinned(void **p, size_t bytes) { *p = ::malloc(bytes ? bytes : 1); return *p ? OK : E_OOM; }
+inline void host_free_pinned(void *p) { ::free(p); }
 
 template <int BLOCK, class Body>
 inline int launch(const Body &body, size_t n, stream_t) {
@@ -101,6 +108,13 @@ inline int copy_d2h_2d(void *h, size_t hpitch, const void *d, size_t dpitch, siz
 }
 inline int stream_sync(stream_t s) { return map_cuda(cudaStreamSynchronize(s)); }
 inline int last_error() { return map_cuda(cudaGetLastError()); }
+typedef cudaEvent_t event_t;
+inline int event_create(event_t *e) { return map_cuda(cudaEventCreateWithFlags(e, cudaEventDisableTiming)); }
+inline void event_destroy(event_t e) { cudaEventDestroy(e); }
+inline int event_record(event_t e, stream_t s) { return map_cuda(cudaEventRecord(e, s)); }
+inline int stream_wait_event(stream_t s, event_t e) { return map_cuda(cudaStreamWaitEvent(s, e, 0)); }
+inline int host_alloc_pinned(void **p, size_t bytes) { return map_cuda(cudaMallocHost(p, bytes ? bytes : 1)); }
+inline void host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 
 template <class Body, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) run_kernel(const Body body, size_t n) {

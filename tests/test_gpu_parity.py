@@ -19,7 +19,7 @@ from tests.test_hostcheck import (test_fixed_base_mul, test_fr_div_linear, test_
                                   test_wire_roundtrip_vs_oracle, test_wire_bls12_381_generator_known_answer,
                                   test_wire_rejects_like_the_oracle, test_wire_kzg_containers, test_msm_bases_unregistered,
                                   test_kzg10_batch_check_combination, test_ligero_reed_solomon_like_the_reference, test_msm_small_path_limits, test_ipa_fold_glv_equals_plain_ladder, test_sonic_pc_host_mirror,
-                                  test_ligero_compute_matrices)
+                                  test_ligero_compute_matrices, test_kzg_commit_open_fused)
 
 pytestmark = pytest.mark.gpu
 
@@ -130,6 +130,22 @@ def test_cfg2_commit_open_vs_oracle(eng, big):
     assert rc == 0
     got = eng.kzg_open(big["srs"], big["coeffs"], z)
     assert got[1] == winf and (got[0] == wxy).all()
+
+
+def test_cfg2_fused_commit_open(eng, pc, big):
+    """the one-call commit+open (two overlapped MSM pipelines, one upload) at the cfg2 size, host and device-resident inputs"""
+    import torch
+    C, n = big["C"], big["n"]
+    z = util.rand_fr("bls12_381", 1, seed=71, mont=True)[0]
+    rc, exy, einf = orc.kzg_commit(C.id, big["bases"], big["coeffs"])
+    rc2, wxy, winf, _ = orc.kzg_open(C.id, big["bases"], big["coeffs"], z)
+    assert rc == 0 and rc2 == 0
+    (c, ci), (w, wi) = eng.kzg_commit_open(big["srs"], big["coeffs"], z)
+    assert (c == exy).all() and ci == einf and (w == wxy).all() and wi == winf
+    d = torch.from_numpy(big["coeffs"].view(np.int64)).cuda()
+    cb, cib, wb, wib = eng.kzg_commit_open_batch(big["srs"], [(d.data_ptr(), n)] * 3, z, flags=pc.DEVICE_PTRS)
+    for i in range(3):
+        assert (cb[i] == exy).all() and cib[i] == einf and (wb[i] == wxy).all() and wib[i] == winf
 
 
 def test_cfg2_properties(eng, pc, big):

@@ -262,6 +262,46 @@ def test_kzg_commit_batch(eng, pc):
     assert ei.value.code == -6
 
 
+def test_kzg_commit_open_fused(eng, pc):
+    """pcgpu_kzg_commit_open / _batch: one call == KZG10::commit then KZG10::open (kzg10/mod.rs:157-210, :287-310), including
+    trailing zero coefficients, a constant and a zero polynomial, n beyond the small-MSM threshold, and the degree error"""
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    n = 4400
+    powers = util.synthetic_srs(cname, n, seed=12)
+    pg = eng.srs_register(C.id, powers, flags=pc.SRS_PRECOMPUTE)
+    z = util.rand_fr(cname, 1, seed=401, mont=True)[0]
+    polys = [util.rand_fr(cname, n, seed=400, mont=True), util.rand_fr(cname, 77, seed=402, mont=True),
+             util.rand_fr(cname, 1, seed=403, mont=True), np.zeros((5, 4), dtype=np.uint64)]
+    polys[0][-9:] = 0                                                       # trailing zeros are not part of the polynomial
+    exp = []
+    for p in polys:
+        rc, cxy, cinf = orc.kzg_commit(C.id, powers, p)
+        rc2, wxy, winf, _ = orc.kzg_open(C.id, powers, p, z)
+        assert rc == 0 and rc2 == 0
+        exp.append((cxy, cinf, wxy, winf))
+        (c, ci), (w, wi) = eng.kzg_commit_open(pg, p, z)
+        assert (c == cxy).all() and ci == cinf and (w == wxy).all() and wi == winf
+    c, ci, w, wi = eng.kzg_commit_open_batch(pg, polys, z)
+    for i, e in enumerate(exp):
+        assert (c[i] == e[0]).all() and ci[i] == e[1] and (w[i] == e[2]).all() and wi[i] == e[3]
+    with pytest.raises(pc.PcgpuError) as ei:
+        eng.kzg_commit_open(pg, util.rand_fr(cname, n + 1, seed=404, mont=True), z)
+    assert ei.value.code == -6
+    # "device" pointers (host pointers under emulation): the trailing zeros must be trimmed on the device side as well
+    for p, e in zip(polys, exp):
+        (c, ci), (w, wi) = eng.kzg_commit_open(pg, p.ctypes.data, z, n=p.shape[0], flags=pc.DEVICE_PTRS)
+        assert (c == e[0]).all() and ci == e[1] and (w == e[2]).all() and wi == e[3]
+        got = eng.kzg_commit(pg, p.ctypes.data, n=p.shape[0], flags=pc.DEVICE_PTRS)
+        assert (got[0] == e[0]).all() and got[1] == e[1]
+    padded = np.zeros((n + 50, 4), dtype=np.uint64)
+    padded[:n] = polys[0]
+    got = eng.kzg_commit(pg, padded.ctypes.data, n=n + 50, flags=pc.DEVICE_PTRS)   # zero-padded beyond the SRS length: no E_DEGREE
+    assert (got[0] == exp[0][0]).all()
+    got = eng.kzg_open(pg, padded.ctypes.data, z, n=n + 50, flags=pc.DEVICE_PTRS)
+    assert (got[0] == exp[0][2]).all()
+
+
 def test_marlin_pc_host_mirror(eng, pc):
     """marlin_pc.commit / open (mirror of marlin_pc/mod.rs:172-336) with and without degree bounds vs the oracle composed
     the same way: two_polys_degree_bound_single_query_test's shape (marlin_pc/mod.rs:720ff)."""
