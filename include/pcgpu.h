@@ -44,7 +44,7 @@ enum {
   PCGPU_E_OOM = -2,    /* device allocation failed */
   PCGPU_E_BADARG = -3, /* null pointer, unknown curve id, ... */
   PCGPU_E_LEN = -4,    /* base_offset + n exceeds the registered bases (msm() returns Err(len) in ark-ec) */
-  PCGPU_E_RANGE = -5,  /* a canonical scalar is >= 2^255 (2^254 for BN254): not a reduced field element */
+  PCGPU_E_RANGE = -5,  /* a canonical scalar is >= r: not a reduced field element (into_bigint never produces one) */
   PCGPU_E_DEGREE = -6, /* Error::TooManyCoefficients, kzg10/mod.rs:392-402 */
   PCGPU_E_HIDING = -7, /* Error::HidingBoundToolarge, kzg10/mod.rs:404-422 */
   PCGPU_E_INVALID = -8, /* SerializationError::{InvalidData, UnexpectedFlags}: a wire-format element failed to decode / validate */

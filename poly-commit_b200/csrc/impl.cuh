@@ -121,7 +121,7 @@ int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, siz
   uint32_t groups = 1, c = 0;
   if ((flags & PCGPU_SRS_PRECOMPUTE) && n > 0) {
     c = srs_precompute_window(n);
-    groups = C::Fr::BITS / c + 1;
+    groups = (C::Fr::BITS + c - 1) / c;   // one table group per window (msm_geometry's W)
   }
   int rc = rt::dev_malloc(&srs->d_tables, psz * (n ? n : 1));
   if (rc) return rc;
@@ -231,6 +231,10 @@ int msm_device_planes(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, 
     while (R < 8 && (avg >> R) >= 4 && (entries >> (R + 1)) >= 16 * Tmax) R++;
     if (const char *e = getenv("PCGPU_MSM_AFFINE_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= 12) R = (uint32_t)v; }
     g.affine_rounds = R;
+    size_t PT = 0;
+    if ((rc = rt::persistent_threads_occ<128, PAIR_MIN_BLOCKS, MsmAffineChunkBody<C, true>>(&PT))) return rc;
+    g.pair_threads = (uint32_t)PT;
+    if (const char *e = getenv("PCGPU_PAIR_MODE")) g.pair_mode = e[0] == '0' ? 0u : 1u;   // A/B knob: 0 = one-shot pair kernel
   }
   if (g.affine_rounds && !ctx->d_pow2[C::ID]) {
     using QP = typename C::Fq;

@@ -47,6 +47,8 @@ struct MsmGeom {
                           // 2^h * sum_hi hi * R_hi + sum_lo (lo+1) * C_lo over row sums R and column sums C (large c)
   uint32_t pt_words;      // table record stride in 32-bit words (2N raw; 32 for 128-byte aligned BLS12-381 records)
   uint32_t y_words;       // offset of y inside a record, in words (N raw; 16 in the aligned BLS12-381 layout)
+  uint32_t pair_threads;  // resident threads of the pair-round kernel (sizes its scratch)
+  uint32_t pair_mode;     // 1: chunked persistent pair kernel (default), 0: one-shot kernel
 };
 
 enum : uint32_t { ENTRY_SIGN = 0x80000000u, ENTRY_GROUP_SHIFT = 26, ENTRY_IDX_MASK = (1u << 26) - 1 };
@@ -54,10 +56,10 @@ enum : uint32_t { ENTRY_SIGN = 0x80000000u, ENTRY_GROUP_SHIFT = 26, ENTRY_IDX_MA
 // ---------------------------------------------------------------------------------------------
 // scalar loading + signed-digit recoding
 // ---------------------------------------------------------------------------------------------
+// scalar i as a canonical integer (Montgomery input converted), no range handling: the fixed-base / comb kernels of srs.cuh
 template <class C>
-PCGPU_DEV void load_scalar(const uint32_t *scalars, size_t i, bool mont, uint32_t *k) {
+PCGPU_DEV void load_scalar_plain(const uint32_t *scalars, size_t i, bool mont, uint32_t *k) {
   using R = typename C::Fr;
-  static_assert(R::N == 8, "256-bit scalar fields only");
   const u32x4 *p = reinterpret_cast<const u32x4 *>(scalars) + 2 * i;
   u32x4 lo = p[0], hi = p[1];
   Fp<R> v;
@@ -66,6 +68,46 @@ PCGPU_DEV void load_scalar(const uint32_t *scalars, size_t i, bool mont, uint32_
   if (mont) v = fp_from_mont<R>(v);
 #pragma unroll
   for (int j = 0; j < 8; j++) k[j] = v.l[j];
+}
+
+// Loads scalar i as a canonical integer k and halves its range: a scalar above (r - 1) / 2 is replaced by r - k and the
+// caller negates every digit (k P = (r - k)(-P)).  The halved range is what lets W = ceil(bits / c) windows suffice for the
+// signed-digit recoding: the top window then holds at most 2^(c-1) - 1, so the final carry can never leave it.  Returns
+// false for a scalar that is not a reduced field element (k >= r).
+template <class C>
+PCGPU_DEV bool load_scalar(const uint32_t *scalars, size_t i, bool mont, uint32_t *k, bool *flip) {
+  using R = typename C::Fr;
+  static_assert(R::N == 8, "256-bit scalar fields only");
+  const u32x4 *p = reinterpret_cast<const u32x4 *>(scalars) + 2 * i;
+  u32x4 lo = p[0], hi = p[1];
+  Fp<R> v;
+  v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w;
+  v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+  if (mont) v = fp_from_mont<R>(v);
+  // compare with r and with (r - 1) / 2, most significant limb first
+  bool lt_r = false, gt_half = false, decided_r = false, decided_h = false;
+#pragma unroll
+  for (int j = 7; j >= 0; j--) {
+    const uint32_t m = R::mod(j), h = (R::mod(j) >> 1) | (j + 1 < 8 ? R::mod(j + 1 < 8 ? j + 1 : 7) << 31 : 0u);   // limb j of (r - 1) / 2
+    if (!decided_r && v.l[j] != m) { lt_r = v.l[j] < m; decided_r = true; }
+    if (!decided_h && v.l[j] != h) { gt_half = v.l[j] > h; decided_h = true; }
+  }
+  *flip = gt_half;
+  if (gt_half) {
+    Fp<R> m;
+#pragma unroll
+    for (int j = 0; j < 8; j++) m.l[j] = R::mod(j);
+    // r - v as plain integers (v < r here unless the scalar is out of range, which the caller rejects)
+    uint32_t borrow = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint64_t dd = (uint64_t)m.l[j] - v.l[j] - borrow;
+      v.l[j] = (uint32_t)dd; borrow = (uint32_t)(dd >> 63);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) k[j] = v.l[j];
+  return lt_r;
 }
 
 // raw c-bit field starting at bit position pos of a 256-bit little-endian integer
@@ -104,8 +146,8 @@ struct MsmCountBody {
   const uint32_t *scalars; MsmGeom g; uint32_t *counts; uint32_t *err;
   PCGPU_KERNEL_DEV void operator()(size_t i) const {
     uint32_t k[8];
-    load_scalar<C>(scalars, i, g.scalars_mont != 0, k);
-    if (!scalar_in_range(k, g.scalar_bits)) { rt::atomic_or(err, 1u); return; }
+    bool flip;
+    if (!load_scalar<C>(scalars, i, g.scalars_mont != 0, k, &flip)) { rt::atomic_or(err, 1u); return; }
     uint32_t *cnt = counts; const MsmGeom gg = g;
     for_each_digit(k, gg, [&](uint32_t w, uint32_t mag, bool) {
       uint32_t s = w % gg.S;
@@ -119,13 +161,13 @@ struct MsmScatterBody {
   const uint32_t *scalars; MsmGeom g; uint32_t *cursor; uint32_t *entries;
   PCGPU_KERNEL_DEV void operator()(size_t i) const {
     uint32_t k[8];
-    load_scalar<C>(scalars, i, g.scalars_mont != 0, k);
-    if (!scalar_in_range(k, g.scalar_bits)) return;
+    bool flip;
+    if (!load_scalar<C>(scalars, i, g.scalars_mont != 0, k, &flip)) return;
     uint32_t *cur = cursor; uint32_t *ent = entries; const MsmGeom gg = g;
     for_each_digit(k, gg, [&](uint32_t w, uint32_t mag, bool neg) {
       uint32_t s = w % gg.S, grp = w / gg.S;
       uint32_t pos = rt::atomic_add(cur + (size_t)s * gg.NB + (mag - 1), 1u);
-      ent[pos] = (neg ? ENTRY_SIGN : 0u) | (grp << ENTRY_GROUP_SHIFT) | (uint32_t)i;
+      ent[pos] = ((neg != flip) ? ENTRY_SIGN : 0u) | (grp << ENTRY_GROUP_SHIFT) | (uint32_t)i;
     });
   }
 };
@@ -476,7 +518,7 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
                             uint64_t table_stride, uint64_t base_off) {
   MsmGeom g;
   g.n = (uint32_t)n; g.c = c;
-  g.W = scalar_bits / c + 1;
+  g.W = (scalar_bits + c - 1) / c;   // enough because load_scalar halves the scalar range (see there)
   g.G = groups < 1 ? 1 : groups;
   g.S = (g.W + g.G - 1) / g.G;
   g.NB = 1u << (c - 1);
@@ -490,6 +532,7 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
   g.affine_rounds = 0;
   g.h_split = (c - 1) / 2;
   g.pt_words = 0; g.y_words = 0;  // set by the caller (table_layout)
+  g.pair_threads = 0; g.pair_mode = 1;
   return g;
 }
 
@@ -497,6 +540,12 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
 inline size_t msm_plane_scratch_elems(const MsmGeom &g) {
   size_t cols = (size_t)1 << g.h_split, rows = g.NB >> g.h_split;
   return (size_t)g.S * (rows + cols);
+}
+
+// field elements of the pair rounds' scratch: prefix | x1 | d of the one-shot kernel, or the 5 * K * T columns of the chunked one
+inline size_t pair_scratch_elems(const MsmGeom &g, size_t bound0) {
+  size_t a = 3 * (bound0 + (1u << 20)), b = (size_t)5 * 32 * g.pair_threads;
+  return a > b ? a : b;
 }
 
 template <class C>
@@ -516,7 +565,7 @@ inline size_t msm_workspace_bytes(const MsmGeom &g) {
     size_t bound0 = max_entries / 2 + g.TB + 1, bound1 = bound0 / 2 + g.TB + 1;
     b += 3 * rt::Arena::pad((g.TB + 2) * sizeof(uint32_t));
     b += rt::Arena::pad(bound0 * sizeof(uint32_t));
-    b += rt::Arena::pad(3 * (bound0 + (1u << 20)) * sizeof(Fp<typename C::Fq>));
+    b += rt::Arena::pad(pair_scratch_elems(g, bound0) * sizeof(Fp<typename C::Fq>));
     b += rt::Arena::pad(bound0 * sizeof(Affine<C>)) + rt::Arena::pad(bound1 * sizeof(Affine<C>));
   }
   return b + 4096;
@@ -578,7 +627,7 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
     size_t bound0 = max_entries / 2 + g.TB + 1, bound1 = bound0 / 2 + g.TB + 1;
     uint32_t *offA = arena.take<uint32_t>(g.TB + 2), *offB = arena.take<uint32_t>(g.TB + 2), *cnt = arena.take<uint32_t>(g.TB + 2);
     uint32_t *src = arena.take<uint32_t>(bound0);
-    uint32_t *prefix = (uint32_t *)arena.take<QF>(3 * (bound0 + (1u << 20)));   // prefix | x1 | d  (x1, d: round 0 only)
+    uint32_t *prefix = (uint32_t *)arena.take<QF>(pair_scratch_elems(g, bound0));   // prefix | x1 | d, or the chunked kernel's columns
     Affine<C> *ptsA = arena.take<Affine<C>>(bound0), *ptsB = arena.take<Affine<C>>(bound1);
     if (!offA || !offB || !cnt || !src || !prefix || !ptsA || !ptsB) return rt::E_OOM;
     size_t Tmax = 0;
@@ -598,7 +647,17 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
       if ((rc = rt::launch<256>(PairPlanBody{off_in, off_out, g.TB, src}, bound, st))) return rc;
       uint32_t T = (uint32_t)Tmax;
       if (r == 0) prof.begin(12, st);
-      if (r == 0) rc = rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, true>{tables, g, entries, nullptr, src, off_out, T, prefix, pow2, out}, T, st);
+      if (g.pair_mode == 1 && g.pair_threads) {
+        // chunked persistent kernel: K slots per thread per chunk, about four chunks per warp in round 0
+        const uint32_t PT = g.pair_threads;
+        uint32_t K = (uint32_t)((bound + 4 * (size_t)PT - 1) / (4 * (size_t)PT));
+        if (K < 16) K = 16;
+        if (K > PAIR_CHUNK_MAX_K) K = PAIR_CHUNK_MAX_K;
+        if (const char *e = getenv("PCGPU_PAIR_K")) { int v = atoi(e); if (v >= 1 && v <= PAIR_CHUNK_MAX_K) K = (uint32_t)v; }   // tuning knob
+        if ((rc = rt::dev_memset(err + 10, 0, 4, st))) return rc;
+        if (r == 0) rc = rt::launch_persistent_occ<128, PAIR_MIN_BLOCKS>(MsmAffineChunkBody<C, true>{tables, g, entries, nullptr, src, off_out, PT, K, prefix, pow2, out, err + 10}, st);
+        else rc = rt::launch_persistent_occ<128, PAIR_MIN_BLOCKS>(MsmAffineChunkBody<C, false>{tables, g, entries, in, src, off_out, PT, K, prefix, pow2, out, err + 10}, st);
+      } else if (r == 0) rc = rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, true>{tables, g, entries, nullptr, src, off_out, T, prefix, pow2, out}, T, st);
       else rc = rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, false>{tables, g, entries, in, src, off_out, T, prefix, pow2, out}, T, st);
       if (rc) return rc;
       if (r == 0) prof.end(12, st);

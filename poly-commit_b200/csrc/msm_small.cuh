@@ -52,7 +52,7 @@ struct MsmSmallBody {
   uint32_t mont;         // scalars are Montgomery Fr (converted in the digit pass) / canonical
   uint32_t split;        // blocks per window; block q of a window takes the terms i = q (mod split)
   XYZZ<C> *out;          // out[(p * W + w) * split + q] = partial U_w of problem p
-  uint32_t *err;         // bit 0: a canonical scalar >= 2^bits
+  uint32_t *err;         // bit 0: a canonical scalar >= r
   PCGPU_KERNEL_DEV void operator()(size_t blk, uint32_t *smem) const {
     using R = typename C::Fr;
     constexpr uint32_t W = small_windows<R>();
@@ -69,7 +69,11 @@ struct MsmSmallBody {
       const uint32_t g = q + split * i;
       Fp<R> s = load_fr<R>(g < P.n ? P.scalars : P.extra_scalar, g < P.n ? g : 0);
       if (mont) s = fp_from_mont<R>(s);
-      if (R::BITS < 256 && (s.l[7] >> (R::BITS - 224))) rt::atomic_or(err, 1u);
+      {   // not a reduced field element (>= r): rejected like the bucket pipeline does (load_scalar)
+        bool lt_r = false, decided = false;
+        for (int j = 7; j >= 0; j--) if (!decided && s.l[j] != R::mod(j)) { lt_r = s.l[j] < R::mod(j); decided = true; }
+        if (!lt_r) rt::atomic_or(err, 1u);
+      }
       dig[i] = (int8_t)small_digit(s.l, K, w);
     }
     PCGPU_BLOCK_SYNC();

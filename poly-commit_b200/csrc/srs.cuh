@@ -18,7 +18,7 @@ enum : size_t { SRS_PRECOMPUTE_MIN_N = 1u << 12 };
 inline uint32_t srs_precompute_window(size_t n) {
   if (const char *e = getenv("PCGPU_SRS_C")) { int v = atoi(e); if (v >= 8 && v <= 22) return (uint32_t)v; }   // tuning knob
   uint32_t lg = ilog2_floor(n ? n : 1);
-  if (lg >= 18) return 16;
+  if (lg >= 18) return 17;   // 255 / 17 = 15 windows exactly (load_scalar halves the scalar range, so no 16th carry window)
   if (lg >= 15) return 14;
   return 12;
 }
@@ -64,7 +64,7 @@ struct FixedBaseMulBody {
   const Affine<C> *table; const uint32_t *scalars; Affine<C> *out;
   PCGPU_KERNEL_DEV void operator()(size_t i) const {
     uint32_t k[8];
-    load_scalar<C>(scalars, i, false, k);
+    load_scalar_plain<C>(scalars, i, false, k);
     XYZZ<C> acc = XYZZ<C>::inf();
     for (uint32_t j = 0; j < 64; j++) {
       uint32_t d = (k[j >> 3] >> ((j & 7) * 4)) & 15;
@@ -113,7 +113,7 @@ struct CombAccumulateBody {
     const Affine<C> *tab = table; const CombGeom gg = g;
     for (uint32_t i = lo; i < hi; i++) {
       uint32_t k[8];
-      load_scalar<C>(scalars, (size_t)row * g.n + i, g.scalars_mont != 0, k);
+      load_scalar_plain<C>(scalars, (size_t)row * g.n + i, g.scalars_mont != 0, k);
       if (!scalar_in_range(k, g.scalar_bits)) { rt::atomic_or(err, 1u); continue; }
       for_each_digit(k, mg, [&](uint32_t w, uint32_t mag, bool neg) {
         Affine<C> a = load_affine<C>(tab + ((size_t)i * gg.W + w) * gg.NBk + (mag - 1));
