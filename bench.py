@@ -44,7 +44,9 @@ def parse():
     ap.add_argument("--impl", default="pcgpu", choices=["pcgpu", "reference"])
     ap.add_argument("--log-deg", type=int, default=LOG_DEG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=4, help="polynomials in flight per GPU (one context + stream each)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded MSM / cfg5 / NTT sub-record")
+    ap.add_argument("--sharded-log-n", type=int, default=22)
+    ap.add_argument("--cfg5-polys", type=int, default=64)
     return ap.parse_args()
 
 
@@ -216,12 +218,15 @@ def main():
     import torch
     import pkgload
     pc = pkgload.load()
-    from poly_commit_b200 import params  # the oracle is imported by the cpu_baseline leg only (cpu_port_run)
+    from poly_commit_b200 import params, sharded  # the oracle is imported by the cpu_baseline leg only (cpu_reference_run)
 
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist = SingleDist()
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     eng = pc.Engine(local_rank)  # raises without the CUDA library / an sm_100 device
     cid = pc.CURVES[CURVE]
     n = (1 << log_deg) + 1
@@ -239,41 +244,17 @@ def main():
     n_polys = 4
     host_polys = [torch.from_numpy(params.random_fr(cid, n, 100 + rank * n_polys + i).view(np.int64)).pin_memory() for i in range(n_polys)]
     dev_polys = [h.cuda() for h in host_polys]
+    host_views = [h.numpy().view(np.uint64) for h in host_polys]
     z = params.random_fr(cid, 1, 4)[0]
-    # `inflight` independent polynomials are processed concurrently, each on its own context (own stream + workspace),
-    # sharing the read-only SRS tables: the latency-bound tails of one MSM overlap the multiply-bound phase of another.
-    import threading
-    inflight = max(1, args.inflight)
-    engines = [eng] + [pc.Engine(local_rank) for _ in range(inflight - 1)]
 
-    def step_dev(i, e=None):
-        e = e or eng
-        d = dev_polys[i % n_polys]
-        c = e.kzg_commit(srs, d.data_ptr(), n=n, flags=pc.DEVICE_PTRS)
-        w = e.kzg_open(srs, d.data_ptr(), z, n=n, flags=pc.DEVICE_PTRS)
-        return c, w
+    # One step = commit + open of one polynomial.  The timed region is ONE call of the library's batch entry point over the
+    # K polynomials of the K steps (pcgpu_kzg_commit_open_batch: coefficients uploaded once per polynomial, two polynomials in
+    # flight, each with its commitment and witness MSM pipelines on two streams) -- a single host thread, no Python threading.
+    def run_dev(k):
+        return eng.kzg_commit_open_batch(srs, [(dev_polys[i % n_polys].data_ptr(), n) for i in range(k)], z, flags=pc.DEVICE_PTRS)
 
-    def step_host(i, e=None):
-        e = e or eng
-        h = host_polys[i % n_polys].numpy().view(np.uint64)
-        c = e.kzg_commit(srs, h, n=n)
-        w = e.kzg_open(srs, h, z, n=n)
-        return c, w
-
-    def run_steps(fn, k):
-        """k steps spread over the in-flight contexts (thread j takes steps j, j+inflight, ...)."""
-        if inflight == 1:
-            for i in range(k):
-                fn(i)
-            return
-        def work(j):
-            for i in range(j, k, inflight):
-                fn(i, engines[j])
-        ts = [threading.Thread(target=work, args=(j,)) for j in range(inflight)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
+    def run_host(k):
+        return eng.kzg_commit_open_batch(srs, [host_views[i % n_polys] for i in range(k)], z)
 
     def barrier():
         if world > 1:
@@ -283,12 +264,12 @@ def main():
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # the library's calls are synchronous (each ends with a sync of its own stream), so events recorded on the
-        # current stream before the first call and after the last one bracket all the work of all contexts
+        # the library's calls are synchronous (each ends with a sync of its own streams), so events recorded on the
+        # current stream before the call and after it bracket all the work of all its streams
         e0.record()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        run_steps(fn, k)
+        fn(k)
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
         e1.record()
@@ -302,21 +283,30 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()                      # started before the warm-up so nvidia-smi is already streaming samples
-    run_steps(step_dev, warmup * inflight)
+    run_dev(max(warmup, 3))
     sampler.mark()
     l0 = eng.launch_count()
-    ms_dev = timed(step_dev, steps)
+    ms_dev = timed(run_dev, steps)
     launches = eng.launch_count() - l0
     clocks = sampler.stop()
-    eng.profile_enable(False)
-    run_steps(step_host, 2 * inflight)
-    ms_host = timed(step_host, steps)
-    # kernel-level timings: a separate pass with ONE polynomial in flight, CUDA events around every stage on the
-    # launching stream (with several contexts in flight the per-stage times would include the other context's kernels)
+    run_host(max(warmup, 3))
+    ms_host = timed(run_host, steps)
+    # single-call latency (one polynomial per call: what a serial Rust caller of commit-then-open sees)
+    eng.kzg_commit_open(srs, dev_polys[0].data_ptr(), z, n=n, flags=pc.DEVICE_PTRS)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(min(steps, 8)):
+        eng.kzg_commit_open(srs, dev_polys[i % n_polys].data_ptr(), z, n=n, flags=pc.DEVICE_PTRS)
+    torch.cuda.synchronize()
+    ms_single_call = (time.perf_counter() - t0) * 1e3 / min(steps, 8)
+    # kernel-level timings: a separate pass with ONE pipeline in flight (commit, then open), CUDA events around every stage
+    # on the launching stream (with several pipelines in flight the per-stage times would include the other pipeline's kernels)
     eng.profile_enable(True)
     prof_steps = min(steps, 8)
     for i in range(prof_steps):
-        step_dev(i)
+        d = dev_polys[i % n_polys]
+        eng.kzg_commit(srs, d.data_ptr(), n=n, flags=pc.DEVICE_PTRS)
+        eng.kzg_open(srs, d.data_ptr(), z, n=n, flags=pc.DEVICE_PTRS)
     acc_ms, acc_cnt = eng.profile_get(4)
     stage_ms = {name: eng.profile_get(s)[0] / max(prof_steps, 1) for s, name in
                 enumerate(["digits_count", "scan", "scatter", "tasks", "bucket_accumulate", "bucket_reduce", "final_host", "fr_division"])}
@@ -324,7 +314,16 @@ def main():
     pair0_ms, pair0_cnt = eng.profile_get(12)
     eng.profile_enable(False)
 
+    shard = None
+    if not args.no_sharded:
+        try:
+            shard = sharded_record(args, eng, pc, params, sharded, dist, dev, rank, world, cid)
+        except Exception as e:  # the headline line must survive a failure of the extra record
+            shard = {"error": repr(e)[:300]}
+
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     polys = steps * world
     value = polys / (ms_dev / 1e3)
@@ -334,43 +333,198 @@ def main():
     imad_peak = eng.measure_imad_peak()
     # multiply count of one 2^log_deg MSM: entries = n * W windows, 3 affine rounds at 6.2 modmuls, the rest XYZZ at 9.5,
     # 288 wide multiplies per 12-limb Montgomery product
-    msm_entries = n * 16
+    windows = 15 if log_deg >= 18 else 16
+    msm_entries = n * windows
     wide_per_msm = (msm_entries * (7.0 / 8.0) * 6.2 + msm_entries * (1.0 / 8.0) * 9.5) * 288
     msm_kernel_ms = (stage_ms["affine_pair_rounds"] + stage_ms["bucket_accumulate"]) / 2
     # dominant kernel = round 0 of the batched-affine pair rounds (one launch per MSM, touches every (base, scalar) pair)
     dom_ms = pair0_ms / pair0_cnt if pair0_cnt else (acc_ms / max(acc_cnt, 1))
-    dom_name = "run_kernel_occ<MsmAffinePairBody<Bls12381, true>>" if pair0_cnt else "run_persistent_kernel<MsmAccumulateBody<Bls12381>>"
+    dom_name = "run_persistent_kernel_occ<MsmAffineChunkBody<Bls12381, true>>" if pair0_cnt else "run_persistent_kernel<MsmAccumulateBody<Bls12381>>"
     achieved = (n * ALGO_BYTES_PER_SCALAR_MULT / 1e9) / (dom_ms / 1e3) if dom_ms else None
+    traffic, traffic_src = ncu_traffic(log_deg)
     line = {
         "metric": "MarlinKZG10/BLS12-381 commit+open polys/s at deg 2^20", "value": value, "unit": "polys/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32-limb Montgomery (Fq 381-bit x12, Fr 255-bit x8)",
         "data": "synthetic",
-        "config": {"workload": workload, "parallelism": f"poly-sharded x{world}, SRS replicated, {inflight} polynomials in flight per GPU",
-                   "l2": "per-step working set (window-folded SRS tables 1.6 GB gather + 34 MB coefficients, rotating "
+        "config": {"workload": workload, "parallelism": f"poly-sharded x{world}, SRS replicated; one batch call per rank, 2 polynomials "
+                   "(4 MSM pipelines) in flight inside the library",
+                   "l2": "per-step working set (window-folded SRS tables 1.5 GB gather + 34 MB coefficients, rotating "
                          "polynomials) exceeds the 126 MB L2; no explicit flush"},
         "msm_scalar_mults_per_s": 2 * n * polys / (ms_dev / 1e3),
         "stage_ms_per_step": stage_ms,
-        "e2e": {"value": e2e, "unit": "polys/s", "h2d_bytes_per_step": 2 * n * 32 + 2 * 32, "d2h_bytes_per_step": 2 * 96 + 2 * 4,
+        "single_call_ms_per_step": ms_single_call,
+        "e2e": {"value": e2e, "unit": "polys/s", "h2d_bytes_per_step": n * 32 + 32, "d2h_bytes_per_step": 2 * 96 + 2 * 4,
                 "ms_per_step": ms_host / steps},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC_BYTES.get(log_deg), "peak_source": peak_src,
-                     "launch_ms": dom_ms,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "launch_ms": dom_ms,
                      "compute_roofline": {"bound": "int32 multiply pipe (IMAD.WIDE.U32)", "peak_wide_mul_per_s": imad_peak,
                                           "achieved_wide_mul_per_s": wide_per_msm / (msm_kernel_ms / 1e3) if msm_kernel_ms else None,
                                           "frac": (wide_per_msm / (msm_kernel_ms / 1e3) / imad_peak) if (msm_kernel_ms and imad_peak) else None,
-                                          "kernels": "MsmAffinePairBody x3 rounds + MsmAccumulateBody, per MSM"},
+                                          "kernels": "pair rounds x3 + MsmAccumulateBody, per MSM (multiply counts assumed: 6.2 / 9.5 modmuls "
+                                                     "per affine / XYZZ addition, 288 wide multiplies per modmul)"},
                      "note": "MSM is INT32-multiply bound (~3.4k IMAD.WIDE per 128 algorithmic bytes); the HBM fraction "
                              "is reported because north_star asks for it"},
     }
+    if shard is not None:
+        line["sharded"] = shard
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference_run(args, log_deg, steps=1, warmup=0, budget_s=25.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+class SingleDist:
+    """the torch.distributed calls the sharded helpers use, for a world of one process (python bench.py --gpus 1)"""
+
+    class ReduceOp:
+        MAX = "max"
+        MIN = "min"
+
+    def get_rank(self):
+        return 0
+
+    def get_world_size(self):
+        return 1
+
+    def barrier(self):
+        pass
+
+    def all_gather(self, outs, t):
+        outs[0].copy_(t)
+
+    def all_reduce(self, t, op=None):
+        return t
+
+    def all_to_all_single(self, out, inp):
+        out.copy_(inp)
+
+
+def ncu_traffic(log_deg):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu --set full
+    capture of THIS code (profiles/r02_ncu_pair0_traffic.json, written by tools/ncu_traffic.py from the capture's raw page)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_pair0_traffic.json")) as f:
+            d = json.load(f)
+        if int(d.get("log_deg", -1)) == log_deg:
+            return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"]), d.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
+def sharded_record(args, eng, pc, params, sharded, dist, dev, rank, world, cid):
+    """The north_star's multi-GPU splits, measured next to the headline (same process group, device-resident, max over ranks):
+      msm        ONE 2^22-term MSM sharded by index range over the N GPUs: fused NVLink point-sum (pcgpu_msm_peer), the NCCL
+                 all-gather baseline, and the same MSM on one GPU (every rank runs it; the slowest rank is reported)
+      cfg5       BASELINE.json configs[4]: 64 polynomials of degree 2^22 committed over the N GPUs (sharded by polynomial,
+                 SRS replicated), commitments gathered with NCCL
+      ntt        one 2^22 NTT sharded by the four-step split: exchange fused into pass 1 (NVLink stores + flag barrier), the NCCL
+                 all-to-all baseline, and the single-GPU transform"""
+    import numpy as np
+    import torch
+    log_n = args.sharded_log_n
+    n = (1 << log_n) + 1
+    out = {"log_n": log_n}
+
+    def tmax(fn, reps):
+        torch.cuda.synchronize(dev); dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / reps * 1e3
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    ks = torch.from_numpy(params.random_fr(cid, n, 2001).view(np.int64)).to(dev)
+    d_bases = torch.empty((n, 12), dtype=torch.int64, device=dev)
+    eng.fixed_base_mul(cid, params.g1_generator(cid), ks.data_ptr(), n=n, flags=pc.DEVICE_PTRS, out=d_bases.data_ptr())
+    del ks
+    full = eng.srs_register(cid, d_bases.data_ptr(), n=n, flags=pc.DEVICE_PTRS | pc.SRS_PRECOMPUTE)
+    base_polys = [torch.from_numpy(params.random_fr(cid, n, 3000 + i).view(np.int64)).to(dev) for i in range(2)]
+    fl = pc.SCALARS_MONT | pc.DEVICE_PTRS
+    peers = sharded.PeerGroup(eng, dist, device=dev if world > 1 else None)
+    # ---- one MSM, index-sharded
+    d_sc = base_polys[0]
+    ref = eng.msm(full, d_sc.data_ptr(), n=n, flags=fl)
+    single_ms = tmax(lambda: eng.msm(full, d_sc.data_ptr(), n=n, flags=fl), 3)
+    res = {}
+    for mode in ("peer", "nccl"):
+        if world == 1:
+            sm_srs_owner = None
+        sm = sharded.ShardedMsm(eng, cid, d_bases.data_ptr(), dist, flags=pc.SRS_PRECOMPUTE, device=dev if world > 1 else None, n=n,
+                                peers=peers if mode == "peer" else None, mode=mode)
+        lo, hi = sm.local_slice()
+        ptr = d_sc.data_ptr() + lo * 32
+        got = sm.msm(ptr, flags=fl, n=n)
+        res[mode + "_ok"] = bool((got[0] == ref[0]).all() and got[1] == ref[1])
+        res[mode + "_ms"] = tmax(lambda: sm.msm(ptr, flags=fl, n=n), 3)
+        sm.srs.release()
+    out["msm"] = {"terms": n, "single_gpu_ms": round(single_ms, 3), "sharded_nvlink_fused_ms": round(res["peer_ms"], 3),
+                  "sharded_nccl_allgather_ms": round(res["nccl_ms"], 3), "bit_exact_vs_single_gpu": res["peer_ok"] and res["nccl_ok"],
+                  "scalar_mults_per_s": round(n / (res["peer_ms"] / 1e3)), "speedup_vs_single_gpu": round(single_ms / res["peer_ms"], 3),
+                  "collective": f"{world} x ~3.3 KB bit-plane records stored into the peers' windows by the pipeline's last kernel, "
+                                "flag wait, one D2H copy; bounded by the slowest rank's Pippenger pipeline, not by the exchange"}
+    # ---- cfg5: 64 polynomials over the ranks
+    npoly = args.cfg5_polys
+    mine = sharded.poly_assignment(npoly, rank, world)
+    polys = []
+    for i in mine:   # distinct polynomials derived on the device: p_i = base_0 * c_i + base_1
+        p = base_polys[1].clone()
+        eng.fr_axpy(cid, p.data_ptr(), params.random_fr(cid, 1, 4000 + i)[0], base_polys[0].data_ptr(), n=n, flags=pc.DEVICE_PTRS)
+        polys.append(p)
+    torch.cuda.synchronize(dev)
+    run = lambda: sharded.commit_batch_sharded(eng, full, [(p.data_ptr(), n) for p in polys], dist, device=dev if world > 1 else None,
+                                               flags=pc.DEVICE_PTRS, num_polys=npoly)
+    comms, _ = run()
+    spot = eng.kzg_commit(full, polys[0].data_ptr(), n=n, flags=pc.DEVICE_PTRS)
+    ms = tmax(run, 1)
+    out["cfg5"] = {"workload": f"Batched MarlinKZG10 commit, {npoly} polys, degree 2^{log_n}, BLS12-381, sharded by polynomial over {world} GPU(s)",
+                   "ms_total": round(ms, 2), "polys_per_s": round(npoly / (ms / 1e3), 2), "scalar_mults_per_s": round(npoly * n / (ms / 1e3)),
+                   "spot_check_ok": bool((comms[mine[0]] == spot[0]).all()),
+                   "collective": "NCCL all_gather of the commitments (104 bytes per polynomial) after the local batches; no data-path exchange"}
+    del polys
+    full.release()
+    del d_bases
+    torch.cuda.empty_cache()
+    # ---- one NTT, four-step sharded
+    ntt_log = min(log_n, 22)
+    n_in = (1 << ntt_log) - 3
+    x = base_polys[0]
+    exp = torch.empty((1 << ntt_log, 4), dtype=torch.int64, device=dev)
+    eng.ntt(cid, x.data_ptr(), ntt_log, n_in=n_in, flags=pc.DEVICE_PTRS, out=exp.data_ptr())
+    ntt_single = tmax(lambda: eng.ntt(cid, x.data_ptr(), ntt_log, n_in=n_in, flags=pc.DEVICE_PTRS, out=exp.data_ptr()), 5)
+    rec = {"log_n": ntt_log, "single_gpu_ms": round(ntt_single, 4)}
+    m1, m2 = eng.ntt_split(ntt_log)
+    if world > 1 and (1 << m1) % world == 0 and (1 << m2) % world == 0:
+        pn = sharded.PeerNtt.from_group(eng, cid, ntt_log, peers)
+        rows = pn.N1 // world
+        o1 = torch.empty((pn.N2, rows, 4), dtype=torch.int64, device=dev)
+        pn.forward_rank(x.data_ptr(), n_in, o1.data_ptr())
+        want = exp.view(pn.N2, pn.N1, 4)[:, rank * rows:(rank + 1) * rows, :]
+        ok = bool((o1 == want).all())
+        rec["sharded_nvlink_fused_ms"] = round(tmax(lambda: pn.forward_rank(x.data_ptr(), n_in, o1.data_ptr()), 5), 4)
+        sn = sharded.ShardedNtt(eng, cid, ntt_log, dist, device=dev)
+        ok = ok and bool((sn.forward_device(x, n_in) == want).all())
+        rec["sharded_nccl_alltoall_ms"] = round(tmax(lambda: sn.forward_device(x, n_in), 5), 4)
+        okt = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        rec["bit_exact_vs_single_gpu"] = bool(okt.item())
+        rec["speedup_vs_single_gpu"] = round(ntt_single / rec["sharded_nvlink_fused_ms"], 3)
+        rec["nvlink_bytes_per_rank"] = (1 << ntt_log) * 32 * (world - 1) // (world * world)
+        rec["collective"] = "pass-1 blocks store their outputs straight into the row owners' buffers (NVLink P2P), epoch-flag barrier, pass 2"
+    out["ntt"] = rec
+    peers.close()
+    return out
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpcgpu.so")
 CURVES = ["Bls12381", "Bn254", "Pallas"]
-GROUPS = [1, 2, 3, 4, 5]   # inst_unit.cu: Pippenger pipeline | small MSM | SRS + MSM entry points | Fr / NTT | IPA + wire
+GROUPS = [6, 8, 9, 5, 2, 3, 1, 4]   # inst_unit.cu groups, heaviest first (see the list at the top of that file)
 # heaviest first so the thread pool keeps every core busy to the end
 UNITS = [("inst_unit", c, g) for g in GROUPS for c in CURVES] + [("api", None, None)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -52,7 +52,9 @@ def build(force=False, verbose=False, extra=()):
         if rc:
             raise RuntimeError(f"nvcc failed on {unit}.cu")
         objs.append(out)
-    subprocess.check_call(["nvcc", "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    # link next to the target and rename: a reader (or a snapshot of the tree) never sees a half-written library
+    subprocess.check_call(["nvcc", "-shared", "-o", LIB + ".tmp"] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    os.replace(LIB + ".tmp", LIB)
     return LIB
 
 

@@ -225,16 +225,12 @@ int msm_device_planes(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, 
   // batched-affine rounds while buckets hold >= 64 points and a round still gives every thread >= 16 additions
   {
     size_t Tmax = 0;
-    if ((rc = rt::resident_threads_occ<128, PAIR_MIN_BLOCKS, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
+    if ((rc = msm_pair_oneshot_threads<C>(&Tmax))) return rc;
     size_t entries = (size_t)g.n * g.W, avg = entries / g.TB;
     uint32_t R = 0;
     while (R < 8 && (avg >> R) >= 4 && (entries >> (R + 1)) >= 16 * Tmax) R++;
     if (const char *e = getenv("PCGPU_MSM_AFFINE_ROUNDS")) { int v = atoi(e); if (v >= 0 && v <= 12) R = (uint32_t)v; }
     g.affine_rounds = R;
-    size_t PT = 0;
-    if ((rc = rt::persistent_threads_occ<128, PAIR_MIN_BLOCKS, MsmAffineChunkBody<C, true>>(&PT))) return rc;
-    g.pair_threads = (uint32_t)PT;
-    if (const char *e = getenv("PCGPU_PAIR_MODE")) g.pair_mode = e[0] == '0' ? 0u : 1u;   // A/B knob: 0 = one-shot pair kernel
   }
   if (g.affine_rounds && !ctx->d_pow2[C::ID]) {
     using QP = typename C::Fq;
@@ -1366,6 +1362,16 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int msm_to_host<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const uint32_t *, size_t, bool, host::HXYZZ<C> *); \
   EXT template int msm_issue<C>(pcgpu_ctx *, const pcgpu_srs *, size_t, const uint32_t *, size_t, bool, MsmPending<C> *);   \
   EXT template int msm_collect<C>(pcgpu_ctx *, MsmPending<C> *, host::HXYZZ<C> *);
+#define PCGPU_INST_PAIR1(C, EXT)                                                                                           \
+  EXT template int pcgpu::msm_pair_round_oneshot<C>(bool, const uint32_t *, const MsmGeom &, const uint32_t *, const Affine<C> *, uint32_t *, \
+                                             const uint32_t *, uint32_t, uint32_t *, const uint32_t *, Affine<C> *, rt::stream_t);   \
+  EXT template int pcgpu::msm_pair_oneshot_threads<C>(size_t *);
+#define PCGPU_INST_ACC(C, EXT)                                                                                             \
+  EXT template int pcgpu::msm_accumulate_launch<C>(const uint32_t *, const MsmGeom &, const uint32_t *, const uint32_t *, const uint32_t *, \
+                                            const uint32_t *, XYZZ<C> *, uint32_t *, const Affine<C> *, rt::stream_t);
+#define PCGPU_INST_REDUCE(C, EXT)                                                                                          \
+  EXT template int pcgpu::msm_reduce_launch<C>(const MsmGeom &, const uint32_t *, const XYZZ<C> *, XYZZ<C> *, XYZZ<C> *, XYZZ<C> *,    \
+                                        const uint32_t *, const uint32_t *, rt::stream_t);
 #define PCGPU_INST_SMALL(C, EXT)                                                                                           \
   EXT template int msm_small_to_host<C>(pcgpu_ctx *, const MsmSmallProblem<C> *, uint32_t, bool, host::HXYZZ<C> *);
 #define PCGPU_INST_SRS(C, EXT)                                                                                             \
@@ -1403,4 +1409,5 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int g1_serialize_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, uint8_t *); \
   EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *);
 #define PCGPU_INSTANTIATE(C, EXT) \
+  PCGPU_INST_PAIR1(C, EXT) PCGPU_INST_ACC(C, EXT) PCGPU_INST_REDUCE(C, EXT) \
   PCGPU_INST_PIPE(C, EXT) PCGPU_INST_SMALL(C, EXT) PCGPU_INST_SRS(C, EXT) PCGPU_INST_FR(C, EXT) PCGPU_INST_IPA(C, EXT)

@@ -47,8 +47,6 @@ struct MsmGeom {
                           // 2^h * sum_hi hi * R_hi + sum_lo (lo+1) * C_lo over row sums R and column sums C (large c)
   uint32_t pt_words;      // table record stride in 32-bit words (2N raw; 32 for 128-byte aligned BLS12-381 records)
   uint32_t y_words;       // offset of y inside a record, in words (N raw; 16 in the aligned BLS12-381 layout)
-  uint32_t pair_threads;  // resident threads of the pair-round kernel (sizes its scratch)
-  uint32_t pair_mode;     // 1: chunked persistent pair kernel (default), 0: one-shot kernel
 };
 
 enum : uint32_t { ENTRY_SIGN = 0x80000000u, ENTRY_GROUP_SHIFT = 26, ENTRY_IDX_MASK = (1u << 26) - 1 };
@@ -382,6 +380,17 @@ struct MsmAccumulateBody {
 // ---------------------------------------------------------------------------------------------
 enum { HEAVY_BUCKET_TASKS = 8, HEAVY_BLOCK = 128, HEAVY_GRID = 64, REDUCE_BLOCK = 128 };
 
+// Out-of-line XYZZ addition for the latency-bound reduction kernels: keeps every kernel small (with the addition inlined at
+// each site the BLS12-381 unit spent > 10 minutes in cicc) at no measurable cost -- these kernels wait on chains of dependent
+// additions, not on issue slots.
+template <class C>
+#ifdef __CUDACC__
+__device__ __noinline__
+#else
+inline
+#endif
+void xyzz_add_ool(XYZZ<C> &acc, const XYZZ<C> &p) { xyzz_add<C>(acc, p); }
+
 // one thread block per heavy bucket (grid-strided over the list): strided partial sums, then a shared-memory tree
 template <class C>
 struct MsmHeavyBucketBody {
@@ -393,12 +402,14 @@ struct MsmHeavyBucketBody {
       const uint32_t b = heavy_list[hb], t0 = task_off[b], t1 = task_off[b + 1];
       PCGPU_BLOCK_FOR(i, HEAVY_BLOCK) {
         XYZZ<C> acc = XYZZ<C>::inf();
-        for (uint32_t q = t0 + i; q < t1; q += HEAVY_BLOCK) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add<C>(acc, p); }
+#pragma unroll 1
+        for (uint32_t q = t0 + i; q < t1; q += HEAVY_BLOCK) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add_ool<C>(acc, p); }
         sh[i] = acc;
       }
       PCGPU_BLOCK_SYNC();
+#pragma unroll 1
       for (uint32_t half = HEAVY_BLOCK / 2; half >= 1; half >>= 1) {
-        PCGPU_BLOCK_FOR(i, half) { XYZZ<C> x = sh[i], y = sh[i + half]; xyzz_add<C>(x, y); sh[i] = x; }
+        PCGPU_BLOCK_FOR(i, half) { XYZZ<C> x = sh[i], y = sh[i + half]; xyzz_add_ool<C>(x, y); sh[i] = x; }
         PCGPU_BLOCK_SYNC();
       }
       PCGPU_BLOCK_FOR(i, 1) { store_xyzz<C>(buckets + b, sh[0]); }
@@ -410,8 +421,9 @@ struct MsmHeavyBucketBody {
 // shared-memory tree over REDUCE_BLOCK per-thread values; the sum ends in sh[0]
 template <class C>
 PCGPU_KERNEL_DEV void block_tree_sum(XYZZ<C> *sh) {
+#pragma unroll 1
   for (uint32_t half = REDUCE_BLOCK / 2; half >= 1; half >>= 1) {
-    PCGPU_BLOCK_FOR(i, half) { XYZZ<C> x = sh[i], y = sh[i + half]; xyzz_add<C>(x, y); sh[i] = x; }
+    PCGPU_BLOCK_FOR(i, half) { XYZZ<C> x = sh[i], y = sh[i + half]; xyzz_add_ool<C>(x, y); sh[i] = x; }
     PCGPU_BLOCK_SYNC();
   }
 }
@@ -431,6 +443,7 @@ struct MsmRowReduceBody {
     const uint32_t s = (uint32_t)(blk / rows), hi = (uint32_t)(blk % rows);
     PCGPU_BLOCK_FOR(t, REDUCE_BLOCK) {
       XYZZ<C> acc = XYZZ<C>::inf();
+#pragma unroll 1
       for (uint32_t lo = t; lo < cols; lo += REDUCE_BLOCK) {
         const size_t b = (size_t)s * NB + (size_t)hi * cols + lo;
         const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
@@ -438,10 +451,11 @@ struct MsmRowReduceBody {
         if (t1 - t0 > HEAVY_BUCKET_TASKS) bs = load_xyzz<C>(buckets + b);          // written by MsmHeavyBucketBody
         else {
           bs = XYZZ<C>::inf();
-          for (uint32_t q = t0; q < t1; q++) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add<C>(bs, p); }
+#pragma unroll 1
+          for (uint32_t q = t0; q < t1; q++) { XYZZ<C> p = load_xyzz<C>(partial + q); xyzz_add_ool<C>(bs, p); }
           store_xyzz<C>(buckets + b, bs);
         }
-        xyzz_add<C>(acc, bs);
+        xyzz_add_ool<C>(acc, bs);
       }
       sh[t] = acc;
     }
@@ -460,9 +474,10 @@ struct MsmColReduceBody {
     const uint32_t s = (uint32_t)(blk / cols), lo = (uint32_t)(blk % cols);
     PCGPU_BLOCK_FOR(t, REDUCE_BLOCK) {
       XYZZ<C> acc = XYZZ<C>::inf();
+#pragma unroll 1
       for (uint32_t hi = t; hi < rows; hi += REDUCE_BLOCK) {
         XYZZ<C> p = load_xyzz<C>(buckets + (size_t)s * NB + (size_t)hi * cols + lo);
-        xyzz_add<C>(acc, p);
+        xyzz_add_ool<C>(acc, p);
       }
       sh[t] = acc;
     }
@@ -486,8 +501,9 @@ struct MsmPlaneReduceBody {
     const uint32_t cnt = col ? cols : rows, wofs = col ? 1u : 0u, bit = col ? j : j - bits_c;
     PCGPU_BLOCK_FOR(t, REDUCE_BLOCK) {
       XYZZ<C> acc = XYZZ<C>::inf();
+#pragma unroll 1
       for (uint32_t k = t; k < cnt; k += REDUCE_BLOCK)
-        if (((k + wofs) >> bit) & 1) { XYZZ<C> p = load_xyzz<C>(vals + k); xyzz_add<C>(acc, p); }
+        if (((k + wofs) >> bit) & 1) { XYZZ<C> p = load_xyzz<C>(vals + k); xyzz_add_ool<C>(acc, p); }
       sh[t] = acc;
     }
     PCGPU_BLOCK_SYNC();
@@ -532,7 +548,6 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
   g.affine_rounds = 0;
   g.h_split = (c - 1) / 2;
   g.pt_words = 0; g.y_words = 0;  // set by the caller (table_layout)
-  g.pair_threads = 0; g.pair_mode = 1;
   return g;
 }
 
@@ -540,12 +555,6 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
 inline size_t msm_plane_scratch_elems(const MsmGeom &g) {
   size_t cols = (size_t)1 << g.h_split, rows = g.NB >> g.h_split;
   return (size_t)g.S * (rows + cols);
-}
-
-// field elements of the pair rounds' scratch: prefix | x1 | d of the one-shot kernel, or the 5 * K * T columns of the chunked one
-inline size_t pair_scratch_elems(const MsmGeom &g, size_t bound0) {
-  size_t a = 3 * (bound0 + (1u << 20)), b = (size_t)5 * 32 * g.pair_threads;
-  return a > b ? a : b;
 }
 
 template <class C>
@@ -565,7 +574,7 @@ inline size_t msm_workspace_bytes(const MsmGeom &g) {
     size_t bound0 = max_entries / 2 + g.TB + 1, bound1 = bound0 / 2 + g.TB + 1;
     b += 3 * rt::Arena::pad((g.TB + 2) * sizeof(uint32_t));
     b += rt::Arena::pad(bound0 * sizeof(uint32_t));
-    b += rt::Arena::pad(pair_scratch_elems(g, bound0) * sizeof(Fp<typename C::Fq>));
+    b += rt::Arena::pad(3 * (bound0 + (1u << 20)) * sizeof(Fp<typename C::Fq>));
     b += rt::Arena::pad(bound0 * sizeof(Affine<C>)) + rt::Arena::pad(bound1 * sizeof(Affine<C>));
   }
   return b + 4096;
@@ -575,6 +584,38 @@ inline size_t msm_workspace_bytes(const MsmGeom &g) {
 #define PCGPU_PAIR_MIN_BLOCKS 4
 #endif
 enum { PAIR_MIN_BLOCKS = PCGPU_PAIR_MIN_BLOCKS };  // resident blocks per SM requested for the affine pair kernel
+
+// ---- launch wrappers of the heavy kernels: separate function templates so that every one of them can be instantiated in its
+// own translation unit (inst_unit.cu groups 6-9) and the BLS12-381 build does not serialise on one 9-minute ptxas run ----
+template <class C>
+int msm_pair_round_oneshot(bool round0, const uint32_t *tables, const MsmGeom &g, const uint32_t *entries, const Affine<C> *in,
+                           uint32_t *src, const uint32_t *off_out, uint32_t T, uint32_t *prefix, const uint32_t *pow2, Affine<C> *out,
+                           rt::stream_t st) {
+  if (round0) return rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, true>{tables, g, entries, nullptr, src, off_out, T, prefix, pow2, out}, T, st);
+  return rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, false>{tables, g, entries, in, src, off_out, T, prefix, pow2, out}, T, st);
+}
+template <class C> int msm_pair_oneshot_threads(size_t *out) { return rt::resident_threads_occ<128, PAIR_MIN_BLOCKS, MsmAffinePairBody<C, true>>(out); }
+
+template <class C>
+int msm_accumulate_launch(const uint32_t *tables, const MsmGeom &g, const uint32_t *offsets, const uint32_t *task_off,
+                          const uint32_t *task_bucket, const uint32_t *entries, XYZZ<C> *partial, uint32_t *queue, const Affine<C> *pts,
+                          rt::stream_t st) {
+  return rt::launch_persistent<128>(MsmAccumulateBody<C>{tables, g, offsets, task_off, task_bucket, entries, partial, queue, pts}, st);
+}
+
+template <class C>
+int msm_reduce_launch(const MsmGeom &g, const uint32_t *task_off, const XYZZ<C> *partial, XYZZ<C> *buckets, XYZZ<C> *planes,
+                      XYZZ<C> *plane_out, const uint32_t *heavy_count, const uint32_t *heavy_list, rt::stream_t st) {
+  const uint32_t h = g.h_split, cols = 1u << h, rows = g.NB >> h, bits_c = h + 1, bits_r = g.c - 1 - h;
+  const size_t smem = REDUCE_BLOCK * sizeof(XYZZ<C>);
+  XYZZ<C> *Rv = planes, *Cv = planes + (size_t)g.S * rows;
+  int rc;
+  if ((rc = rt::launch_blocks<HEAVY_BLOCK>(MsmHeavyBucketBody<C>{task_off, partial, buckets, heavy_count, heavy_list}, HEAVY_GRID,
+                                           HEAVY_BLOCK * sizeof(XYZZ<C>), st))) return rc;
+  if ((rc = rt::launch_blocks<REDUCE_BLOCK>(MsmRowReduceBody<C>{task_off, partial, buckets, Rv, g.NB, rows, cols}, (size_t)g.S * rows, smem, st))) return rc;
+  if ((rc = rt::launch_blocks<REDUCE_BLOCK>(MsmColReduceBody<C>{buckets, Cv, g.NB, rows, cols}, (size_t)g.S * cols, smem, st))) return rc;
+  return rt::launch_blocks<REDUCE_BLOCK>(MsmPlaneReduceBody<C>{Rv, Cv, plane_out, rows, cols, bits_c, bits_r}, (size_t)g.S * (bits_c + bits_r), smem, st);
+}
 
 // Runs the device pipeline on `st`.  d_scalars: n x 8 uint32 on the device.  On return (asynchronously)
 // *d_planes points at the S*c bit-plane sums, element (s*c + j) at index (s*c + j) * plane_stride, and
@@ -627,11 +668,11 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
     size_t bound0 = max_entries / 2 + g.TB + 1, bound1 = bound0 / 2 + g.TB + 1;
     uint32_t *offA = arena.take<uint32_t>(g.TB + 2), *offB = arena.take<uint32_t>(g.TB + 2), *cnt = arena.take<uint32_t>(g.TB + 2);
     uint32_t *src = arena.take<uint32_t>(bound0);
-    uint32_t *prefix = (uint32_t *)arena.take<QF>(pair_scratch_elems(g, bound0));   // prefix | x1 | d, or the chunked kernel's columns
+    uint32_t *prefix = (uint32_t *)arena.take<QF>(3 * (bound0 + (1u << 20)));   // prefix | x1 | d  (x1, d: round 0 only)
     Affine<C> *ptsA = arena.take<Affine<C>>(bound0), *ptsB = arena.take<Affine<C>>(bound1);
     if (!offA || !offB || !cnt || !src || !prefix || !ptsA || !ptsB) return rt::E_OOM;
     size_t Tmax = 0;
-    if ((rc = rt::resident_threads_occ<128, PAIR_MIN_BLOCKS, MsmAffinePairBody<C, true>>(&Tmax))) return rc;
+    if ((rc = msm_pair_oneshot_threads<C>(&Tmax))) return rc;
     if (Tmax > (1u << 20)) Tmax = 1u << 20;
     if (const char *e = getenv("PCGPU_MSM_AFFINE_TDIV")) { int v = atoi(e); if (v >= 1 && v <= 16) Tmax = (Tmax / v + 127) / 128 * 128; }  // tuning knob
     prof.begin(11, st);
@@ -647,18 +688,7 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
       if ((rc = rt::launch<256>(PairPlanBody{off_in, off_out, g.TB, src}, bound, st))) return rc;
       uint32_t T = (uint32_t)Tmax;
       if (r == 0) prof.begin(12, st);
-      if (g.pair_mode == 1 && g.pair_threads) {
-        // chunked persistent kernel: K slots per thread per chunk, about four chunks per warp in round 0
-        const uint32_t PT = g.pair_threads;
-        uint32_t K = (uint32_t)((bound + 4 * (size_t)PT - 1) / (4 * (size_t)PT));
-        if (K < 16) K = 16;
-        if (K > PAIR_CHUNK_MAX_K) K = PAIR_CHUNK_MAX_K;
-        if (const char *e = getenv("PCGPU_PAIR_K")) { int v = atoi(e); if (v >= 1 && v <= PAIR_CHUNK_MAX_K) K = (uint32_t)v; }   // tuning knob
-        if ((rc = rt::dev_memset(err + 10, 0, 4, st))) return rc;
-        if (r == 0) rc = rt::launch_persistent_occ<128, PAIR_MIN_BLOCKS>(MsmAffineChunkBody<C, true>{tables, g, entries, nullptr, src, off_out, PT, K, prefix, pow2, out, err + 10}, st);
-        else rc = rt::launch_persistent_occ<128, PAIR_MIN_BLOCKS>(MsmAffineChunkBody<C, false>{tables, g, entries, in, src, off_out, PT, K, prefix, pow2, out, err + 10}, st);
-      } else if (r == 0) rc = rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, true>{tables, g, entries, nullptr, src, off_out, T, prefix, pow2, out}, T, st);
-      else rc = rt::launch_occ<128, PAIR_MIN_BLOCKS>(MsmAffinePairBody<C, false>{tables, g, entries, in, src, off_out, T, prefix, pow2, out}, T, st);
+      rc = msm_pair_round_oneshot<C>(r == 0, tables, g, entries, in, src, off_out, T, prefix, pow2, out, st);
       if (rc) return rc;
       if (r == 0) prof.end(12, st);
       off_in = off_out;
@@ -676,20 +706,11 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
   prof.end(3, st);
 
   prof.begin(4, st);
-  if ((rc = rt::launch_persistent<128>(MsmAccumulateBody<C>{tables, g, offsets, task_off, task_bucket, entries, partial, err + 8, pts}, st))) return rc;
+  if ((rc = msm_accumulate_launch<C>(tables, g, offsets, task_off, task_bucket, entries, partial, err + 8, pts, st))) return rc;
   prof.end(4, st);
 
   prof.begin(5, st);
-  {
-    const uint32_t h = g.h_split, cols = 1u << h, rows = g.NB >> h, bits_c = h + 1, bits_r = g.c - 1 - h;
-    const size_t smem = REDUCE_BLOCK * sizeof(XYZZ<C>);
-    XYZZ<C> *Rv = planes, *Cv = planes + (size_t)g.S * rows;
-    if ((rc = rt::launch_blocks<HEAVY_BLOCK>(MsmHeavyBucketBody<C>{task_off, partial, buckets, err + 12, cursor}, HEAVY_GRID,
-                                             HEAVY_BLOCK * sizeof(XYZZ<C>), st))) return rc;
-    if ((rc = rt::launch_blocks<REDUCE_BLOCK>(MsmRowReduceBody<C>{task_off, partial, buckets, Rv, g.NB, rows, cols}, (size_t)g.S * rows, smem, st))) return rc;
-    if ((rc = rt::launch_blocks<REDUCE_BLOCK>(MsmColReduceBody<C>{buckets, Cv, g.NB, rows, cols}, (size_t)g.S * cols, smem, st))) return rc;
-    if ((rc = rt::launch_blocks<REDUCE_BLOCK>(MsmPlaneReduceBody<C>{Rv, Cv, plane_out, rows, cols, bits_c, bits_r}, (size_t)g.S * (bits_c + bits_r), smem, st))) return rc;
-  }
+  if ((rc = msm_reduce_launch<C>(g, task_off, partial, buckets, planes, plane_out, err + 12, cursor, st))) return rc;
   prof.end(5, st);
   return rt::OK;
 }

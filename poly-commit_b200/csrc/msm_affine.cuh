@@ -64,15 +64,6 @@ PCGPU_DEV Fp<Q> load_fq(const uint32_t *p) {
   return r;
 }
 template <class Q>
-PCGPU_DEV Fp<Q> load_fq_plain(const uint32_t *p) {   // coherent load: data written earlier in the same kernel
-  constexpr int N = Q::N;
-  const u32x4 *q = reinterpret_cast<const u32x4 *>(p);
-  Fp<Q> r;
-#pragma unroll
-  for (int j = 0; j < N / 4; j++) { u32x4 v = q[j]; r.l[4 * j] = v.x; r.l[4 * j + 1] = v.y; r.l[4 * j + 2] = v.z; r.l[4 * j + 3] = v.w; }
-  return r;
-}
-template <class Q>
 PCGPU_DEV void store_fq(uint32_t *p, const Fp<Q> &a) {
   constexpr int N = Q::N;
   u32x4 *q = reinterpret_cast<u32x4 *>(p);
@@ -239,125 +230,6 @@ struct MsmAffinePairBody {
       Affine<C> *dst = pts_out + o;
       store_fq<Q>(reinterpret_cast<uint32_t *>(dst), R.x);
       store_fq<Q>(reinterpret_cast<uint32_t *>(dst) + N, R.y);
-    }
-  }
-};
-
-// ---------------------------------------------------------------------------------------------------------------------------
-// Chunked variant (default).  Same arithmetic, different schedule:
-//   * every warp of a persistent grid claims chunks of K * 32 output slots from a global counter and runs
-//     [pass 1 | inversion | pass 2] per chunk, so the warps of an SM drift out of phase: the DRAM-bound gathers of one warp's
-//     pass 1 and the ALU-bound binary-GCD inversion of another hide under the multiply-bound pass 2 of the rest (the one-shot
-//     kernel above runs the three phases in lock step across the whole grid: 0.62 ms of gathers and 0.17 ms of inversion
-//     exposed per 2^20-term round 0, profiles/r01_final_ncu_prof_pair0_final.txt);
-//   * every operand record is fetched ONCE: pass 1 reads the complete points (one 128-byte DRAM burst per table record),
-//     and leaves x1, d = x2 - x1, y1, dy = y2 - y1 next to the prefix product in a per-thread scratch column (coalesced
-//     across the warp); pass 2 is pure streaming + five multiplications and never touches the tables again.
-// Scratch layout: element (k, thread) of array a at ((a * K + k) * T + thread) * N words, T = resident threads.
-// ---------------------------------------------------------------------------------------------------------------------------
-enum { PAIR_CHUNK_MAX_K = 32 };
-
-template <class C, bool FROM_TABLES>
-struct MsmAffineChunkBody {
-  const uint32_t *tables; MsmGeom g; const uint32_t *entries;
-  const Affine<C> *pts_in;
-  uint32_t *src; const uint32_t *off_out;
-  uint32_t T, K;                       // resident threads, slots per thread per chunk
-  uint32_t *scratch;                   // 5 * K * T field elements
-  const uint32_t *pow2;
-  Affine<C> *pts_out;
-  uint32_t *counter;                   // chunk queue (zeroed before the launch)
-
-  PCGPU_DEV Affine<C> fetch(uint32_t a) const {          // operand `a`: a round-0 entry word or an index into pts_in
-    using Q = typename C::Fq;
-    if (FROM_TABLES) {
-      const uint32_t grp = (a & ~ENTRY_SIGN) >> ENTRY_GROUP_SHIFT;
-      const uint32_t *rec = table_record<C>(tables, (size_t)grp * g.table_stride + g.base_off + (a & ENTRY_IDX_MASK), g);
-      Affine<C> p; p.x = load_fq<Q>(rec); p.y = load_fq<Q>(rec + g.y_words);
-      if (!p.is_inf()) p.y = fp_cneg<Q>(p.y, (a & ENTRY_SIGN) != 0);
-      return p;
-    }
-    return load_affine<C>(pts_in + a);
-  }
-
-  PCGPU_KERNEL_DEV void operator()(size_t gtid) const {
-    using Q = typename C::Fq;
-    constexpr int N = Q::N;
-    const uint32_t total = off_out[g.TB];
-    uint32_t lane, width;
-    uint32_t *pre = scratch + (size_t)gtid * N;
-    const size_t plane = (size_t)K * T * N, step = (size_t)T * N;
-    uint32_t *sx1 = pre + plane, *sd = sx1 + plane, *sy1 = sd + plane, *sdy = sy1 + plane;
-    for (;;) {
-      const uint32_t c = rt::claim_chunk(counter, &lane, &width);
-      const uint64_t base = (uint64_t)c * width * K;
-      if (base >= total) break;
-      // slots of this lane: base + k * width + lane, k < K
-      uint32_t kmax = 0;
-      if (base + lane < total) { uint64_t left = total - (base + lane); kmax = (uint32_t)((left + width - 1) / width); if (kmax > K) kmax = K; }
-      // ---- pass 1 ----
-      Fp<Q> acc = Fp<Q>::one();
-      for (uint32_t k = 0; k < kmax; k++) {
-        const uint32_t o = (uint32_t)(base + (uint64_t)k * width + lane);
-        const uint32_t sv = ldg_plain(src + o);
-        const uint32_t i0 = sv & ~(PAIR_SINGLE | PAIR_EXC);
-        const bool single = (sv & PAIR_SINGLE) != 0;
-        uint32_t a = i0, b = i0 + 1;
-        if (FROM_TABLES) { a = ldg1(entries + i0); b = single ? 0u : ldg1(entries + i0 + 1); }
-        Affine<C> P = fetch(a);
-        Fp<Q> d = Fp<Q>::one(), dy = Fp<Q>::zero();
-        if (!single) {
-          Affine<C> Qp = fetch(b);
-          if (P.x != Qp.x && !P.x.is_zero() && !Qp.x.is_zero()) { d = fp_sub<Q>(Qp.x, P.x); dy = fp_sub<Q>(Qp.y, P.y); }
-          else { pair_classify<C>(P, Qp, false, d); src[o] = sv | PAIR_EXC; }      // exceptional pair: pass 2 re-derives it
-        }
-        store_fq<Q>(pre + k * step, acc);
-        store_fq<Q>(sx1 + k * step, P.x);
-        store_fq<Q>(sd + k * step, d);
-        store_fq<Q>(sy1 + k * step, P.y);
-        store_fq<Q>(sdy + k * step, dy);
-        acc = fp_mul<Q>(acc, d);
-      }
-      Fp<Q> inv = kmax ? fp_inv_gcd<Q>(acc, pow2) : acc;
-      // ---- pass 2 ----
-      for (uint32_t k = kmax; k-- > 0;) {
-        const uint32_t o = (uint32_t)(base + (uint64_t)k * width + lane);
-        const uint32_t sv = ldg_plain(src + o);
-        const bool single = (sv & PAIR_SINGLE) != 0, exc = (sv & PAIR_EXC) != 0;
-        const Fp<Q> d = load_fq_plain<Q>(sd + k * step);
-        const Fp<Q> dinv = fp_mul<Q>(inv, load_fq_plain<Q>(pre + k * step));
-        inv = fp_mul<Q>(inv, d);
-        Affine<C> R;
-        if (!exc) {
-          const Fp<Q> x1 = load_fq_plain<Q>(sx1 + k * step), y1 = load_fq_plain<Q>(sy1 + k * step);
-          if (single) { R.x = x1; R.y = y1; }       // (0, 0) stays the identity encoding
-          else {
-            const Fp<Q> lam = fp_mul<Q>(load_fq_plain<Q>(sdy + k * step), dinv);
-            const Fp<Q> x3 = fp_sub<Q>(fp_sub<Q>(fp_sub<Q>(fp_sqr<Q>(lam), x1), x1), d);     // lam^2 - x1 - x2, x2 = x1 + d
-            R.x = x3;
-            R.y = fp_sub<Q>(fp_mul<Q>(lam, fp_sub<Q>(x1, x3)), y1);
-          }
-        } else {
-          const uint32_t i0 = sv & ~(PAIR_SINGLE | PAIR_EXC);
-          uint32_t a = i0, b = i0 + 1;
-          if (FROM_TABLES) { a = ldg1(entries + i0); b = ldg1(entries + i0 + 1); }
-          Affine<C> P = fetch(a), Qp = fetch(b);
-          Fp<Q> dd;
-          const uint32_t kind = pair_classify<C>(P, Qp, false, dd);
-          if (kind == PK_ADD || kind == PK_DBL) {
-            Fp<Q> num = kind == PK_ADD ? fp_sub<Q>(Qp.y, P.y) : fp_mul3<Q>(fp_sqr<Q>(P.x));
-            Fp<Q> lam = fp_mul<Q>(num, dinv);
-            Fp<Q> x3 = fp_sub<Q>(fp_sub<Q>(fp_sqr<Q>(lam), P.x), kind == PK_ADD ? Qp.x : P.x);
-            R.x = x3;
-            R.y = fp_sub<Q>(fp_mul<Q>(lam, fp_sub<Q>(P.x, x3)), P.y);
-          } else if (kind == PK_TAKE_P) R = P;
-          else if (kind == PK_TAKE_Q) R = Qp;
-          else R = Affine<C>::inf();
-        }
-        uint32_t *dst = reinterpret_cast<uint32_t *>(pts_out + o);
-        store_fq<Q>(dst, R.x);
-        store_fq<Q>(dst + N, R.y);
-      }
     }
   }
 };

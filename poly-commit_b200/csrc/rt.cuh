@@ -72,10 +72,6 @@ inline int launch_persistent(const Body &body, stream_t) { body(0); return OK; }
 // threads of one resident wave of `Body` (host emulation: a small number so multi-iteration paths are exercised)
 template <int BLOCK, class Body> inline int resident_threads(size_t *out) { *out = 48; return OK; }
 template <int BLOCK, int MINB, class Body> inline int launch_occ(const Body &body, size_t n, stream_t s) { return launch<BLOCK>(body, n, s); }
-// chunked persistent bodies: a "warp" (one lane under emulation) claims the next chunk index
-inline uint32_t claim_chunk(uint32_t *counter, uint32_t *lane, uint32_t *width) { *lane = 0; *width = 1; return atomic_add(counter, 1u); }
-template <int BLOCK, int MINB, class Body> inline int launch_persistent_occ(const Body &body, stream_t) { body(0); return OK; }
-template <int BLOCK, int MINB, class Body> inline int persistent_threads_occ(size_t *out) { *out = 1; return OK; }
 template <int BLOCK, int MINB, class Body> inline int resident_threads_occ(size_t *out) { *out = 48; return OK; }
 // Block-cooperative bodies: body(block_id, shared_memory).  Work inside the body is written as
 // PCGPU_BLOCK_FOR loops separated by PCGPU_BLOCK_SYNC(); anything that must survive a sync lives in shared memory.
@@ -219,40 +215,6 @@ inline int launch_persistent(const Body &body, stream_t s) {
     grid = sms * (per_sm > 0 ? per_sm : 1);
   }
   run_persistent_kernel<Body, BLOCK><<<grid, BLOCK, 0, s>>>(body);
-  launch_counter().fetch_add(1, std::memory_order_relaxed);
-  return last_error();
-}
-// chunked persistent kernels: every warp claims ONE chunk index at a time (lane 0 bumps the counter, the warp shares it)
-__device__ __forceinline__ uint32_t claim_chunk(uint32_t *counter, uint32_t *lane, uint32_t *width) {
-  *lane = threadIdx.x & 31; *width = 32;
-  uint32_t c = 0;
-  if (*lane == 0) c = atomicAdd(counter, 1u);
-  return __shfl_sync(0xffffffffu, c, 0);
-}
-template <class Body, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) run_persistent_kernel_occ(const Body body) {
-  body((size_t)blockIdx.x * BLOCK + threadIdx.x);
-}
-template <int BLOCK, int MINB, class Body>
-inline int persistent_threads_occ(size_t *out) {
-  static size_t cached = 0;
-  if (!cached) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, run_persistent_kernel_occ<Body, BLOCK, MINB>, BLOCK, 0);
-    if (e != cudaSuccess) return map_cuda(e);
-    cached = (size_t)sms * (per_sm > 0 ? per_sm : 1) * BLOCK;
-  }
-  *out = cached;
-  return OK;
-}
-template <int BLOCK, int MINB, class Body>
-inline int launch_persistent_occ(const Body &body, stream_t s) {
-  size_t threads = 0;
-  int rc = persistent_threads_occ<BLOCK, MINB, Body>(&threads);
-  if (rc) return rc;
-  run_persistent_kernel_occ<Body, BLOCK, MINB><<<(unsigned)(threads / BLOCK), BLOCK, 0, s>>>(body);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   return last_error();
 }

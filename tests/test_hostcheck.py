@@ -123,15 +123,8 @@ def test_msm_edge_scalars(eng, pc, msm_path):
     assert ei.value.code == -4
 
 
-@pytest.mark.parametrize("pair_mode", ["0", "1"])
 @pytest.mark.parametrize("rounds", [1, 3, 5])
-def test_msm_batched_affine_rounds(eng, pc, rounds, pair_mode, monkeypatch):
-    monkeypatch.setenv("PCGPU_PAIR_MODE", pair_mode)    # 0: one-shot pair kernel, 1: chunked persistent kernel (default)
-    monkeypatch.setenv("PCGPU_PAIR_K", "3" if rounds == 3 else "16")   # a short chunk exercises several chunks per lane
-    _affine_rounds_cases(eng, pc, rounds, monkeypatch)
-
-
-def _affine_rounds_cases(eng, pc, rounds, monkeypatch):
+def test_msm_batched_affine_rounds(eng, pc, rounds, monkeypatch):
     """msm_affine.cuh: forced batched-affine pairwise rounds (Montgomery batch inversion with the binary-GCD inverse)
     must give the same point, including the exceptional pairs: P + P, P + (-P), identity operands, odd bucket sizes."""
     monkeypatch.setenv("PCGPU_MSM_SMALL", "0")          # these cases target the bucket pipeline
