@@ -8,7 +8,7 @@ hiding_bound=None, degree_bound=None: the protocol of bench-templates/src/lib.rs
   value   whole-job polys/s with the coefficient vectors already resident in HBM (PCGPU_DEVICE_PTRS)
   e2e     the same through the C ABI with pinned HOST buffers (H2D of the coefficients inside the timed region,
           D2H of the two 96-byte points)
-  roofline    dominant kernel (bucket accumulate): algorithmic bytes (128 B per scalar-mult) over the
+  roofline    dominant kernel (round 0 of the batched-affine pair rounds): algorithmic bytes (128 B per scalar-mult) over the
               average launch duration from CUDA events on the launching stream; peak = MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle port (oracle/, OpenMP over Pippenger windows) timed on this box's host cores
   --impl reference   times that CPU path alone (the reference's Rust cannot be built here: no cargo/rustc)
@@ -31,9 +31,6 @@ sys.path.insert(0, ROOT)
 LOG_DEG = 20
 CURVE = "bls12_381"
 ALGO_BYTES_PER_SCALAR_MULT = 128  # 96 B affine base + 32 B scalar
-# dram__bytes_read.sum + dram__bytes_write.sum of one MsmAffinePairBody<Bls12381, round 0> launch, from the committed
-# ncu --set full capture profiles/r01_final_ncu_prof_pair0_final.txt (5.710451 GB + 2.001377 GB)
-NCU_TRAFFIC_BYTES = {20: 5710451000 + 2001377000}
 
 
 def parse():
@@ -333,13 +330,13 @@ def main():
     imad_peak = eng.measure_imad_peak()
     # multiply count of one 2^log_deg MSM: entries = n * W windows, 3 affine rounds at 6.2 modmuls, the rest XYZZ at 9.5,
     # 288 wide multiplies per 12-limb Montgomery product
-    windows = 15 if log_deg >= 18 else 16
+    windows = 16
     msm_entries = n * windows
     wide_per_msm = (msm_entries * (7.0 / 8.0) * 6.2 + msm_entries * (1.0 / 8.0) * 9.5) * 288
     msm_kernel_ms = (stage_ms["affine_pair_rounds"] + stage_ms["bucket_accumulate"]) / 2
     # dominant kernel = round 0 of the batched-affine pair rounds (one launch per MSM, touches every (base, scalar) pair)
     dom_ms = pair0_ms / pair0_cnt if pair0_cnt else (acc_ms / max(acc_cnt, 1))
-    dom_name = "run_persistent_kernel_occ<MsmAffineChunkBody<Bls12381, true>>" if pair0_cnt else "run_persistent_kernel<MsmAccumulateBody<Bls12381>>"
+    dom_name = "run_kernel_occ<MsmAffinePairBody<Bls12381, true>>" if pair0_cnt else "run_persistent_kernel<MsmAccumulateBody<Bls12381>>"
     achieved = (n * ALGO_BYTES_PER_SCALAR_MULT / 1e9) / (dom_ms / 1e3) if dom_ms else None
     traffic, traffic_src = ncu_traffic(log_deg)
     line = {
@@ -349,7 +346,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "parallelism": f"poly-sharded x{world}, SRS replicated; one batch call per rank, 2 polynomials "
                    "(4 MSM pipelines) in flight inside the library",
-                   "l2": "per-step working set (window-folded SRS tables 1.5 GB gather + 34 MB coefficients, rotating "
+                   "l2": "per-step working set (window-folded SRS tables 1.6 GB gather + 34 MB coefficients, rotating "
                          "polynomials) exceeds the 126 MB L2; no explicit flush"},
         "msm_scalar_mults_per_s": 2 * n * polys / (ms_dev / 1e3),
         "stage_ms_per_step": stage_ms,

@@ -299,6 +299,17 @@ int pcgpu_kzg_commit_open_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, co
                                 const void *z, uint32_t flags, void *out_comm_xy, uint8_t *out_comm_inf, void *out_w_xy,
                                 uint8_t *out_w_inf);
 
+/* ---- device buffers ------------------------------------------------------------------------------------------------------
+ * For callers that keep polynomials on the GPU across calls: the accumulators of MarlinKZG10::open (p, r, shifted_w,
+ * shifted_r: `p += (challenge_j, polynomial)`, marlin_pc/mod.rs:286-307) live in such buffers, so every polynomial crosses
+ * PCIe once and the combined polynomial never does.  The pointers are plain device pointers: pass them to any entry point
+ * together with PCGPU_DEVICE_PTRS (offsets are byte arithmetic on the pointer).  alloc zero-fills. */
+int pcgpu_buf_alloc(pcgpu_ctx *ctx, size_t bytes, void **out);
+int pcgpu_buf_free(pcgpu_ctx *ctx, void *buf);
+int pcgpu_buf_write(pcgpu_ctx *ctx, void *dst, size_t dst_offset, const void *src_host, size_t bytes);
+int pcgpu_buf_read(pcgpu_ctx *ctx, const void *src, size_t src_offset, void *dst_host, size_t bytes);
+int pcgpu_buf_zero(pcgpu_ctx *ctx, void *dst, size_t dst_offset, size_t bytes);
+
 /* ---- diagnostics -------------------------------------------------------------------------------- */
 /* Device self-test of the field layer: n pseudo-random pairs per field (Fq and Fr of `curve`), production
  * multiplier (carry-chained mad.lo/mad.hi schedule) against the plain 64-bit-accumulate multiplier compiled into

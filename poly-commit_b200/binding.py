@@ -98,6 +98,11 @@ def _load(path):
         "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
+        "pcgpu_buf_alloc": [_vp, _sz, ctypes.POINTER(_vp)],
+        "pcgpu_buf_free": [_vp, _vp],
+        "pcgpu_buf_write": [_vp, _vp, _sz, _vp, _sz],
+        "pcgpu_buf_read": [_vp, _vp, _sz, _vp, _sz],
+        "pcgpu_buf_zero": [_vp, _vp, _sz, _sz],
         "pcgpu_kzg_commit_open": [_vp, _vp, _vp, _sz, _vp, ctypes.c_uint32, _vp, _vp, _vp, _vp],
         "pcgpu_kzg_commit_open_batch": [_vp, _vp, _vp, _vp, _sz, _vp, ctypes.c_uint32, _vp, _vp, _vp, _vp],
         "pcgpu_lincode_hash_columns": [_vp, ctypes.c_int, _vp, _sz, _sz, ctypes.c_int, ctypes.c_uint32, _vp],
@@ -157,6 +162,66 @@ class Srs:
             pass
 
 
+class DeviceBuffer:
+    """`count` Fr elements (32 bytes each) on the engine's device; `ptr(i)` is the device pointer of element i, to be passed
+    with DEVICE_PTRS.  Freed on release() / garbage collection."""
+
+    def __init__(self, engine, count):
+        self.engine, self.count = engine, count
+        p = _vp()
+        engine._ck(engine.lib.pcgpu_buf_alloc(engine.ctx, max(count, 1) * 32, ctypes.byref(p)))
+        self.base = int(p.value)
+
+    def ptr(self, i=0):
+        return self.base + 32 * i
+
+    def write(self, arr, at=0):
+        arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+        if at + arr.shape[0] > self.count:
+            raise ValueError("write beyond the buffer")
+        self.engine._ck(self.engine.lib.pcgpu_buf_write(self.engine.ctx, _vp(self.base), 32 * at, _ptr(arr), arr.shape[0] * 32))
+
+    def read(self, at=0, count=None):
+        count = self.count - at if count is None else count
+        out = np.zeros((count, 4), dtype=np.uint64)
+        self.engine._ck(self.engine.lib.pcgpu_buf_read(self.engine.ctx, _vp(self.base), 32 * at, _ptr(out), count * 32))
+        return out
+
+    def zero(self, at=0, count=None):
+        count = self.count - at if count is None else count
+        self.engine._ck(self.engine.lib.pcgpu_buf_zero(self.engine.ctx, _vp(self.base), 32 * at, count * 32))
+
+    def release(self):
+        if getattr(self, "base", None) and getattr(self.engine, "ctx", None):
+            b, self.base = self.base, None
+            self.engine.lib.pcgpu_buf_free(self.engine.ctx, _vp(b))
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class IpaState:
+    """Device-resident state of one InnerProductArgPC::open halving loop; released by ipa_finish, by release() or when the
+    object is dropped (an exception between ipa_begin and ipa_finish therefore does not leak device memory)."""
+
+    def __init__(self, engine, handle, curve):
+        self.engine, self.handle, self.curve = engine, handle, curve
+
+    def release(self):
+        if self.handle is not None and getattr(self.engine, "ctx", None):
+            h, self.handle = self.handle, None
+            self.engine.lib.pcgpu_ipa_finish(self.engine.ctx, h, None, None)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class Engine:
     """One pcgpu context (one CUDA device, one stream).  `lib_path` exists so the host-emulation unit tests
     can drive the identical C ABI of tests/host_emul/libpcgpu_hostcheck.so; product code never passes it."""
@@ -184,6 +249,10 @@ class Engine:
     def _ck(self, rc):
         if rc:
             raise PcgpuError(rc, self.lib.pcgpu_strerror(rc).decode())
+
+    def buffer(self, count):
+        """zero-filled device buffer of `count` Fr elements"""
+        return DeviceBuffer(self, count)
 
     # ---- context ----
     def set_stream(self, cuda_stream):
@@ -482,21 +551,21 @@ class Engine:
         h = _vp()
         self._ck(self.lib.pcgpu_ipa_begin(self.ctx, curve, _ptr(comm_key_xy), n, _ptr(coeffs), coeffs.size // 4, _ptr(point), flags,
                                           ctypes.byref(h)))
-        return h
+        return IpaState(self, h, curve)
 
-    def ipa_round_lr(self, curve, state, h_prime_xy):
+    def ipa_round_lr(self, curve, state, h_prime_xy, with_inf=False):
         h_prime_xy = _u64(h_prime_xy)
         nq = fq_limbs(curve)
         l, r = np.zeros(2 * nq, dtype=np.uint64), np.zeros(2 * nq, dtype=np.uint64)
         li, ri = np.zeros(1, dtype=np.uint8), np.zeros(1, dtype=np.uint8)
-        self._ck(self.lib.pcgpu_ipa_round_lr(self.ctx, state, _ptr(h_prime_xy), _ptr(l), _ptr(li), _ptr(r), _ptr(ri)))
-        return l, r
+        self._ck(self.lib.pcgpu_ipa_round_lr(self.ctx, state.handle, _ptr(h_prime_xy), _ptr(l), _ptr(li), _ptr(r), _ptr(ri)))
+        return (l, int(li[0]), r, int(ri[0])) if with_inf else (l, r)
 
     def ipa_round_fold(self, state, challenge, challenge_inv):
-        self._ck(self.lib.pcgpu_ipa_round_fold(self.ctx, state, _ptr(_u64(challenge)), _ptr(_u64(challenge_inv))))
+        self._ck(self.lib.pcgpu_ipa_round_fold(self.ctx, state.handle, _ptr(_u64(challenge)), _ptr(_u64(challenge_inv))))
 
     def ipa_len(self, state):
-        return int(self.lib.pcgpu_ipa_len(state))
+        return int(self.lib.pcgpu_ipa_len(state.handle)) if state.handle is not None else 0
 
     def ipa_check_final_key(self, comm_key_srs, challenges):
         """InnerProductArgPC::check's linear-time step: cm_commit(comm_key, check_poly.compute_coeffs())."""
@@ -508,8 +577,10 @@ class Engine:
         return out, int(inf[0])
 
     def ipa_finish(self, curve, state):
+        """final_comm_key and c; releases the device state"""
         key, c = np.zeros(2 * fq_limbs(curve), dtype=np.uint64), np.zeros(4, dtype=np.uint64)
-        self._ck(self.lib.pcgpu_ipa_finish(self.ctx, state, _ptr(key), _ptr(c)))
+        h, state.handle = state.handle, None            # pcgpu_ipa_finish frees the state whatever it returns
+        self._ck(self.lib.pcgpu_ipa_finish(self.ctx, h, _ptr(key), _ptr(c)))
         return key, c
 
     # ---- KZG10 ----

@@ -4,6 +4,14 @@
 
 #include "impl.cuh"
 
+// Nothing unwinds across the C ABI: every entry point runs inside this guard (std::vector / std::thread / new can throw).
+template <class F>
+static int guarded(F f) {
+  try { return f(); }
+  catch (const std::bad_alloc &) { return PCGPU_E_OOM; }
+  catch (...) { return PCGPU_E_CUDA; }
+}
+
 PCGPU_INSTANTIATE(Bls12381, extern)
 PCGPU_INSTANTIATE(Bn254, extern)
 PCGPU_INSTANTIATE(Pallas, extern)
@@ -25,6 +33,7 @@ extern "C" const char *pcgpu_strerror(int code) {
 }
 
 extern "C" int pcgpu_init(int device, pcgpu_ctx **out) {
+  return guarded([&]() -> int {
   if (!out) return PCGPU_E_BADARG;
   *out = nullptr;
 #ifndef PCGPU_EMUL
@@ -49,6 +58,7 @@ extern "C" int pcgpu_init(int device, pcgpu_ctx **out) {
   if ((rc = rt::host_alloc_pinned(&ctx->h_pinned, PINNED_BYTES))) { rt::dev_free(ctx->d_slots); delete ctx; return rc; }
   *out = ctx;
   return PCGPU_OK;
+  });
 }
 
 extern "C" void pcgpu_destroy(pcgpu_ctx *ctx) {
@@ -73,13 +83,16 @@ extern "C" void pcgpu_destroy(pcgpu_ctx *ctx) {
 }
 
 extern "C" int pcgpu_set_stream(pcgpu_ctx *ctx, void *cuda_stream) {
+  return guarded([&]() -> int {
   if (!ctx) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->stream = cuda_stream ? (rt::stream_t)cuda_stream : ctx->own_stream;
   return PCGPU_OK;
+  });
 }
 
 extern "C" int pcgpu_profile_enable(pcgpu_ctx *ctx, int enable) {
+  return guarded([&]() -> int {
   if (!ctx) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
@@ -87,9 +100,11 @@ extern "C" int pcgpu_profile_enable(pcgpu_ctx *ctx, int enable) {
   ctx->prof.on = enable != 0;
   if (enable) ctx->prof.reset();
   return PCGPU_OK;
+  });
 }
 
 extern "C" int pcgpu_profile_get(pcgpu_ctx *ctx, int stage, double *ms, uint64_t *count) {
+  return guarded([&]() -> int {
   if (!ctx || stage < 0 || stage >= PROF_STAGES) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
@@ -97,10 +112,12 @@ extern "C" int pcgpu_profile_get(pcgpu_ctx *ctx, int stage, double *ms, uint64_t
   if (ms) *ms = ctx->prof.ms[stage];
   if (count) *count = ctx->prof.cnt[stage];
   return PCGPU_OK;
+  });
 }
 
 extern "C" int pcgpu_srs_register(pcgpu_ctx *ctx, int curve, const void *bases_xy, const uint8_t *inf, size_t n,
                                   uint32_t flags, pcgpu_srs **out) {
+  return guarded([&]() -> int {
   if (!ctx || !out || (n && !bases_xy) || n >= (1u << 26)) return PCGPU_E_BADARG;
   *out = nullptr;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -118,6 +135,7 @@ extern "C" int pcgpu_srs_register(pcgpu_ctx *ctx, int curve, const void *bases_x
   if (rc) { rt::dev_free(srs->d_tables); rt::dev_free(srs->d_folded); rt::dev_free(srs->d_comb); delete srs; return rc; }
   *out = srs;
   return PCGPU_OK;
+  });
 }
 
 extern "C" void pcgpu_srs_release(pcgpu_ctx *ctx, pcgpu_srs *srs) {
@@ -140,121 +158,150 @@ extern "C" int pcgpu_srs_curve(const pcgpu_srs *srs) { return srs ? srs->curve :
 
 extern "C" int pcgpu_msm(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n,
                          uint32_t flags, void *out_xy, uint8_t *out_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !srs || (n && !scalars) || !out_xy) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(srs->curve, return msm_impl<C>(ctx, srs, base_offset, scalars, n, flags, out_xy, out_inf, nullptr));
+  });
 }
 
 extern "C" int pcgpu_msm_partial(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n,
                                  uint32_t flags, void *out_xyzz) {
+  return guarded([&]() -> int {
   if (!ctx || !srs || (n && !scalars) || !out_xyzz) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(srs->curve, return msm_impl<C>(ctx, srs, base_offset, scalars, n, flags, nullptr, nullptr, out_xyzz));
+  });
 }
 
 extern "C" int pcgpu_g1_sum_xyzz(pcgpu_ctx *ctx, int curve, const void *xyzz, size_t count, void *out_xy, uint8_t *out_inf) {
+  return guarded([&]() -> int {
   if (!ctx || (count && !xyzz) || !out_xy) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return g1_sum_impl<C>(ctx, xyzz, count, out_xy, out_inf));
+  });
 }
 
 extern "C" int pcgpu_g1_fixed_base_mul(pcgpu_ctx *ctx, int curve, const void *base_xy, const void *scalars, size_t n,
                                        uint32_t flags, void *out_xy) {
+  return guarded([&]() -> int {
   if (!ctx || !base_xy || (n && (!scalars || !out_xy))) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return fixed_base_impl<C>(ctx, base_xy, scalars, n, flags, out_xy));
+  });
 }
 
 extern "C" int pcgpu_fr_from_mont(pcgpu_ctx *ctx, int curve, const void *in, void *out, size_t n, uint32_t flags) {
+  return guarded([&]() -> int {
   if (!ctx || (n && (!in || !out))) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return fr_from_mont_impl<C>(ctx, in, out, n, flags));
+  });
 }
 
 extern "C" int pcgpu_fr_axpy(pcgpu_ctx *ctx, int curve, void *y, const void *c, const void *x, size_t n, uint32_t flags) {
+  return guarded([&]() -> int {
   if (!ctx || !c || (n && (!y || !x))) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return fr_axpy_impl<C>(ctx, y, c, x, n, flags));
+  });
 }
 
 extern "C" int pcgpu_fr_div_linear(pcgpu_ctx *ctx, int curve, const void *p, size_t n, const void *z, void *q, void *rem,
                                    uint32_t flags) {
+  return guarded([&]() -> int {
   if (!ctx || !z || (n && !p) || (n > 1 && !q)) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return fr_div_impl<C>(ctx, p, n, z, q, rem, flags));
+  });
 }
 
 extern "C" int pcgpu_fr_inner_product(pcgpu_ctx *ctx, int curve, const void *a, const void *b, size_t n, void *out,
                                       uint32_t flags) {
+  return guarded([&]() -> int {
   if (!ctx || !out || (n && (!a || !b))) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return fr_ip_impl<C>(ctx, a, b, n, out, flags));
+  });
 }
 
 extern "C" int pcgpu_fr_row_mul(pcgpu_ctx *ctx, int curve, const void *v, const void *m, size_t rows, size_t cols, void *out,
                                 uint32_t flags) {
+  return guarded([&]() -> int {
   if (!ctx || (cols && !out) || (rows && cols && (!v || !m))) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return fr_row_mul_impl<C>(ctx, v, m, rows, cols, out, flags));
+  });
 }
 
 extern "C" int pcgpu_kzg_commit(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coeffs, size_t n,
                                 const pcgpu_srs *powers_of_gamma_g, const void *blind, size_t n_blind, uint32_t flags,
                                 void *out_xy, uint8_t *out_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !powers_of_g || (n && !coeffs) || (n_blind && !blind) || !out_xy) return PCGPU_E_BADARG;
   if (powers_of_gamma_g && powers_of_gamma_g->curve != powers_of_g->curve) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(powers_of_g->curve,
                  return kzg_commit_impl<C>(ctx, powers_of_g, coeffs, n, powers_of_gamma_g, blind, n_blind, flags, out_xy, out_inf));
+  });
 }
 
 extern "C" int pcgpu_kzg_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coeffs, size_t n, const void *z,
                               const pcgpu_srs *powers_of_gamma_g, const void *blind, size_t n_blind, uint32_t flags,
                               void *out_w_xy, uint8_t *out_w_inf, void *out_random_v) {
+  return guarded([&]() -> int {
   if (!ctx || !powers_of_g || !z || (n && !coeffs) || (n_blind && !blind) || !out_w_xy) return PCGPU_E_BADARG;
   if (powers_of_gamma_g && powers_of_gamma_g->curve != powers_of_g->curve) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(powers_of_g->curve, return kzg_open_impl<C>(ctx, powers_of_g, coeffs, n, z, powers_of_gamma_g, blind,
                                                              n_blind, flags, out_w_xy, out_w_inf, out_random_v));
+  });
 }
 
 extern "C" int pcgpu_selftest_field(pcgpu_ctx *ctx, int curve, uint64_t seed, size_t n, uint64_t *mismatches) {
+  return guarded([&]() -> int {
   if (!ctx || !mismatches) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return selftest_field_impl<C>(ctx, seed, n, mismatches));
+  });
 }
 
 extern "C" uint64_t pcgpu_launch_count(void) { return rt::launch_counter().load(); }
 
 extern "C" int pcgpu_ntt(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in, uint32_t logn, uint32_t flags, void *out) {
+  return guarded([&]() -> int {
   if (!ctx || !out || (n_in && !in)) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return ntt_impl<C>(ctx, in, n_in, logn, flags, out));
+  });
 }
 
 extern "C" int pcgpu_msm_batch(pcgpu_ctx *ctx, const pcgpu_srs *srs, const void *scalars, size_t n, size_t count, uint32_t flags,
                                void *out_xy, uint8_t *out_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !srs || (n && count && !scalars) || (count && !out_xy)) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(srs->curve, return msm_batch_impl<C>(ctx, srs, scalars, n, count, flags, out_xy, out_inf));
+  });
 }
 
 extern "C" int pcgpu_ipa_begin(pcgpu_ctx *ctx, int curve, const void *comm_key_xy, size_t n, const void *coeffs, size_t n_coeffs,
                                const void *point, uint32_t flags, pcgpu_ipa **out) {
+  return guarded([&]() -> int {
   if (!ctx || !out || !comm_key_xy || !point || n == 0 || (n & (n - 1)) || n_coeffs > n || (n_coeffs && !coeffs)) return PCGPU_E_BADARG;
   *out = nullptr;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -268,29 +315,35 @@ extern "C" int pcgpu_ipa_begin(pcgpu_ctx *ctx, int curve, const void *comm_key_x
     case PCGPU_PALLAS: rc = ipa_begin_impl<Pallas>(ctx, comm_key_xy, n, coeffs, n_coeffs, point, flags, st); break;
     default: rc = PCGPU_E_BADARG;
   }
-  if (rc) { rt::dev_free(st->d_key); rt::dev_free(st->d_coeffs); delete st; return rc; }
+  if (rc) { rt::dev_free(st->d_key); rt::dev_free(st->d_coeffs); rt::dev_free(st->d_w); delete st; return rc; }
   *out = st;
   return PCGPU_OK;
+  });
 }
 
 extern "C" int pcgpu_ipa_round_lr(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_prime_xy, void *out_l_xy, uint8_t *out_l_inf,
                                   void *out_r_xy, uint8_t *out_r_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !st || !h_prime_xy || !out_l_xy || !out_r_xy) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(st->curve, return ipa_round_lr_impl<C>(ctx, st, h_prime_xy, out_l_xy, out_l_inf, out_r_xy, out_r_inf));
+  });
 }
 
 extern "C" int pcgpu_ipa_round_fold(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *challenge, const void *challenge_inv) {
+  return guarded([&]() -> int {
   if (!ctx || !st || !challenge || !challenge_inv) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(st->curve, return ipa_round_fold_impl<C>(ctx, st, challenge, challenge_inv));
+  });
 }
 
 extern "C" size_t pcgpu_ipa_len(const pcgpu_ipa *st) { return st ? st->n : 0; }
 
 extern "C" int pcgpu_ipa_finish(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_key_xy, void *out_c) {
+  return guarded([&]() -> int {
   if (!ctx || !st) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
@@ -301,22 +354,26 @@ extern "C" int pcgpu_ipa_finish(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_k
     case PCGPU_PALLAS: rc = ipa_finish_impl<Pallas>(ctx, st, out_final_key_xy, out_c); break;
     default: rc = PCGPU_E_BADARG;
   }
-  rt::dev_free(st->d_key); rt::dev_free(st->d_coeffs);
+  rt::dev_free(st->d_key); rt::dev_free(st->d_coeffs); rt::dev_free(st->d_w);
   delete st;
   return rc;
+  });
 }
 
 extern "C" int pcgpu_measure_imad_peak(pcgpu_ctx *ctx, double *ops_per_s) {
+  return guarded([&]() -> int {
   if (!ctx || !ops_per_s) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   return measure_imad_peak_impl(ctx, ops_per_s);
+  });
 }
 
 enum { PCGPU_BATCH_WAYS = 4 };
 
 extern "C" int pcgpu_kzg_commit_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *const *coeffs, const size_t *n,
                                       size_t count, uint32_t flags, void *out_xy, uint8_t *out_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !powers_of_g || (count && (!coeffs || !n || !out_xy))) return PCGPU_E_BADARG;
   size_t ways = count < (size_t)PCGPU_BATCH_WAYS ? count : (size_t)PCGPU_BATCH_WAYS;
   {
@@ -344,14 +401,17 @@ extern "C" int pcgpu_kzg_commit_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of
   for (auto &t : th) t.join();
   for (int rc : rcs) if (rc) return rc;
   return PCGPU_OK;
+  });
 }
 
 extern "C" int pcgpu_ipa_check_final_key(pcgpu_ctx *ctx, const pcgpu_srs *comm_key, const void *challenges, uint32_t log_d,
                                          void *out_xy, uint8_t *out_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !comm_key || (log_d && !challenges) || !out_xy) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(comm_key->curve, return ipa_check_final_key_impl<C>(ctx, comm_key, challenges, log_d, out_xy, out_inf));
+  });
 }
 
 extern "C" int pcgpu_ntt_split(uint32_t logn, uint32_t *m1, uint32_t *m2) {
@@ -362,10 +422,12 @@ extern "C" int pcgpu_ntt_split(uint32_t logn, uint32_t *m1, uint32_t *m2) {
 
 extern "C" int pcgpu_ntt_pass(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, int which, size_t lo, size_t count,
                               const void *in, size_t n_in, void *out) {
+  return guarded([&]() -> int {
   if (!ctx || !out || (n_in && !in)) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return ntt_pass_impl<C>(ctx, logn, flags, which, lo, count, in, n_in, out));
+  });
 }
 
 extern "C" size_t pcgpu_g1_wire_size(int curve, uint32_t flags) {
@@ -380,31 +442,38 @@ extern "C" size_t pcgpu_g1_wire_size(int curve, uint32_t flags) {
 
 extern "C" int pcgpu_g1_serialize(pcgpu_ctx *ctx, int curve, const void *xy, const uint8_t *inf, size_t n, uint32_t flags,
                                   uint8_t *out_bytes) {
+  return guarded([&]() -> int {
   if (!ctx || (n && (!xy || !out_bytes))) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return g1_serialize_impl<C>(ctx, xy, inf, n, flags, out_bytes));
+  });
 }
 
 extern "C" int pcgpu_g1_deserialize(pcgpu_ctx *ctx, int curve, const uint8_t *bytes, size_t n, uint32_t flags, void *out_xy,
                                     uint8_t *out_inf, size_t *first_bad, int *reason) {
+  return guarded([&]() -> int {
   if (!ctx || (n && (!bytes || !out_xy || !out_inf))) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return g1_deserialize_impl<C>(ctx, bytes, n, flags, out_xy, out_inf, first_bad, reason));
+  });
 }
 
 extern "C" int pcgpu_fr_mul(pcgpu_ctx *ctx, int curve, const void *a, const void *b, void *out, size_t n, uint32_t flags) {
+  return guarded([&]() -> int {
   if (!ctx || (n && (!a || !b || !out))) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return fr_mul_impl<C>(ctx, a, b, out, n, flags));
+  });
 }
 
 // VariableBaseMSM::msm_bigint(bases, scalars) on bases that are not a registered key: the verifier-side combinations
 // (hyrax/mod.rs:501-504 over row_coms; kzg10/mod.rs:357-373; marlin/mod.rs:109-148).  Composes the public entry points.
 extern "C" int pcgpu_msm_bases(pcgpu_ctx *ctx, int curve, const void *bases_xy, const uint8_t *inf, const void *scalars, size_t n,
                                uint32_t flags, void *out_xy, uint8_t *out_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !out_xy || (n && (!bases_xy || !scalars)) || (flags & (PCGPU_DEVICE_PTRS | PCGPU_SRS_PRECOMPUTE | PCGPU_SRS_COMB)))
     return PCGPU_E_BADARG;
   pcgpu_srs *srs = nullptr;
@@ -413,28 +482,34 @@ extern "C" int pcgpu_msm_bases(pcgpu_ctx *ctx, int curve, const void *bases_xy, 
   rc = pcgpu_msm(ctx, srs, 0, scalars, n, flags, out_xy, out_inf);
   pcgpu_srs_release(ctx, srs);
   return rc;
+  });
 }
 
 extern "C" int pcgpu_ntt_batch(pcgpu_ctx *ctx, int curve, const void *in, size_t n_in, size_t count, uint32_t logn, uint32_t flags,
                                void *out) {
+  return guarded([&]() -> int {
   if (!ctx || (count && (!out || (n_in && !in)))) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return ntt_batch_impl<C>(ctx, in, n_in, count, logn, flags, out));
+  });
 }
 
 extern "C" int pcgpu_ntt_pass1_peer(pcgpu_ctx *ctx, int curve, uint32_t logn, uint32_t flags, size_t lo, size_t count, const void *in,
                                     size_t n_in, void *const *dst, uint32_t world) {
+  return guarded([&]() -> int {
   if (!ctx || !dst || (n_in && !in)) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return ntt_pass1_peer_impl<C>(ctx, logn, flags, lo, count, in, n_in, dst, world));
+  });
 }
 
 // ---- multi-GPU over NVLink peer memory (peer.cuh) ---------------------------------------------------------------------
 extern "C" size_t pcgpu_peer_window_bytes(void) { return (size_t)PEER_WINDOW_BYTES; }
 
 extern "C" int pcgpu_peer_alloc(pcgpu_ctx *ctx, size_t bytes, void **out_ptr, uint8_t *handle) {
+  return guarded([&]() -> int {
   if (!ctx || !out_ptr || !handle || bytes == 0) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
@@ -454,9 +529,11 @@ extern "C" int pcgpu_peer_alloc(pcgpu_ctx *ctx, size_t bytes, void **out_ptr, ui
 #endif
   *out_ptr = p;
   return PCGPU_OK;
+  });
 }
 
 extern "C" int pcgpu_peer_open(pcgpu_ctx *ctx, const uint8_t *handle, void **out_ptr) {
+  return guarded([&]() -> int {
   if (!ctx || !handle || !out_ptr) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
@@ -470,9 +547,11 @@ extern "C" int pcgpu_peer_open(pcgpu_ctx *ctx, const uint8_t *handle, void **out
   memcpy(out_ptr, handle, sizeof(void *));
 #endif
   return PCGPU_OK;
+  });
 }
 
 extern "C" int pcgpu_peer_close(pcgpu_ctx *ctx, void *mapped) {
+  return guarded([&]() -> int {
   if (!ctx || !mapped) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
@@ -481,9 +560,11 @@ extern "C" int pcgpu_peer_close(pcgpu_ctx *ctx, void *mapped) {
   if (cudaIpcCloseMemHandle(mapped) != cudaSuccess) return PCGPU_E_CUDA;
 #endif
   return PCGPU_OK;
+  });
 }
 
 extern "C" int pcgpu_peer_free(pcgpu_ctx *ctx, void *ptr) {
+  return guarded([&]() -> int {
   if (!ctx || !ptr) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
@@ -492,6 +573,7 @@ extern "C" int pcgpu_peer_free(pcgpu_ctx *ctx, void *ptr) {
 #endif
   rt::dev_free(ptr);
   return PCGPU_OK;
+  });
 }
 
 static int peer_args_ok(void *const *win, uint32_t rank, uint32_t world) {
@@ -501,6 +583,7 @@ static int peer_args_ok(void *const *win, uint32_t rank, uint32_t world) {
 }
 
 extern "C" int pcgpu_peer_signal(pcgpu_ctx *ctx, void *const *win, uint32_t rank, uint32_t world, uint32_t channel, uint64_t epoch) {
+  return guarded([&]() -> int {
   if (!ctx || !peer_args_ok(win, rank, world) || channel >= 8) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
@@ -511,9 +594,11 @@ extern "C" int pcgpu_peer_signal(pcgpu_ctx *ctx, void *const *win, uint32_t rank
   int rc = rt::launch<32>(b, world, ctx->stream);
   if (rc) return rc;
   return rt::stream_sync(ctx->stream);
+  });
 }
 
 extern "C" int pcgpu_peer_wait(pcgpu_ctx *ctx, void *local_win, uint32_t world, uint32_t channel, uint64_t epoch) {
+  return guarded([&]() -> int {
   if (!ctx || !local_win || world == 0 || world > (uint32_t)PEER_MAX_WORLD || channel >= 8) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
@@ -526,41 +611,50 @@ extern "C" int pcgpu_peer_wait(pcgpu_ctx *ctx, void *local_win, uint32_t world, 
   if ((rc = rt::copy_d2h(&t, d_timeout, 4, st))) return rc;
   if ((rc = rt::stream_sync(st))) return rc;
   return t ? PCGPU_E_PEER : PCGPU_OK;
+  });
 }
 
 extern "C" int pcgpu_msm_peer(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, const void *scalars, size_t n, uint32_t flags,
                               void *const *win, uint32_t rank, uint32_t world, uint64_t epoch, void *out_xy, uint8_t *out_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !srs || (n && !scalars) || !out_xy || !peer_args_ok(win, rank, world) || epoch == 0) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(srs->curve, return msm_peer_impl<C>(ctx, srs, base_offset, scalars, n, flags, win, rank, world, epoch, out_xy, out_inf));
+  });
 }
 
 // ---- linear-code commitments (hash.cuh) ---------------------------------------------------------------------------------
 extern "C" int pcgpu_lincode_hash_columns(pcgpu_ctx *ctx, int curve, const void *ext_mat, size_t n_rows, size_t n_cols, int hash,
                                           uint32_t flags, uint8_t *out_leaves) {
+  return guarded([&]() -> int {
   if (!ctx || (n_cols && !out_leaves) || (n_rows && n_cols && !ext_mat)) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return lincode_hash_columns_impl<C>(ctx, ext_mat, n_rows, n_cols, hash, flags, out_leaves));
+  });
 }
 
 extern "C" int pcgpu_merkle_tree(pcgpu_ctx *ctx, const uint8_t *leaves, size_t n_leaves, uint32_t flags, uint8_t *out_nodes,
                                  uint8_t *out_root) {
+  return guarded([&]() -> int {
   if (!ctx || !leaves) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   return merkle_tree_impl(ctx, leaves, n_leaves, flags, out_nodes, out_root);
+  });
 }
 
 extern "C" int pcgpu_lincode_commit(pcgpu_ctx *ctx, int curve, const void *mat, size_t n_rows, size_t n_cols, uint32_t log_ext_cols,
                                     int hash, uint32_t flags, void *out_ext_mat, uint8_t *out_leaves, uint8_t *out_nodes,
                                     uint8_t *out_root) {
+  return guarded([&]() -> int {
   if (!ctx || (n_rows && n_cols && !mat)) return PCGPU_E_BADARG;
   std::lock_guard<std::mutex> lk(ctx->mu);
   SET_DEVICE(ctx);
   DISPATCH_CURVE(curve, return lincode_commit_impl<C>(ctx, mat, n_rows, n_cols, log_ext_cols, hash, flags, out_ext_mat, out_leaves,
                                                       out_nodes, out_root));
+  });
 }
 
 // ---- fused KZG10 commit + open ------------------------------------------------------------------------------------------
@@ -586,10 +680,12 @@ static int commit_open_pair(pcgpu_ctx *a, pcgpu_ctx *b, const pcgpu_srs *pg, con
 
 extern "C" int pcgpu_kzg_commit_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *coeffs, size_t n, const void *z,
                                      uint32_t flags, void *out_comm_xy, uint8_t *out_comm_inf, void *out_w_xy, uint8_t *out_w_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !powers_of_g || !z || (n && !coeffs) || !out_comm_xy || !out_w_xy) return PCGPU_E_BADARG;
   int rc = ensure_siblings(ctx, 1);
   if (rc) return rc;
   return commit_open_pair(ctx, ctx->siblings[0], powers_of_g, coeffs, n, z, flags, out_comm_xy, out_comm_inf, out_w_xy, out_w_inf);
+  });
 }
 
 enum { PCGPU_COMMIT_OPEN_WAYS = 2 };   // polynomials in flight (two MSM pipelines each)
@@ -597,6 +693,7 @@ enum { PCGPU_COMMIT_OPEN_WAYS = 2 };   // polynomials in flight (two MSM pipelin
 extern "C" int pcgpu_kzg_commit_open_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *const *coeffs, const size_t *n,
                                            size_t count, const void *z, uint32_t flags, void *out_comm_xy, uint8_t *out_comm_inf,
                                            void *out_w_xy, uint8_t *out_w_inf) {
+  return guarded([&]() -> int {
   if (!ctx || !powers_of_g || !z || (count && (!coeffs || !n || !out_comm_xy || !out_w_xy))) return PCGPU_E_BADARG;
   const size_t ways = count < (size_t)PCGPU_COMMIT_OPEN_WAYS ? count : (size_t)PCGPU_COMMIT_OPEN_WAYS;
   if (ways == 0) return PCGPU_OK;
@@ -620,4 +717,57 @@ extern "C" int pcgpu_kzg_commit_open_batch(pcgpu_ctx *ctx, const pcgpu_srs *powe
   } catch (...) { return PCGPU_E_OOM; }
   for (size_t w = 0; w < ways; w++) if (rcs[w]) return rcs[w];
   return PCGPU_OK;
+  });
+}
+
+// ---- device buffers for callers that keep polynomials on the GPU across calls (PCGPU_DEVICE_PTRS arguments) ------------------
+extern "C" int pcgpu_buf_alloc(pcgpu_ctx *ctx, size_t bytes, void **out) {
+  return guarded([&]() -> int {
+    if (!ctx || !out) return PCGPU_E_BADARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SET_DEVICE(ctx);
+    void *p = nullptr;
+    int rc = rt::dev_malloc(&p, bytes);
+    if (rc) return rc;
+    if ((rc = rt::dev_memset(p, 0, bytes ? bytes : 1, ctx->stream)) || (rc = rt::stream_sync(ctx->stream))) { rt::dev_free(p); return rc; }
+    *out = p;
+    return PCGPU_OK;
+  });
+}
+extern "C" int pcgpu_buf_free(pcgpu_ctx *ctx, void *p) {
+  return guarded([&]() -> int {
+    if (!ctx) return PCGPU_E_BADARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SET_DEVICE(ctx);
+    int rc = rt::stream_sync(ctx->stream);
+    rt::dev_free(p);
+    return rc;
+  });
+}
+extern "C" int pcgpu_buf_write(pcgpu_ctx *ctx, void *dst, size_t dst_off, const void *src, size_t bytes) {
+  return guarded([&]() -> int {
+    if (!ctx || (bytes && (!dst || !src))) return PCGPU_E_BADARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SET_DEVICE(ctx);
+    int rc = bytes ? rt::copy_h2d((char *)dst + dst_off, src, bytes, ctx->stream) : PCGPU_OK;
+    return rc ? rc : rt::stream_sync(ctx->stream);
+  });
+}
+extern "C" int pcgpu_buf_read(pcgpu_ctx *ctx, const void *src, size_t src_off, void *dst, size_t bytes) {
+  return guarded([&]() -> int {
+    if (!ctx || (bytes && (!dst || !src))) return PCGPU_E_BADARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SET_DEVICE(ctx);
+    int rc = bytes ? rt::copy_d2h(dst, (const char *)src + src_off, bytes, ctx->stream) : PCGPU_OK;
+    return rc ? rc : rt::stream_sync(ctx->stream);
+  });
+}
+extern "C" int pcgpu_buf_zero(pcgpu_ctx *ctx, void *dst, size_t dst_off, size_t bytes) {
+  return guarded([&]() -> int {
+    if (!ctx || (bytes && !dst)) return PCGPU_E_BADARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SET_DEVICE(ctx);
+    int rc = bytes ? rt::dev_memset((char *)dst + dst_off, 0, bytes, ctx->stream) : PCGPU_OK;
+    return rc ? rc : rt::stream_sync(ctx->stream);
+  });
 }

@@ -131,9 +131,16 @@ int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, siz
     if (flags & PCGPU_DEVICE_PTRS) rc = rt::copy_d2d(srs->d_tables, bases, psz * n, st);
     else rc = rt::copy_h2d(srs->d_tables, bases, psz * n, st);
     if (rc) return rc;
-    if (inf && !(flags & PCGPU_DEVICE_PTRS))
-      for (size_t i = 0; i < n; i++)
-        if (inf[i] && (rc = rt::dev_memset((char *)srs->d_tables + psz * i, 0, psz, st))) return rc;
+    if (inf) {   // identity bases become the device's (0, 0) encoding -- one kernel, for host and device flag arrays alike
+      const uint8_t *d_inf = inf;
+      if (!(flags & PCGPU_DEVICE_PTRS)) {
+        if ((rc = ctx->stage.reserve(rt::Arena::pad(n) + 4096))) return rc;
+        uint8_t *t = ctx->stage.take<uint8_t>(n);
+        if ((rc = rt::copy_h2d(t, inf, n, st))) return rc;
+        d_inf = t;
+      }
+      if ((rc = rt::launch<256>(SrsZeroIdentityBody{(uint32_t *)srs->d_tables, d_inf, (uint32_t)(psz / 4)}, n, st))) return rc;
+    }
     if (groups > 1 && (rc = srs_build_groups<C>((const Affine<C> *)srs->d_tables, (uint32_t *)srs->d_folded, n, c, groups, st))) return rc;
     if (flags & PCGPU_SRS_COMB) {
       CombGeom cg; memset(&cg, 0, sizeof cg);
@@ -823,10 +830,35 @@ int kzg_commit_open_impl(pcgpu_ctx *ctx, pcgpu_ctx *sib, const pcgpu_srs *pg, co
 // ---------------------------------------------------------------------------------------------
 struct pcgpu_ipa {
   int curve; size_t n0, n;
-  void *d_key;        // n0 affine points (folded in place)
+  void *d_key;        // n0 affine points (folded in place until the key is frozen)
   uint32_t *d_coeffs, *d_z, *d_scr;  // n0 Fr each; scratch for inner products
   pcgpu_srs view;     // non-owning SRS view over d_key for the MSM pipeline
+  size_t frozen_m;    // 0: the key is folded explicitly; else the key stays at frozen_m points (ipa.cuh, "late rounds")
+  uint32_t *d_w;      // frozen_m weights, then 2 * frozen_m MSM scalars (allocated at the freeze)
 };
+
+template <class C>
+static int ensure_pow2(pcgpu_ctx *ctx) {
+  using QP = typename C::Fq;
+  if (ctx->d_pow2[C::ID]) return PCGPU_OK;
+  int rc;
+  if ((rc = rt::dev_malloc((void **)&ctx->d_pow2[C::ID], (size_t)(64 * QP::N + 1) * QP::N * 4))) return rc;
+  return rt::launch<32>(Pow2TableBody<QP>{ctx->d_pow2[C::ID]}, 1, ctx->stream);
+}
+
+// freeze the key at its current length (<= SMALL_MAX_N): weights start at one
+template <class C>
+static int ipa_freeze(pcgpu_ctx *ctx, pcgpu_ipa *st) {
+  using R = typename C::Fr;
+  int rc;
+  if ((rc = rt::dev_malloc((void **)&st->d_w, 3 * st->n * 32 + 64))) return rc;
+  st->frozen_m = st->n;
+  return rt::launch<128>(FrFillOneBody<R>{st->d_w}, st->n, ctx->stream);
+}
+inline bool ipa_freeze_enabled() {
+  const char *e = getenv("PCGPU_IPA_FREEZE");
+  return msm_small_enabled() && !(e && e[0] == '0');
+}
 
 template <class C>
 int ipa_begin_impl(pcgpu_ctx *ctx, const void *key_xy, size_t n, const void *coeffs, size_t n_coeffs, const void *point,
@@ -836,7 +868,8 @@ int ipa_begin_impl(pcgpu_ctx *ctx, const void *key_xy, size_t n, const void *coe
   int rc;
   bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
   st->curve = C::ID; st->n0 = st->n = n;
-  st->d_key = nullptr; st->d_coeffs = nullptr;
+  st->d_key = nullptr; st->d_coeffs = nullptr; st->frozen_m = 0; st->d_w = nullptr;
+  if ((rc = ensure_pow2<C>(ctx))) return rc;
   if ((rc = rt::dev_malloc(&st->d_key, n * sizeof(Affine<C>)))) return rc;
   if ((rc = rt::dev_malloc((void **)&st->d_coeffs, (2 * n + IP_THREADS + IP_THREADS / IP_BLOCK + 32) * 32))) return rc;
   st->d_z = st->d_coeffs + 8 * n; st->d_scr = st->d_z + 8 * n;
@@ -848,6 +881,7 @@ int ipa_begin_impl(pcgpu_ctx *ctx, const void *key_xy, size_t n, const void *coe
   if ((rc = rt::launch<128>(FrPowersBody<R>{d_pt, st->d_z}, n, s))) return rc;
   st->view.curve = C::ID; st->view.n = n; st->view.c = 0; st->view.groups = 1; st->view.d_tables = st->d_key; st->view.d_folded = nullptr;
   st->view.d_comb = nullptr; st->view.comb_c = 0;
+  if (n <= SMALL_MAX_N && n > 1 && ipa_freeze_enabled() && (rc = ipa_freeze<C>(ctx, st))) return rc;
   return rt::stream_sync(s);
 }
 
@@ -862,6 +896,23 @@ int ipa_round_lr_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_prime_xy, voi
   const uint32_t *cl = st->d_coeffs, *cr = st->d_coeffs + 8 * m, *zl = st->d_z, *zr = st->d_z + 8 * m;
   uint32_t *d_ip = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 6);
   uint64_t ip_m[2][4], ip_c[2][4];
+  if (st->frozen_m) {
+    // frozen key: both commitments are frozen_m-term MSMs over the same points, scalars expanded on the device
+    const size_t M = st->frozen_m;
+    uint32_t *d_h = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 12);
+    uint32_t *s_l = st->d_w + 8 * M, *s_r = s_l + 8 * M;
+    if ((rc = fr_inner_product<R>(cr, zl, m, d_ip, st->d_scr, s))) return rc;
+    if ((rc = fr_inner_product<R>(cl, zr, m, d_ip + 8, st->d_scr, s))) return rc;
+    if ((rc = rt::copy_h2d(d_h, h_prime_xy, sizeof(Affine<C>), s))) return rc;
+    if ((rc = rt::launch<128>(IpaFrozenScalarsBody<R>{st->d_w, st->d_coeffs, (uint32_t)st->n, s_l, s_r}, M, s))) return rc;
+    const Affine<C> *key = (const Affine<C> *)st->d_key;
+    MsmSmallProblem<C> pr[2] = {{key, s_l, (const Affine<C> *)d_h, d_ip, (uint32_t)M}, {key, s_r, (const Affine<C> *)d_h, d_ip + 8, (uint32_t)M}};
+    host::HXYZZ<C> lr[2];
+    if ((rc = msm_small_to_host<C>(ctx, pr, 2, true, lr))) return rc;
+    host::to_affine<C>(lr[0], out_l_xy, out_l_inf);
+    host::to_affine<C>(lr[1], out_r_xy, out_r_inf);
+    return PCGPU_OK;
+  }
   if (m < SMALL_MAX_N && msm_small_enabled()) {
     // late rounds: both commitments, each with its  + h' * <.,.>  term, in ONE launch; the inner products never leave HBM
     uint32_t *d_h = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 12);   // 3 slots, clear of d_ip / d_ch
@@ -908,6 +959,11 @@ int ipa_round_fold_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *challenge, co
   if ((rc = rt::copy_h2d(d_chi, challenge_inv, 32, s))) return rc;
   if ((rc = rt::launch<256>(FrAxpyBody<R>{st->d_coeffs, d_chi, st->d_coeffs + 8 * m}, m, s))) return rc;  // :691-693
   if ((rc = rt::launch<256>(FrAxpyBody<R>{st->d_z, d_ch, st->d_z + 8 * m}, m, s))) return rc;              // :695-697
+  if (st->frozen_m) {   // the key's fold is a multiplication of the weights (ipa.cuh)
+    if ((rc = rt::launch<128>(IpaFrozenWeightBody<R>{st->d_w, d_ch, (uint32_t)st->n}, st->frozen_m, s))) return rc;
+    st->n = m;
+    return rt::stream_sync(s);
+  }
   uint64_t canon[4];
   host::fr_from_mont_host<R>(challenge, canon);
   host::GlvSplit gs;
@@ -919,14 +975,15 @@ int ipa_round_fold_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *challenge, co
   if (gs.ok) {
     G1FoldGlvBody<C> gb; gb.key = (Affine<C> *)st->d_key; gb.m = (uint32_t)m;
     memcpy(gb.k1, gs.k1, sizeof gb.k1); memcpy(gb.k2, gs.k2, sizeof gb.k2);
-    gb.neg1 = gs.neg1; gb.neg2 = gs.neg2; gb.nbits = gs.nbits;
+    gb.neg1 = gs.neg1; gb.neg2 = gs.neg2; gb.nbits = gs.nbits; gb.pow2 = ctx->d_pow2[C::ID];
     if ((rc = rt::launch<128>(gb, m, s))) return rc;                                                        // :699-707
   } else {
     G1FoldBody<C> fb; fb.key = (Affine<C> *)st->d_key; fb.m = (uint32_t)m;
-    memcpy(fb.chal, canon, 32);
+    memcpy(fb.chal, canon, 32); fb.pow2 = ctx->d_pow2[C::ID];
     if ((rc = rt::launch<128>(fb, m, s))) return rc;                                                        // :699-707
   }
   st->n = m; st->view.n = m;
+  if (m <= SMALL_MAX_N && m > 1 && ipa_freeze_enabled() && (rc = ipa_freeze<C>(ctx, st))) return rc;
   return rt::stream_sync(s);
 }
 
@@ -934,7 +991,13 @@ template <class C>
 int ipa_finish_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_key_xy, void *out_c) {
   rt::stream_t s = ctx->stream;
   int rc;
-  if (out_final_key_xy && (rc = rt::copy_d2h(out_final_key_xy, st->d_key, sizeof(Affine<C>), s))) return rc;
+  if (out_final_key_xy && st->frozen_m) {   // final_comm_key = sum_j w[j] B[j]
+    MsmSmallProblem<C> pr{(const Affine<C> *)st->d_key, st->d_w, nullptr, nullptr, (uint32_t)st->frozen_m};
+    host::HXYZZ<C> k;
+    if ((rc = msm_small_to_host<C>(ctx, &pr, 1, true, &k))) return rc;
+    uint8_t inf = 0;
+    host::to_affine<C>(k, out_final_key_xy, &inf);
+  } else if (out_final_key_xy && (rc = rt::copy_d2h(out_final_key_xy, st->d_key, sizeof(Affine<C>), s))) return rc;
   if (out_c && (rc = rt::copy_d2h(out_c, st->d_coeffs, 32, s))) return rc;
   return rt::stream_sync(s);
 }

@@ -22,9 +22,23 @@ struct FrPowersBody {
 };
 
 // key[i] = affine(key[i] + chal * key[i + m])   -- k_l += k_r.mul(chal); normalize_batch  (:699-707)
+// projective -> affine with the binary-GCD inverse (fp_inv_gcd runs on the ALU pipe, which idles while the ladders of the
+// other warps saturate the integer-multiply pipe; the Fermat inverse of xyzz_to_affine costs ~380 more multiplications per point)
+template <class C>
+PCGPU_DEV Affine<C> xyzz_to_affine_gcd(const XYZZ<C> &p, const uint32_t *pow2) {
+  using Q = typename C::Fq;
+  if (p.is_inf()) return Affine<C>::inf();
+  Fp<Q> inv = fp_inv_gcd<Q>(fp_mul<Q>(p.zz, p.zzz), pow2);
+  Affine<C> a;
+  a.x = fp_mul<Q>(p.x, fp_mul<Q>(inv, p.zzz));
+  a.y = fp_mul<Q>(p.y, fp_mul<Q>(inv, p.zz));
+  return a;
+}
+
 template <class C>
 struct G1FoldBody {
   Affine<C> *key; uint32_t m; uint32_t chal[8];  // canonical scalar, same for every point
+  const uint32_t *pow2;
   PCGPU_KERNEL_DEV void operator()(size_t i) const {
     Affine<C> r = load_affine<C>(key + m + i);
     XYZZ<C> acc = XYZZ<C>::inf();
@@ -34,7 +48,7 @@ struct G1FoldBody {
     }
     Affine<C> l = load_affine<C>(key + i);
     xyzz_madd<C>(acc, l, false);
-    key[i] = xyzz_to_affine<C>(acc);
+    key[i] = xyzz_to_affine_gcd<C>(acc, pow2);
   }
 };
 
@@ -45,6 +59,7 @@ struct G1FoldBody {
 template <class C>
 struct G1FoldGlvBody {
   Affine<C> *key; uint32_t m; uint32_t k1[5], k2[5]; uint32_t neg1, neg2, nbits;
+  const uint32_t *pow2;
   PCGPU_KERNEL_DEV void operator()(size_t i) const {
     using Q = typename C::Fq;
     Affine<C> r = load_affine<C>(key + m + i);
@@ -66,8 +81,43 @@ struct G1FoldGlvBody {
       else if (s == 3) xyzz_add<C>(acc, t);
     }
     xyzz_madd<C>(acc, l, false);
-    key[i] = xyzz_to_affine<C>(acc);
+    key[i] = xyzz_to_affine_gcd<C>(acc, pow2);
   }
+};
+
+// ---- late rounds on a FROZEN key ------------------------------------------------------------------------------------------
+// Once the key has been folded down to M <= SMALL_MAX_N points it is not folded any further.  The key of a later round of
+// logical size n_t is  key_t[i] = sum_{j = i (mod n_t)} w[j] * B[j]  over the frozen points B, where w[j] is the product of the
+// round challenges selected by the bits of j above log2(n_t) (the first challenge after the freeze on the top bit -- the
+// coefficient structure of SuccinctCheckPolynomial, ipa_pc/data_structures.rs:204-220).  Hence
+//   l_t = cm_commit(key_l, coeffs_r) = sum_j [ (j mod n_t) <  n_t/2 ] w[j] coeffs[(j mod n_t) + n_t/2] * B[j]
+//   r_t = cm_commit(key_r, coeffs_l) = sum_j [ (j mod n_t) >= n_t/2 ] w[j] coeffs[(j mod n_t) - n_t/2] * B[j]
+// are two M-term MSMs that run in ONE launch of the small-MSM kernel, the fold of the key (ipa_pc/mod.rs:699-707) becomes
+// M field multiplications on w, and final_comm_key = sum_j w[j] B[j].  Same group elements as the reference's explicit
+// folds; what disappears are the 128-step scalar-multiplication ladders of the twelve latency-bound late rounds.
+template <class R>
+struct IpaFrozenScalarsBody {   // s_l[j], s_r[j] (Montgomery) from w, coeffs and the logical size n_t
+  const uint32_t *w, *coeffs; uint32_t n_t; uint32_t *s_l, *s_r;
+  PCGPU_KERNEL_DEV void operator()(size_t j) const {
+    const uint32_t i = (uint32_t)j & (n_t - 1), half = n_t >> 1;
+    const Fp<R> wj = load_fr<R>(w, j);
+    const bool left = i < half;
+    const Fp<R> v = fp_mul<R>(wj, load_fr<R>(coeffs, left ? i + half : i - half));
+    store_fr<R>(s_l, j, left ? v : Fp<R>::zero());
+    store_fr<R>(s_r, j, left ? Fp<R>::zero() : v);
+  }
+};
+template <class R>
+struct IpaFrozenWeightBody {    // the fold of a frozen key: w[j] *= chal for the j in the right half of their period n_t
+  uint32_t *w; const uint32_t *chal; uint32_t n_t;
+  PCGPU_KERNEL_DEV void operator()(size_t j) const {
+    if (((uint32_t)j & (n_t - 1)) >= (n_t >> 1)) store_fr<R>(w, j, fp_mul<R>(load_fr<R>(w, j), load_fr<R>(chal, 0)));
+  }
+};
+template <class R>
+struct FrFillOneBody {
+  uint32_t *out;
+  PCGPU_KERNEL_DEV void operator()(size_t j) const { store_fr<R>(out, j, Fp<R>::one()); }
 };
 
 // SuccinctCheckPolynomial::compute_coeffs (ipa_pc/data_structures.rs:204-220): coeffs[idx] = product of challenge_i over

@@ -201,33 +201,41 @@ struct ScanApplyBody {
   }
 };
 
-// One-launch variant for inputs up to SCAN_BLOCK_MAX elements (every histogram of a window-folded MSM): a single block,
-// each thread scans a contiguous slice, the slice totals are scanned in shared memory.
-enum { SCAN_BLOCK = 1024, SCAN_BLOCK_MAX = 1 << 17 };
+// One-launch variant for inputs up to SCAN_BLOCK_MAX elements (every histogram of a window-folded MSM): a single block walks
+// the input in tiles of SCAN_BLOCK * SCAN_PER elements -- coalesced loads (thread t owns SCAN_PER consecutive elements of the
+// tile), a shared-memory scan of the per-thread sums, a running carry from tile to tile.
+enum { SCAN_BLOCK = 1024, SCAN_PER = 8, SCAN_BLOCK_MAX = 1 << 17 };
 struct ScanBlockBody {
   const uint32_t *in; size_t n; uint32_t *out;
   PCGPU_KERNEL_DEV void operator()(size_t, uint32_t *smem) const {
-    const size_t per = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    PCGPU_BLOCK_FOR(t, SCAN_BLOCK) {
-      size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
-      uint32_t sum = 0;
-      for (size_t i = lo; i < hi; i++) sum += in[i];
-      smem[t] = sum;
-    }
+    uint32_t *a = smem, *b = smem + SCAN_BLOCK, *carry = smem + 2 * SCAN_BLOCK;
+    PCGPU_BLOCK_FOR(t, 1) { carry[0] = 0; }
     PCGPU_BLOCK_SYNC();
-    // Hillis-Steele inclusive scan of the SCAN_BLOCK slice totals (double buffer)
-    uint32_t *a = smem, *b = smem + SCAN_BLOCK;
-    for (uint32_t d = 1; d < SCAN_BLOCK; d <<= 1) {
-      PCGPU_BLOCK_FOR(t, SCAN_BLOCK) { b[t] = a[t] + (t >= d ? a[t - d] : 0u); }
+    const size_t tile = (size_t)SCAN_BLOCK * SCAN_PER;
+    for (size_t base = 0; base < n; base += tile) {
+      PCGPU_BLOCK_FOR(t, SCAN_BLOCK) {
+        const size_t lo = base + (size_t)t * SCAN_PER;
+        uint32_t sum = 0;
+        for (uint32_t k = 0; k < SCAN_PER; k++) if (lo + k < n) sum += in[lo + k];
+        a[t] = sum;
+      }
       PCGPU_BLOCK_SYNC();
-      uint32_t *tmp = a; a = b; b = tmp;
+      uint32_t *x = a, *y = b;
+      for (uint32_t d = 1; d < SCAN_BLOCK; d <<= 1) {      // Hillis-Steele inclusive scan of the per-thread sums
+        PCGPU_BLOCK_FOR(t, SCAN_BLOCK) { y[t] = x[t] + (t >= d ? x[t - d] : 0u); }
+        PCGPU_BLOCK_SYNC();
+        uint32_t *tmp = x; x = y; y = tmp;
+      }
+      PCGPU_BLOCK_FOR(t, SCAN_BLOCK) {
+        const size_t lo = base + (size_t)t * SCAN_PER;
+        uint32_t run = carry[0] + (t ? x[t - 1] : 0u);
+        for (uint32_t k = 0; k < SCAN_PER; k++) if (lo + k < n) { uint32_t v = in[lo + k]; out[lo + k] = run; run += v; }
+      }
+      PCGPU_BLOCK_SYNC();
+      PCGPU_BLOCK_FOR(t, 1) { carry[0] += x[SCAN_BLOCK - 1]; }
+      PCGPU_BLOCK_SYNC();
     }
-    PCGPU_BLOCK_FOR(t, SCAN_BLOCK) {
-      size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
-      uint32_t run = t ? a[t - 1] : 0u;
-      for (size_t i = lo; i < hi; i++) { uint32_t v = in[i]; out[i] = run; run += v; }
-      if (t == SCAN_BLOCK - 1) out[n] = a[SCAN_BLOCK - 1];
-    }
+    PCGPU_BLOCK_FOR(t, 1) { out[n] = carry[0]; }
   }
 };
 
@@ -236,7 +244,7 @@ inline size_t scan_scratch_words(size_t n) { return (n + SCAN_CHUNK - 1) / SCAN_
 inline int exclusive_scan_u32(const uint32_t *in, size_t n, uint32_t *out, uint32_t *scratch, rt::stream_t st) {
   size_t m = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
   if (m == 0) { return rt::dev_memset(out, 0, sizeof(uint32_t), st); }
-  if (n <= SCAN_BLOCK_MAX) return rt::launch_blocks<SCAN_BLOCK>(ScanBlockBody{in, n, out}, 1, 2 * SCAN_BLOCK * sizeof(uint32_t), st);
+  if (n <= SCAN_BLOCK_MAX) return rt::launch_blocks<SCAN_BLOCK>(ScanBlockBody{in, n, out}, 1, (2 * SCAN_BLOCK + 4) * sizeof(uint32_t), st);
   int rc;
   if ((rc = rt::launch<128>(ScanChunkSumBody{in, n, scratch}, m, st))) return rc;
   if ((rc = rt::launch<32>(ScanPartialsBody{scratch, m}, 1, st))) return rc;

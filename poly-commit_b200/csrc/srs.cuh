@@ -18,10 +18,18 @@ enum : size_t { SRS_PRECOMPUTE_MIN_N = 1u << 12 };
 inline uint32_t srs_precompute_window(size_t n) {
   if (const char *e = getenv("PCGPU_SRS_C")) { int v = atoi(e); if (v >= 8 && v <= 22) return (uint32_t)v; }   // tuning knob
   uint32_t lg = ilog2_floor(n ? n : 1);
-  if (lg >= 18) return 17;   // 255 / 17 = 15 windows exactly (load_scalar halves the scalar range, so no 16th carry window)
+  if (lg >= 18) return 16;   // c = 17 (15 windows) measured equal on the pair rounds and slower in scan / reduce (2^16 buckets): profiles/r02_msm_ab_*
   if (lg >= 15) return 14;
   return 12;
 }
+
+// rows of the base array whose ABI infinity byte is set are zeroed: (0, 0) is the device's identity encoding (ec.cuh)
+struct SrsZeroIdentityBody {
+  uint32_t *tables; const uint8_t *inf; uint32_t words;
+  PCGPU_KERNEL_DEV void operator()(size_t i) const {
+    if (inf[i]) for (uint32_t k = 0; k < words; k++) tables[i * (size_t)words + k] = 0;
+  }
+};
 
 template <class C>
 struct SrsGroupsBody {   // raw bases (packed x||y) -> all W groups in the aligned table layout (group 0 = the bases themselves)

@@ -2,11 +2,13 @@
 round kernels.  Names follow the reference (`compute_random_oracle_challenge`, `round_challenge`, `l_vec`,
 `r_vec`, `final_comm_key`, `c`).
 
-Deviation (documented): the reference hashes ark-serialize's `serialize_uncompressed` bytes and maps the Blake2s
-digest to a field element with `Field::from_random_bytes` -- both live in un-vendored crates.  Here the hashed bytes
-are the ABI's packed little-endian limbs (canonical integers for Fr, Montgomery x||y for points) and the digest is
-reduced as a little-endian integer with its top bits cleared, retrying with an incremented counter exactly like
-:74-87.  The challenge values are data to the kernels; parity is asserted on every group/field output.
+Transcript: exactly the reference's.  Every round hashes  round_challenge.serialize_uncompressed() ||
+l.serialize_uncompressed() || r.serialize_uncompressed()  (:681-688) -- 32 little-endian canonical bytes for the scalar,
+the curve's uncompressed point encoding (csrc/wire.cuh, produced on the device by pcgpu_g1_serialize) for l and r -- with
+Blake2s-256 (the digest the reference's tests instantiate) and maps the digest to a scalar with Field::from_random_bytes
+(ark-ff: keep MODULUS_BIT_SIZE bits of the little-endian digest, reject values >= r), retrying with an incremented
+little-endian u64 counter appended (:74-87).  ark-serialize / ark-ff are un-vendored: restated from their published
+behaviour (DESIGN.md section 2 lists what pins them).
 """
 import hashlib
 
@@ -27,16 +29,29 @@ def _fr_mont(curve, v):
     return np.array([(m >> (64 * j)) & (2**64 - 1) for j in range(4)], dtype=np.uint64)
 
 
+def from_random_bytes(curve, digest):
+    """Field::from_random_bytes for Fr (ark-ff Fp::from_random_bytes_with_flags::<EmptyFlags>): the 32 digest bytes as a
+    little-endian integer with the bits above MODULUS_BIT_SIZE cleared; None unless the result is a reduced element"""
+    r = _MODULI[curve]
+    v = int.from_bytes(digest[:32], "little") & ((1 << r.bit_length()) - 1)
+    return v if v < r else None
+
+
 def compute_random_oracle_challenge(curve, data):
     """ipa_pc/mod.rs:74-87 with Blake2s-256 (the digest the reference's tests instantiate, ipa_pc/mod.rs:1051+)."""
-    r = _MODULI[curve]
     i = 0
     while True:
-        h = hashlib.blake2s(data + i.to_bytes(8, "little")).digest()
-        v = int.from_bytes(h, "little") & ((1 << (r.bit_length() - 1)) - 1)
-        if 0 < v < r:
+        v = from_random_bytes(curve, hashlib.blake2s(data + i.to_bytes(8, "little")).digest())
+        if v is not None:
             return v
         i += 1
+
+
+def round_transcript(eng, curve, round_challenge, l, l_inf, r, r_inf):
+    """the bytes hashed for the next round challenge (:681-687)"""
+    pts = np.stack([np.asarray(l, dtype=np.uint64).reshape(-1), np.asarray(r, dtype=np.uint64).reshape(-1)])
+    enc = eng.g1_serialize(curve, pts, np.array([l_inf, r_inf], dtype=np.uint8), compressed=False)
+    return int(round_challenge).to_bytes(32, "little") + enc.tobytes()
 
 
 def open_rounds(eng, curve, comm_key_xy, coeffs, point, h_prime_xy, round_challenge):
@@ -47,10 +62,10 @@ def open_rounds(eng, curve, comm_key_xy, coeffs, point, h_prime_xy, round_challe
     st = eng.ipa_begin(curve, comm_key_xy, coeffs, point)
     l_vec, r_vec, chals = [], [], []
     while eng.ipa_len(st) > 1:
-        l, rr = eng.ipa_round_lr(curve, st, h_prime_xy)
+        l, l_inf, rr, r_inf = eng.ipa_round_lr(curve, st, h_prime_xy, with_inf=True)
         l_vec.append(l)
         r_vec.append(rr)
-        data = int(round_challenge).to_bytes(32, "little") + l.tobytes() + rr.tobytes()   # :681-687
+        data = round_transcript(eng, curve, round_challenge, l, l_inf, rr, r_inf)          # :681-687
         round_challenge = compute_random_oracle_challenge(curve, data)
         chals.append(round_challenge)
         inv = pow(round_challenge, -1, r)                                                    # :689

@@ -23,18 +23,20 @@ def main():
     t0 = time.perf_counter()
     st = eng.ipa_begin(C.id, key, coeffs, point)
     t_begin = time.perf_counter() - t0
-    t_lr = t_fold = 0.0
+    t_lr = t_fold = t_hash = 0.0
     rc = 7
     while eng.ipa_len(st) > 1:
-        t1 = time.perf_counter(); l, r = eng.ipa_round_lr(C.id, st, h_prime); t_lr += time.perf_counter() - t1
-        rc = ipa_pc.compute_random_oracle_challenge(C.id, int(rc).to_bytes(32, "little") + l.tobytes() + r.tobytes())
+        t1 = time.perf_counter(); l, li, r, ri = eng.ipa_round_lr(C.id, st, h_prime, with_inf=True); t_lr += time.perf_counter() - t1
+        t1 = time.perf_counter()
+        rc = ipa_pc.compute_random_oracle_challenge(C.id, ipa_pc.round_transcript(eng, C.id, rc, l, li, r, ri)); t_hash += time.perf_counter() - t1
         inv = pow(rc, -1, C.r)
         t1 = time.perf_counter(); eng.ipa_round_fold(st, ipa_pc._fr_mont(C.id, rc), ipa_pc._fr_mont(C.id, inv)); t_fold += time.perf_counter() - t1
     eng.ipa_finish(C.id, st)
     tot = time.perf_counter() - t0
     print(json.dumps({"workload": "IPA open halving loop, Pallas, 2^18, 18 rounds (host buffers in, device-resident rounds)",
                       "total_ms": round(tot * 1e3, 2), "begin_upload_ms": round(t_begin * 1e3, 2),
-                      "lr_msm_ip_ms": round(t_lr * 1e3, 2), "folds_ms": round(t_fold * 1e3, 2)}))
+                      "lr_msm_ip_ms": round(t_lr * 1e3, 2), "folds_ms": round(t_fold * 1e3, 2),
+                      "transcript_ms": round(t_hash * 1e3, 2), "freeze": os.environ.get("PCGPU_IPA_FREEZE", "1")}))
 
 if __name__ == "__main__":
     main()

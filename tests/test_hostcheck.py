@@ -361,6 +361,64 @@ def test_marlin_pc_host_mirror(eng, pc):
     assert not ainf and (acc == ex[0]).all() and C.fr_from_limbs(cval, True)[0] == exp_val
 
 
+def test_marlin_pc_hiding_and_bounds(eng, pc):
+    """MarlinKZG10::commit / open with hiding bounds AND degree bounds (marlin_pc/mod.rs:192-241, :245-336: r, shifted_r,
+    shifted_r_witness, random_v) against the oracle composed step by step like the reference; accumulators device-resident."""
+    from poly_commit_b200 import marlin_pc
+    cname = "bls12_381"
+    C = pyref.Curve(cname)
+    max_degree, bounds = 40, [20, 33]
+    pp = util.synthetic_srs(cname, max_degree + 1, seed=8)
+    gamma = util.random_points(cname, 8, seed=85)                               # powers_of_gamma_g[0..=hiding_bound+1]
+    supported = 36
+    powers, shifted = pp[: supported + 1], pp[max_degree - bounds[-1]:]
+    ck = marlin_pc.CommitterKey(eng, C.id, powers, shifted, bounds, powers_of_gamma_g_xy=gamma)
+    polys = [(util.rand_fr(cname, 30, seed=80, mont=True), None), (util.rand_fr(cname, 18, seed=81, mont=True), 20),
+             (util.rand_fr(cname, 34, seed=82, mont=True), 33), (util.rand_fr(cname, 9, seed=86, mont=True), None)]
+    rands = [dict(rand=util.rand_fr(cname, 4, seed=87, mont=True)),
+             dict(rand=util.rand_fr(cname, 5, seed=88, mont=True), shifted_rand=util.rand_fr(cname, 5, seed=89, mont=True)),
+             dict(rand=util.rand_fr(cname, 3, seed=90, mont=True), shifted_rand=util.rand_fr(cname, 6, seed=91, mont=True)),
+             None]                                                               # the last polynomial is committed without hiding
+    coms = marlin_pc.commit(ck, polys, rands)
+    for (coeffs, bound), rd, (comm, sh) in zip(polys, rands, coms):
+        rc, exy, _ = orc.kzg_commit(C.id, powers, coeffs, gamma if rd else None, rd["rand"] if rd else None)
+        assert rc == 0 and (comm[0] == exy).all()
+        if bound is not None:
+            rc, sxy, _ = orc.kzg_commit(C.id, shifted[bounds[-1] - bound:], coeffs, gamma, rd["shifted_rand"])
+            assert rc == 0 and (sh[0] == sxy).all()
+    point = util.rand_fr(cname, 1, seed=83, mont=True)[0]
+    chals = util.rand_fr(cname, 6, seed=84, mont=True)
+    w_xy, w_inf, random_v = marlin_pc.open(ck, polys, point, list(chals), rands)
+    # the reference's composition on the oracle
+    p = np.zeros((34, 4), dtype=np.uint64); r = np.zeros((6, 4), dtype=np.uint64)
+    sw = np.zeros((bounds[-1] + 1, 4), dtype=np.uint64); sr = np.zeros((6, 4), dtype=np.uint64); ci = 0
+    for (coeffs, bound), rd in zip(polys, rands):
+        cj = chals[ci]; ci += 1
+        p[: len(coeffs)] = orc.fr_axpy(C.id, p[: len(coeffs)], cj, coeffs)
+        if rd:
+            r[: len(rd["rand"])] = orc.fr_axpy(C.id, r[: len(rd["rand"])], cj, rd["rand"])
+        if bound is not None:
+            cj1 = chals[ci]; ci += 1
+            wit, _ = orc.fr_div_linear(C.id, coeffs, point)
+            s = np.concatenate([np.zeros((bounds[-1] - bound, 4), dtype=np.uint64), wit])
+            sw[: len(s)] = orc.fr_axpy(C.id, sw[: len(s)], cj1, s)
+            sr[: len(rd["shifted_rand"])] = orc.fr_axpy(C.id, sr[: len(rd["shifted_rand"])], cj1, rd["shifted_rand"])
+    rc, w0, _, rv0 = orc.kzg_open(C.id, powers, p, point, gamma, r)
+    srw, rv1 = orc.fr_div_linear(C.id, sr, point)
+    rc2, w1, _ = orc.kzg_commit(C.id, shifted, sw, gamma, srw)                   # msm(shifted, shifted_w) + msm(gamma, shifted_r_witness)
+    exp, _ = orc.g1_sum(C.id, np.stack([w0, w1]))
+    assert rc == 0 and rc2 == 0 and not w_inf and (w_xy == exp).all()
+    rv = (C.fr_from_limbs(rv0, True)[0] + C.fr_from_limbs(rv1, True)[0]) % C.r
+    assert C.fr_from_limbs(random_v, True)[0] == rv
+    # hiding without degree bounds: random_v is blind(point) of the combined blinding polynomial
+    w2 = marlin_pc.open(ck, [polys[0], polys[3]], point, list(chals[:2]), [rands[0], None])
+    p2 = np.zeros((30, 4), dtype=np.uint64)
+    p2[:30] = orc.fr_axpy(C.id, p2[:30], chals[0], polys[0][0]); p2[:9] = orc.fr_axpy(C.id, p2[:9], chals[1], polys[3][0])
+    r2 = orc.fr_axpy(C.id, np.zeros((4, 4), dtype=np.uint64), chals[0], rands[0]["rand"])
+    rc, e2, _, erv = orc.kzg_open(C.id, powers, p2, point, gamma, r2)
+    assert rc == 0 and (w2[0] == e2).all() and (w2[2] == erv).all()
+
+
 def test_hyrax_host_mirror(eng, pc):
     """hyrax.commit / open_row_mul (mirror of hyrax/mod.rs:230-242, :347) vs the oracle, 4 variables -> dim 4."""
     from poly_commit_b200 import hyrax
@@ -473,8 +531,17 @@ def oracle_ipa_rounds(cname, comm_key, coeffs, point, h_prime, round_challenge):
         l = cm(key[:m], co[m:n], orc.fr_inner_product(C.id, co[m:n], z[:m]))
         r = cm(key[m:n], co[:m], orc.fr_inner_product(C.id, co[:m], z[m:n]))
         l_vec.append(l); r_vec.append(r)
-        data = int(round_challenge).to_bytes(32, "little") + l.tobytes() + r.tobytes()
-        round_challenge = ipa_pc.compute_random_oracle_challenge(C.id, data)
+        # the reference's transcript, built independently of the device encoder: canonical LE scalar, then ark-serialize's
+        # uncompressed encodings of l and r (oracle/pyref.py)
+        data = int(round_challenge).to_bytes(32, "little") + pyref.g1_serialize(C, C.points_from_limbs(np.stack([l, r])), False)
+        digest_i = 0
+        while True:                                                   # compute_random_oracle_challenge, ipa_pc/mod.rs:74-87
+            import hashlib
+            v = int.from_bytes(hashlib.blake2s(data + digest_i.to_bytes(8, "little")).digest(), "little") % (1 << C.r.bit_length())
+            if v < C.r:
+                break
+            digest_i += 1
+        round_challenge = v
         inv = pow(round_challenge, -1, C.r)
         co[:m] = orc.fr_axpy(C.id, co[:m], C.fr_to_limbs([inv], True)[0], co[m:n])
         z[:m] = orc.fr_axpy(C.id, z[:m], C.fr_to_limbs([round_challenge], True)[0], z[m:n])
@@ -1135,3 +1202,26 @@ def test_ipa_fold_special_challenges(eng, pc, cname, monkeypatch):
             pts = [C.add(pts[i], C.mul(c, pts[h + i])) for i in range(h)]
         ex, _ = C.points_to_limbs(pts)
         assert (outs[0] == outs[1]).all() and (outs[0].reshape(-1) == ex[0]).all(), hex(c)
+
+
+@pytest.mark.parametrize("cname,n", [("pallas", 8192), ("bn254", 256)])
+def test_ipa_frozen_key_rounds(eng, pc, cname, n, monkeypatch):
+    """late rounds on a frozen key (csrc/ipa.cuh): explicit folds down to 4096 points, then weights instead of ladders.  Same
+    l / r / final key / c as with explicit folds all the way (PCGPU_IPA_FREEZE=0), and the verifier's recomputed key matches."""
+    from poly_commit_b200 import ipa_pc
+    C = pyref.Curve(cname)
+    key = util.random_points(cname, n, seed=270)
+    h_prime = util.random_points(cname, 1, seed=271)[0]
+    coeffs = util.rand_fr(cname, n - 5, seed=272, mont=True)
+    point = util.rand_fr(cname, 1, seed=273, mont=True)[0]
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PCGPU_IPA_FREEZE", flag)
+        outs.append(ipa_pc.open_rounds(eng, C.id, key, coeffs, point, h_prime, 0x77))
+    a, b = outs
+    assert len(a["l_vec"]) == n.bit_length() - 1 and a["challenges"] == b["challenges"]
+    for x, y in zip(a["l_vec"] + a["r_vec"], b["l_vec"] + b["r_vec"]):
+        assert (x == y).all()
+    assert (a["final_comm_key"] == b["final_comm_key"]).all() and (a["c"] == b["c"]).all()
+    fk = ipa_pc.check_final_key(eng, C.id, key, a["challenges"])
+    assert (fk[0] == a["final_comm_key"]).all()
