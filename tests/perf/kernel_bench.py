@@ -130,8 +130,24 @@ def main():
     ms = timeit(lambda: eng.msm_batch(srs2, mat.data_ptr(), dim + 1, dim, flags=F | pc.SCALARS_MONT), reps=3, warm=1)
     report("hyrax commit rows (cfg4): 2^11 MSMs x (2^11+1), BN254, comb c=8", ms, 64 * (dim + 1) + 32 * dim * (dim + 1),
            {"scalar_mults_per_s": round(dim * (dim + 1) / (ms / 1e3))})
-    lvec = dev(util.rand_fr_fast(cn, dim, 7))
-    ms = timeit(lambda: eng.fr_row_mul(C2.id, lvec.data_ptr(), mat.data_ptr(), dim, dim + 1, flags=F, ), reps=3, warm=1) if False else None
+    del mat
+    # Ligero commit of a 2^20-coefficient polynomial (BLS12-381 Fr, rho_inv = 4): row NTTs + column hashes + Merkle tree, device-resident
+    from poly_commit_b200 import linear_codes
+    n_rows, n_cols = linear_codes.compute_dimensions(C.id, 128, 4, 1 << 20)
+    log_ext = max(1, (n_cols * 4 - 1).bit_length())
+    N = 1 << log_ext
+    m = dev(util.rand_fr_fast(cname, n_rows * n_cols, 8))
+    ext = torch.empty((n_rows, N, 4), dtype=torch.int64, device="cuda")
+    leaves = torch.empty((N, 32), dtype=torch.uint8, device="cuda")
+    nodes = torch.empty((N - 1, 32), dtype=torch.uint8, device="cuda")
+    fused = lambda: eng.lincode_commit(C.id, m.data_ptr(), log_ext, n_rows=n_rows, n_cols=n_cols, flags=F, out_ext=ext.data_ptr(),
+                                       out_leaves=leaves.data_ptr(), out_nodes=nodes.data_ptr())
+    ms = timeit(fused, reps=5)
+    report(f"ligero commit 2^20 coeffs ({n_rows} x {n_cols} -> x {N}): row NTTs + Blake2s columns + SHA-256 tree", ms,
+           32 * n_rows * n_cols + 2 * 32 * n_rows * N + 32 * N, {"note": "algorithmic: read mat, write + read ext_mat, write leaves"})
+    ms = timeit(lambda: eng.lincode_hash_columns(C.id, ext.data_ptr(), n_rows=n_rows, n_cols=N, flags=F, out=leaves.data_ptr()), reps=5)
+    report(f"column hashes alone (Blake2s over {n_rows}-element columns, {N} columns)", ms, 32 * n_rows * N + 32 * N)
+    ms = timeit(lambda: eng.ntt_batch_device(C.id, m.data_ptr(), n_cols, n_rows, log_ext, ext.data_ptr()) if hasattr(eng, "ntt_batch_device") else None, reps=1, warm=0)
     eng.close()
 
 
