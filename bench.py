@@ -330,7 +330,7 @@ def main():
     imad_peak = eng.measure_imad_peak()
     # multiply count of one 2^log_deg MSM: entries = n * W windows, 3 affine rounds at 6.2 modmuls, the rest XYZZ at 9.5,
     # 288 wide multiplies per 12-limb Montgomery product
-    windows = 16
+    windows = 15 if log_deg >= 18 else 16
     msm_entries = n * windows
     wide_per_msm = (msm_entries * (7.0 / 8.0) * 6.2 + msm_entries * (1.0 / 8.0) * 9.5) * 288
     msm_kernel_ms = (stage_ms["affine_pair_rounds"] + stage_ms["bucket_accumulate"]) / 2
@@ -346,7 +346,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload, "parallelism": f"poly-sharded x{world}, SRS replicated; one batch call per rank, 2 polynomials "
                    "(4 MSM pipelines) in flight inside the library",
-                   "l2": "per-step working set (window-folded SRS tables 1.6 GB gather + 34 MB coefficients, rotating "
+                   "l2": "per-step working set (window-folded SRS tables 1.5 GB gather + 34 MB coefficients, rotating "
                          "polynomials) exceeds the 126 MB L2; no explicit flush"},
         "msm_scalar_mults_per_s": 2 * n * polys / (ms_dev / 1e3),
         "stage_ms_per_step": stage_ms,

@@ -121,6 +121,15 @@ int pcgpu_msm_bases(pcgpu_ctx *ctx, int curve, const void *bases_xy, const uint8
 int pcgpu_g1_fixed_base_mul(pcgpu_ctx *ctx, int curve, const void *base_xy, const void *scalars, size_t n, uint32_t flags,
                             void *out_xy);
 
+/* InnerProductArgPC::sample_generators (ipa_pc/mod.rs:302-325) and HyraxPC::setup's generator loop (hyrax/mod.rs:143-163):
+ * out[t] = the point obtained from Blake2s-256(protocol_name || (first_index + t) as u64 LE [|| j as u64 LE, j = 0, 1, ... while
+ * G::from_random_bytes returns None]) -- "PC-DL-2020" for the IPA (ipa_pc/mod.rs:50), "Hyrax protocol" for Hyrax
+ * (hyrax/mod.rs:26).  mul_by_cofactor_to_group is the identity on the cofactor-1 curves (BN254, Pallas); for BLS12-381 the
+ * caller clears the cofactor.  n affine points x||y (Montgomery); an identity result (infinity flag on x = 0) is written as
+ * zeros.  name_len <= 40.  With PCGPU_DEVICE_PTRS out_xy is a device pointer. */
+int pcgpu_g1_sample_generators(pcgpu_ctx *ctx, int curve, const uint8_t *protocol_name, size_t name_len, uint64_t first_index, size_t n,
+                               uint32_t flags, void *out_xy);
+
 /* ---- G1 wire formats ------------------------------------------------
  * The bytes CanonicalSerialize / CanonicalDeserialize produce for the G1Affine elements of kzg10::Powers
  * (kzg10/data_structures.rs:142-177), UniversalParams.powers_of_g (:57-112), Commitment (:315-328) and Proof.w (:479-495).

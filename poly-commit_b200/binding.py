@@ -98,6 +98,7 @@ def _load(path):
         "pcgpu_kzg_commit_batch": [_vp, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_commit": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp],
         "pcgpu_kzg_open": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp],
+        "pcgpu_g1_sample_generators": [_vp, ctypes.c_int, _vp, _sz, ctypes.c_uint64, _sz, ctypes.c_uint32, _vp],
         "pcgpu_buf_alloc": [_vp, _sz, ctypes.POINTER(_vp)],
         "pcgpu_buf_free": [_vp, _vp],
         "pcgpu_buf_write": [_vp, _vp, _sz, _vp, _sz],
@@ -331,6 +332,14 @@ class Engine:
         if out is None:
             out = np.zeros((n, 2 * fq_limbs(curve)), dtype=np.uint64)
         self._ck(self.lib.pcgpu_g1_fixed_base_mul(self.ctx, curve, _ptr(base_xy), _ptr(scalars), n, flags, _ptr(out)))
+        return out
+
+    def g1_sample_generators(self, curve, protocol_name, n, first_index=0, flags=0, out=None):
+        """InnerProductArgPC::sample_generators / HyraxPC::setup: n hash-derived points -> (n, 2*limbs) uint64"""
+        name = np.frombuffer(bytes(protocol_name), dtype=np.uint8).copy()
+        if out is None:
+            out = np.zeros((n, 2 * fq_limbs(curve)), dtype=np.uint64)
+        self._ck(self.lib.pcgpu_g1_sample_generators(self.ctx, curve, _ptr(name), name.size, first_index, n, flags, _ptr(out)))
         return out
 
     # ---- Fr ----

@@ -771,3 +771,13 @@ extern "C" int pcgpu_buf_zero(pcgpu_ctx *ctx, void *dst, size_t dst_off, size_t 
     return rc ? rc : rt::stream_sync(ctx->stream);
   });
 }
+
+extern "C" int pcgpu_g1_sample_generators(pcgpu_ctx *ctx, int curve, const uint8_t *protocol_name, size_t name_len, uint64_t first_index,
+                                          size_t n, uint32_t flags, void *out_xy) {
+  return guarded([&]() -> int {
+    if (!ctx || (name_len && !protocol_name) || (n && !out_xy)) return PCGPU_E_BADARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SET_DEVICE(ctx);
+    DISPATCH_CURVE(curve, return g1_sample_generators_impl<C>(ctx, protocol_name, name_len, first_index, n, flags, out_xy));
+  });
+}

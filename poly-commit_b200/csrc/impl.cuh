@@ -115,6 +115,26 @@ static const int NSLOTS = 8;
 // ---------------------------------------------------------------------------------------------
 // SRS
 // ---------------------------------------------------------------------------------------------
+template <class C> static int ensure_pow2(pcgpu_ctx *ctx);
+
+// comb window bits: the widest window whose tables (n * W * 2^(c-1) points) stay below PCGPU_COMB_MAX_GB (default 24 GB)
+inline uint32_t comb_window_bits(size_t n, size_t point_bytes) {
+  if (const char *e = getenv("PCGPU_COMB_C")) { int v = atoi(e); if (v >= 4 && v <= 16) return (uint32_t)v; }
+  double cap = 24e9;
+  if (const char *e = getenv("PCGPU_COMB_MAX_GB")) { double v = atof(e); if (v > 0) cap = v * 1e9; }
+#ifdef PCGPU_EMUL
+  const double max_entries = 65536.0;          // the serial emulation builds every entry with a GCD inversion
+#else
+  const double max_entries = 536870912.0;      // 2^29 entries: ~0.5 s of table construction
+#endif
+  uint32_t best = 4;
+  for (uint32_t c = 4; c <= 16; c++) {
+    double entries = (double)n * ((255 + c - 1) / c) * (double)(1u << (c - 1));
+    if (entries * (double)point_bytes <= cap && entries <= max_entries) best = c;
+  }
+  return best;
+}
+
 template <class C>
 int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, size_t n, uint32_t flags, pcgpu_srs *srs) {
   const size_t psz = sizeof(Affine<C>);
@@ -144,10 +164,13 @@ int srs_register_impl(pcgpu_ctx *ctx, const void *bases, const uint8_t *inf, siz
     if (groups > 1 && (rc = srs_build_groups<C>((const Affine<C> *)srs->d_tables, (uint32_t *)srs->d_folded, n, c, groups, st))) return rc;
     if (flags & PCGPU_SRS_COMB) {
       CombGeom cg; memset(&cg, 0, sizeof cg);
-      cg.n_bases = (uint32_t)n; cg.c = 8; cg.W = C::Fr::BITS / cg.c + 1; cg.NBk = 1u << (cg.c - 1);
+      cg.n_bases = (uint32_t)n; cg.c = comb_window_bits(n, psz); cg.W = (C::Fr::BITS + cg.c - 1) / cg.c; cg.NBk = 1u << (cg.c - 1);
       if ((rc = rt::dev_malloc(&srs->d_comb, psz * n * cg.W * cg.NBk))) return rc;
       srs->comb_c = cg.c;
-      if ((rc = rt::launch<64>(CombTableBody<C>{(const Affine<C> *)srs->d_tables, cg, (Affine<C> *)srs->d_comb}, n * cg.W, st))) return rc;
+      if ((rc = ensure_pow2<C>(ctx))) return rc;
+      const uint32_t chunks = (cg.NBk + COMB_CHUNK - 1) / COMB_CHUNK;
+      if ((rc = rt::launch<64>(CombTableBody<C>{(const Affine<C> *)srs->d_tables, cg, (Affine<C> *)srs->d_comb, ctx->d_pow2[C::ID], chunks},
+                               n * cg.W * chunks, st))) return rc;
     }
   }
   srs->c = c; srs->groups = groups;
@@ -456,7 +479,7 @@ int msm_batch_impl(pcgpu_ctx *ctx, const pcgpu_srs *srs, const void *scalars, si
     return PCGPU_OK;
   }
   CombGeom g; memset(&g, 0, sizeof g);
-  g.n_bases = (uint32_t)srs->n; g.c = srs->comb_c; g.W = C::Fr::BITS / g.c + 1; g.NBk = 1u << (g.c - 1);
+  g.n_bases = (uint32_t)srs->n; g.c = srs->comb_c; g.W = (C::Fr::BITS + g.c - 1) / g.c; g.NBk = 1u << (g.c - 1);
   g.n = (uint32_t)n; g.count = (uint32_t)count;
   g.seg_len = 64; if (count < 4096) { while (g.seg_len > 8 && count * ((n + g.seg_len - 1) / g.seg_len) < 65536) g.seg_len /= 2; }
   g.segs = (uint32_t)((n + g.seg_len - 1) / g.seg_len);
@@ -476,7 +499,8 @@ int msm_batch_impl(pcgpu_ctx *ctx, const pcgpu_srs *srs, const void *scalars, si
   if ((rc = rt::dev_memset(d_err, 0, 64, st))) return rc;
   ctx->prof.begin(10, st);
   if ((rc = rt::launch<128>(CombAccumulateBody<C>{(const Affine<C> *)srs->d_comb, d_s, g, partial, d_err}, ntasks, st))) return rc;
-  if ((rc = rt::launch<64>(CombRowSumBody<C>{partial, g.segs, d_out}, count, st))) return rc;
+  if ((rc = ensure_pow2<C>(ctx))) return rc;
+  if ((rc = rt::launch<64>(CombRowSumBody<C>{partial, g.segs, d_out, ctx->d_pow2[C::ID]}, count, st))) return rc;
   ctx->prof.end(10, st);
   std::vector<Affine<C>> h(count);
   uint32_t herr = 0;
@@ -1315,6 +1339,28 @@ int g1_deserialize_impl(pcgpu_ctx *ctx, const uint8_t *bytes, size_t n, uint32_t
   return PCGPU_OK;
 }
 
+template <class C>
+int g1_sample_generators_impl(pcgpu_ctx *ctx, const uint8_t *name, size_t name_len, uint64_t first, size_t n, uint32_t flags, void *out_xy) {
+  constexpr size_t PT = 2 * C::Fq::N * 4;
+  if (name_len > SAMPLE_NAME_MAX) return PCGPU_E_BADARG;
+  if (n == 0) return PCGPU_OK;
+  rt::stream_t st = ctx->stream;
+  const bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
+  int rc;
+  SampleGeneratorsBody<C> b;
+  memset(&b, 0, sizeof b);
+  memcpy(b.name, name, name_len);
+  b.name_len = (uint32_t)name_len; b.first = first;
+  if (dev) b.out_xy = (uint32_t *)out_xy;
+  else {
+    if ((rc = ctx->stage.reserve(rt::Arena::pad(n * PT) + 4096))) return rc;
+    b.out_xy = ctx->stage.take<uint32_t>(n * PT / 4);
+  }
+  if ((rc = rt::launch<128>(b, n, st))) return rc;
+  if (!dev && (rc = rt::copy_d2h(out_xy, b.out_xy, n * PT, st))) return rc;
+  return rt::stream_sync(st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // device self-test of the field layer
 // ---------------------------------------------------------------------------------------------
@@ -1470,7 +1516,8 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int ipa_finish_impl<C>(pcgpu_ctx *, pcgpu_ipa *, void *, void *); \
   EXT template int ipa_check_final_key_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, uint32_t, void *, uint8_t *); \
   EXT template int g1_serialize_impl<C>(pcgpu_ctx *, const void *, const uint8_t *, size_t, uint32_t, uint8_t *); \
-  EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *);
+  EXT template int g1_deserialize_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint32_t, void *, uint8_t *, size_t *, int *); \
+  EXT template int g1_sample_generators_impl<C>(pcgpu_ctx *, const uint8_t *, size_t, uint64_t, size_t, uint32_t, void *);
 #define PCGPU_INSTANTIATE(C, EXT) \
   PCGPU_INST_PAIR1(C, EXT) PCGPU_INST_ACC(C, EXT) PCGPU_INST_REDUCE(C, EXT) \
   PCGPU_INST_PIPE(C, EXT) PCGPU_INST_SMALL(C, EXT) PCGPU_INST_SRS(C, EXT) PCGPU_INST_FR(C, EXT) PCGPU_INST_IPA(C, EXT)

@@ -18,7 +18,8 @@ enum : size_t { SRS_PRECOMPUTE_MIN_N = 1u << 12 };
 inline uint32_t srs_precompute_window(size_t n) {
   if (const char *e = getenv("PCGPU_SRS_C")) { int v = atoi(e); if (v >= 8 && v <= 22) return (uint32_t)v; }   // tuning knob
   uint32_t lg = ilog2_floor(n ? n : 1);
-  if (lg >= 18) return 16;   // c = 17 (15 windows) measured equal on the pair rounds and slower in scan / reduce (2^16 buckets): profiles/r02_msm_ab_*
+  if (lg >= 18) return 17;   // 255 / 17 = 15 windows (load_scalar halves the scalar range, no 16th carry window): 6 % fewer
+                             // additions than c = 16 -- equal single-MSM latency, +5 % batch throughput (profiles/r02_bench_n1_*)
   if (lg >= 15) return 14;
   return 12;
 }
@@ -94,18 +95,41 @@ struct CombGeom {
   uint32_t scalar_bits, scalars_mont;
 };
 
+// fp_inv_gcd-based projective -> affine (the table build is setup work, but at c = 14 it is 3 * 10^8 conversions: the
+// binary-GCD inverse on the otherwise idle ALU pipe instead of a 380-multiplication Fermat inverse per entry)
+template <class C>
+PCGPU_DEV Affine<C> comb_to_affine(const XYZZ<C> &p, const uint32_t *pow2) {
+  using Q = typename C::Fq;
+  if (p.is_inf()) return Affine<C>::inf();
+  Fp<Q> inv = fp_inv_gcd<Q>(fp_mul<Q>(p.zz, p.zzz), pow2);
+  Affine<C> a;
+  a.x = fp_mul<Q>(p.x, fp_mul<Q>(inv, p.zzz));
+  a.y = fp_mul<Q>(p.y, fp_mul<Q>(inv, p.zz));
+  return a;
+}
+
+// thread (j, w, q) fills entries d = q * COMB_CHUNK + 1 .. of row (j, w): start point by double-and-add, then mixed additions
+enum { COMB_CHUNK = 256 };
 template <class C>
 struct CombTableBody {
-  const Affine<C> *bases; CombGeom g; Affine<C> *table;
+  const Affine<C> *bases; CombGeom g; Affine<C> *table; const uint32_t *pow2; uint32_t chunks;   // chunks per row
   PCGPU_KERNEL_DEV void operator()(size_t t) const {
-    uint32_t j = (uint32_t)(t / g.W), w = (uint32_t)(t % g.W);
+    const uint32_t q = (uint32_t)(t % chunks);
+    const size_t jw = t / chunks;
+    const uint32_t j = (uint32_t)(jw / g.W), w = (uint32_t)(jw % g.W);
     XYZZ<C> p = xyzz_from_affine<C>(load_affine<C>(bases + j));
     for (uint32_t k = 0; k < w * g.c; k++) p = xyzz_dbl<C>(p);
-    XYZZ<C> acc = p;
-    Affine<C> *row = table + t * (size_t)g.NBk;
-    for (uint32_t d = 1; d <= g.NBk; d++) {
-      row[d - 1] = xyzz_to_affine<C>(acc);
-      xyzz_add<C>(acc, p);
+    const Affine<C> pa = comb_to_affine<C>(p, pow2);             // 2^(c w) G_j, affine: the additions below are mixed
+    const uint32_t d0 = q * COMB_CHUNK + 1, d1 = d0 + COMB_CHUNK - 1 < g.NBk ? d0 + COMB_CHUNK - 1 : g.NBk;
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (int b = 31; b >= 0; b--) {                              // acc = d0 * pa
+      acc = xyzz_dbl<C>(acc);
+      if ((d0 >> b) & 1) xyzz_madd<C>(acc, pa, false);
+    }
+    Affine<C> *row = table + jw * (size_t)g.NBk;
+    for (uint32_t d = d0; d <= d1; d++) {
+      row[d - 1] = comb_to_affine<C>(acc, pow2);
+      xyzz_madd<C>(acc, pa, false);
     }
   }
 };
@@ -121,11 +145,11 @@ struct CombAccumulateBody {
     const Affine<C> *tab = table; const CombGeom gg = g;
     for (uint32_t i = lo; i < hi; i++) {
       uint32_t k[8];
-      load_scalar_plain<C>(scalars, (size_t)row * g.n + i, g.scalars_mont != 0, k);
-      if (!scalar_in_range(k, g.scalar_bits)) { rt::atomic_or(err, 1u); continue; }
+      bool flip;   // load_scalar halves the scalar range, so W = ceil(bits / c) windows carry every digit
+      if (!load_scalar<C>(scalars, (size_t)row * g.n + i, g.scalars_mont != 0, k, &flip)) { rt::atomic_or(err, 1u); continue; }
       for_each_digit(k, mg, [&](uint32_t w, uint32_t mag, bool neg) {
         Affine<C> a = load_affine<C>(tab + ((size_t)i * gg.W + w) * gg.NBk + (mag - 1));
-        xyzz_madd<C>(acc, a, neg);
+        xyzz_madd<C>(acc, a, neg != flip);
       });
     }
     store_xyzz<C>(partial + t, acc);
@@ -134,11 +158,11 @@ struct CombAccumulateBody {
 
 template <class C>
 struct CombRowSumBody {
-  const XYZZ<C> *partial; uint32_t segs; Affine<C> *out;
+  const XYZZ<C> *partial; uint32_t segs; Affine<C> *out; const uint32_t *pow2;
   PCGPU_KERNEL_DEV void operator()(size_t row) const {
     XYZZ<C> acc = XYZZ<C>::inf();
     for (uint32_t s = 0; s < segs; s++) { XYZZ<C> p = load_xyzz<C>(partial + row * segs + s); xyzz_add<C>(acc, p); }
-    out[row] = xyzz_to_affine<C>(acc);
+    out[row] = comb_to_affine<C>(acc, pow2);
   }
 };
 

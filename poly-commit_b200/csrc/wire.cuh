@@ -14,6 +14,7 @@
 // curves have cofactor 1).  One thread per point; every kernel here is bound by the integer-multiply pipe like the MSM.
 #pragma once
 #include "ec.cuh"
+#include "hash.cuh"
 #include "msm.cuh"
 
 namespace pcgpu {
@@ -249,6 +250,75 @@ struct G1EncodeBody {
     }
     uint8_t *dst = bytes + i * (size_t)sz;
     for (int k = 0; k < sz; k++) dst[k] = buf[k];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Generator sampling: InnerProductArgPC::sample_generators (ipa_pc/mod.rs:302-325) and HyraxPC::setup's
+// copy of it (hyrax/mod.rs:143-163).  Generator i is  Blake2s(PROTOCOL_NAME || i_le64)  fed to G::from_random_bytes, and
+// while that returns None  Blake2s(PROTOCOL_NAME || i_le64 || j_le64)  for j = 0, 1, ...; then mul_by_cofactor (1 on the
+// curves these schemes are instantiated on here) and normalize_batch (a no-op on affine output).
+// G::from_random_bytes (ark-ec short_weierstrass Affine, un-vendored, restated): the digest is read as an x-coordinate with
+// SWFlags -- Fp::from_random_bytes_with_flags keeps MODULUS_BIT_SIZE bits of the little-endian bytes and takes the flags from
+// the top two bits of byte ceil((bits + 2) / 8) - 1 of the (zero-extended) input, so a 32-byte digest carries flag bits only
+// when bits + 2 <= 256 (BN254) and none on a 255-bit field (Pallas: always "positive"); x >= p, both flags, or the infinity
+// flag on a non-zero x give None; otherwise the point is (x, y) with y the lexicographically LARGER root when the flag says
+// positive (get_point_from_x_unchecked(x, greatest = y_is_positive)) and None when x^3 + b has no root.
+// One thread per generator: one or a few 64-byte Blake2s blocks and one square root in Fq -- bound by the multiply pipe.
+// ---------------------------------------------------------------------------------------------------------------------------
+enum { SAMPLE_NAME_MAX = 40 };
+
+template <class C>
+struct SampleGeneratorsBody {
+  uint8_t name[SAMPLE_NAME_MAX]; uint32_t name_len; uint64_t first; uint32_t *out_xy;
+  PCGPU_DEV static bool hash_to_point(const uint32_t *digest, Affine<C> &pt) {
+    using Q = typename C::Fq;
+    constexpr int N = Q::N;
+    constexpr int FLAG_BYTE = (Q::BITS + 2 + 7) / 8 - 1;          // 31 for a 254-bit field, 32 for a 255-bit one
+    uint32_t flagbits = 0;
+    if (FLAG_BYTE < 32) flagbits = (digest[FLAG_BYTE / 4] >> (8 * (FLAG_BYTE % 4))) & 0xC0u;
+    uint32_t xl[N];
+    for (int i = 0; i < N; i++) xl[i] = i < 8 ? digest[i] : 0u;
+    if (Q::BITS % 32) xl[N - 1] &= (1u << (Q::BITS % 32)) - 1;    // keep MODULUS_BIT_SIZE bits
+    if (limbs_ge_mod<Q>(xl)) return false;
+    const bool neg = (flagbits & 0x80u) != 0, inf = (flagbits & 0x40u) != 0;
+    if (neg && inf) return false;
+    bool zero = true;
+    for (int i = 0; i < N; i++) zero &= xl[i] == 0;
+    if (inf) { if (!zero) return false; pt = Affine<C>::inf(); return true; }
+    Fp<Q> x;
+    for (int i = 0; i < N; i++) x.l[i] = xl[i];
+    x = fp_to_mont<Q>(x);
+    Fp<Q> r;
+    if (!fp_sqrt<Q>(curve_rhs<C>(x), r)) return false;
+    const bool want_larger = !neg;                                 // greatest = y_is_positive
+    pt.x = x;
+    pt.y = (fp_is_larger_half<Q>(r) == want_larger) ? r : fp_neg<Q>(r);
+    return true;
+  }
+  PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    constexpr int N = C::Fq::N;
+    const uint64_t i = first + t;
+    Affine<C> pt;
+    for (uint64_t attempt = 0;; attempt++) {
+      // message: name || i (8 bytes LE) [|| j = attempt - 1 (8 bytes LE)] -- at most 56 bytes, one final block
+      uint8_t msg[64];
+      uint32_t len = 0;
+      for (uint32_t k = 0; k < name_len; k++) msg[len++] = name[k];
+      for (int k = 0; k < 8; k++) msg[len++] = (uint8_t)(i >> (8 * k));
+      if (attempt) { const uint64_t j = attempt - 1; for (int k = 0; k < 8; k++) msg[len++] = (uint8_t)(j >> (8 * k)); }
+      Blake2s b;
+      b.init();
+      for (int w = 0; w < 16; w++) {
+        uint32_t v = 0;
+        for (int k = 0; k < 4; k++) { const uint32_t pos = 4 * w + k; if (pos < len) v |= (uint32_t)msg[pos] << (8 * k); }
+        b.m[w] = v;
+      }
+      b.compress(len, true);
+      if (hash_to_point(b.h, pt)) break;
+    }
+    uint32_t *o = out_xy + t * (size_t)(2 * N);
+    for (int k = 0; k < N; k++) { o[k] = pt.x.l[k]; o[N + k] = pt.y.l[k]; }
   }
 };
 

@@ -1225,3 +1225,16 @@ def test_ipa_frozen_key_rounds(eng, pc, cname, n, monkeypatch):
     assert (a["final_comm_key"] == b["final_comm_key"]).all() and (a["c"] == b["c"]).all()
     fk = ipa_pc.check_final_key(eng, C.id, key, a["challenges"])
     assert (fk[0] == a["final_comm_key"]).all()
+
+
+@pytest.mark.parametrize("cname,name", [("pallas", b"PC-DL-2020"), ("bn254", b"Hyrax protocol"), ("bn254", b"PC-DL-2020")])
+def test_sample_generators(eng, pc, cname, name):
+    """InnerProductArgPC::sample_generators / HyraxPC::setup (ipa_pc/mod.rs:302-325, hyrax/mod.rs:143-163): hash-derived
+    generators, including indices that need the retry counter and (BN254) digests whose flag bits select the smaller root"""
+    C = pyref.Curve(cname)
+    n = 64
+    got = eng.g1_sample_generators(C.id, name, n, first_index=5)
+    exp = pyref.sample_generators(C, name, n, first=5)
+    assert C.points_from_limbs(got) == exp
+    assert all(C.on_curve(P) for P in exp) and len(set(exp)) == n
+    assert (eng.g1_sample_generators(C.id, name, 3, first_index=20) == got[15:18]).all()
