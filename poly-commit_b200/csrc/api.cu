@@ -5,6 +5,8 @@
 #include "impl.cuh"
 
 // Nothing unwinds across the C ABI: every entry point runs inside this guard (std::vector / std::thread / new can throw).
+static int ensure_siblings(pcgpu_ctx *ctx, size_t count);
+
 template <class F>
 static int guarded(F f) {
   try { return f(); }
@@ -73,6 +75,7 @@ extern "C" void pcgpu_destroy(pcgpu_ctx *ctx) {
   for (int k = 0; k < 3; k++) rt::dev_free(ctx->d_pow2[k]);
   ctx->msm_arena.release();
   ctx->stage.release();
+  ctx->ipa_arena.release();
   rt::dev_free(ctx->d_slots);
   rt::host_free_pinned(ctx->h_pinned);
   if (ctx->ev_ok) rt::event_destroy(ctx->ev_upload);
@@ -315,7 +318,7 @@ extern "C" int pcgpu_ipa_begin(pcgpu_ctx *ctx, int curve, const void *comm_key_x
     case PCGPU_PALLAS: rc = ipa_begin_impl<Pallas>(ctx, comm_key_xy, n, coeffs, n_coeffs, point, flags, st); break;
     default: rc = PCGPU_E_BADARG;
   }
-  if (rc) { rt::dev_free(st->d_key); rt::dev_free(st->d_coeffs); rt::dev_free(st->d_w); delete st; return rc; }
+  if (rc) { if (rc != PCGPU_E_BADARG) ctx->ipa_active = false; delete st; return rc; }
   *out = st;
   return PCGPU_OK;
   });
@@ -325,9 +328,13 @@ extern "C" int pcgpu_ipa_round_lr(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_p
                                   void *out_r_xy, uint8_t *out_r_inf) {
   return guarded([&]() -> int {
   if (!ctx || !st || !h_prime_xy || !out_l_xy || !out_r_xy) return PCGPU_E_BADARG;
+  int src = ensure_siblings(ctx, 1);   // the two commitments of a round run on two streams
+  if (src) return src;
+  pcgpu_ctx *sib = ctx->siblings[0];
   std::lock_guard<std::mutex> lk(ctx->mu);
+  std::lock_guard<std::mutex> lk2(sib->mu);
   SET_DEVICE(ctx);
-  DISPATCH_CURVE(st->curve, return ipa_round_lr_impl<C>(ctx, st, h_prime_xy, out_l_xy, out_l_inf, out_r_xy, out_r_inf));
+  DISPATCH_CURVE(st->curve, return ipa_round_lr_impl<C>(ctx, sib, st, h_prime_xy, out_l_xy, out_l_inf, out_r_xy, out_r_inf));
   });
 }
 
@@ -354,7 +361,7 @@ extern "C" int pcgpu_ipa_finish(pcgpu_ctx *ctx, pcgpu_ipa *st, void *out_final_k
     case PCGPU_PALLAS: rc = ipa_finish_impl<Pallas>(ctx, st, out_final_key_xy, out_c); break;
     default: rc = PCGPU_E_BADARG;
   }
-  rt::dev_free(st->d_key); rt::dev_free(st->d_coeffs); rt::dev_free(st->d_w);
+  ctx->ipa_active = false;   // the state's memory belongs to the context's IPA arena and is kept for the next open
   delete st;
   return rc;
   });

@@ -76,6 +76,8 @@ struct pcgpu_ctx {
   int device;
   rt::stream_t own_stream, stream;
   rt::Arena msm_arena, stage;
+  rt::Arena ipa_arena;             // state of the (one) InnerProductArgPC::open in progress on this context; reused across opens
+  bool ipa_active = false;
   void *d_slots;    // 8 XYZZ result slots + 1 affine + err word, generously sized
   Prof prof;
   uint32_t *d_pow2[3] = {nullptr, nullptr, nullptr};  // fp_inv_gcd tables (Fq), per curve
@@ -875,8 +877,7 @@ template <class C>
 static int ipa_freeze(pcgpu_ctx *ctx, pcgpu_ipa *st) {
   using R = typename C::Fr;
   int rc;
-  if ((rc = rt::dev_malloc((void **)&st->d_w, 3 * st->n * 32 + 64))) return rc;
-  st->frozen_m = st->n;
+  st->frozen_m = st->n;   // d_w (3 * SMALL_MAX_N elements) was carved out of the context's IPA arena by ipa_begin
   return rt::launch<128>(FrFillOneBody<R>{st->d_w}, st->n, ctx->stream);
 }
 inline bool ipa_freeze_enabled() {
@@ -894,8 +895,15 @@ int ipa_begin_impl(pcgpu_ctx *ctx, const void *key_xy, size_t n, const void *coe
   st->curve = C::ID; st->n0 = st->n = n;
   st->d_key = nullptr; st->d_coeffs = nullptr; st->frozen_m = 0; st->d_w = nullptr;
   if ((rc = ensure_pow2<C>(ctx))) return rc;
-  if ((rc = rt::dev_malloc(&st->d_key, n * sizeof(Affine<C>)))) return rc;
-  if ((rc = rt::dev_malloc((void **)&st->d_coeffs, (2 * n + IP_THREADS + IP_THREADS / IP_BLOCK + 32) * 32))) return rc;
+  // one arena per context, grown on demand and kept: an open costs no cudaMalloc / cudaFree after the first
+  if (ctx->ipa_active) return PCGPU_E_BADARG;          // one halving loop at a time per context
+  const size_t fr_words = (2 * n + IP_THREADS + IP_THREADS / IP_BLOCK + 32) * 8;
+  if ((rc = ctx->ipa_arena.reserve(rt::Arena::pad(n * sizeof(Affine<C>)) + rt::Arena::pad(fr_words * 4) + rt::Arena::pad(3 * SMALL_MAX_N * 32 + 64) + 4096))) return rc;
+  st->d_key = ctx->ipa_arena.take<Affine<C>>(n);
+  st->d_coeffs = ctx->ipa_arena.take<uint32_t>(fr_words);
+  st->d_w = ctx->ipa_arena.take<uint32_t>(3 * SMALL_MAX_N * 8 + 16);
+  if (!st->d_key || !st->d_coeffs || !st->d_w) return PCGPU_E_OOM;
+  ctx->ipa_active = true;
   st->d_z = st->d_coeffs + 8 * n; st->d_scr = st->d_z + 8 * n;
   if ((rc = dev ? rt::copy_d2d(st->d_key, key_xy, n * sizeof(Affine<C>), s) : rt::copy_h2d(st->d_key, key_xy, n * sizeof(Affine<C>), s))) return rc;
   if ((rc = rt::dev_memset(st->d_coeffs, 0, n * 32, s))) return rc;
@@ -910,7 +918,7 @@ int ipa_begin_impl(pcgpu_ctx *ctx, const void *key_xy, size_t n, const void *coe
 }
 
 template <class C>
-int ipa_round_lr_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_prime_xy, void *out_l_xy, uint8_t *out_l_inf,
+int ipa_round_lr_impl(pcgpu_ctx *ctx, pcgpu_ctx *sib, pcgpu_ipa *st, const void *h_prime_xy, void *out_l_xy, uint8_t *out_l_inf,
                       void *out_r_xy, uint8_t *out_r_inf) {
   using R = typename C::Fr;
   rt::stream_t s = ctx->stream;
@@ -952,16 +960,24 @@ int ipa_round_lr_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *h_prime_xy, voi
     host::to_affine<C>(lr[1], out_r_xy, out_r_inf);
     return PCGPU_OK;
   }
-  // <coeffs_r, z_l>, <coeffs_l, z_r>
+  // <coeffs_r, z_l>, <coeffs_l, z_r> (results fetched after the MSMs have been queued), then the two commitments: cm_commit(key_l,
+  // coeffs_r) on this context's stream and cm_commit(key_r, coeffs_l) on the sibling's, so their latency-bound stages overlap
   if ((rc = fr_inner_product<R>(cr, zl, m, d_ip, st->d_scr, s))) return rc;
+  if ((rc = fr_inner_product<R>(cl, zr, m, d_ip + 8, st->d_scr, s))) return rc;   // stream order: the first product is complete
   if ((rc = rt::copy_d2h(ip_m[0], d_ip, 32, s))) return rc;
-  if ((rc = rt::stream_sync(s))) return rc;
-  if ((rc = fr_inner_product<R>(cl, zr, m, d_ip, st->d_scr, s))) return rc;
-  if ((rc = rt::copy_d2h(ip_m[1], d_ip, 32, s))) return rc;
-  if ((rc = rt::stream_sync(s))) return rc;
+  if ((rc = rt::copy_d2h(ip_m[1], d_ip + 8, 32, s))) return rc;
   host::HXYZZ<C> l, r;
-  if ((rc = msm_to_host<C>(ctx, &st->view, 0, cr, m, true, &l))) return rc;  // cm_commit(key_l, coeffs_r)
-  if ((rc = msm_to_host<C>(ctx, &st->view, m, cl, m, true, &r))) return rc;  // cm_commit(key_r, coeffs_l)
+  if (sib) {
+    MsmPending<C> pl, pr;
+    if ((rc = msm_issue<C>(ctx, &st->view, 0, cr, m, true, &pl))) return rc;
+    if ((rc = msm_issue<C>(sib, &st->view, m, cl, m, true, &pr))) return rc;
+    if ((rc = msm_collect<C>(ctx, &pl, &l))) return rc;
+    if ((rc = msm_collect<C>(sib, &pr, &r))) return rc;
+  } else {
+    if ((rc = msm_to_host<C>(ctx, &st->view, 0, cr, m, true, &l))) return rc;  // cm_commit(key_l, coeffs_r)
+    if ((rc = msm_to_host<C>(ctx, &st->view, m, cl, m, true, &r))) return rc;  // cm_commit(key_r, coeffs_l)
+  }
+  if ((rc = rt::stream_sync(s))) return rc;
   host::fr_from_mont_host<R>(ip_m[0], ip_c[0]);
   host::fr_from_mont_host<R>(ip_m[1], ip_c[1]);
   l = host::padd<C>(l, host::pmul_affine<C>(h_prime_xy, ip_c[0]));
@@ -1511,7 +1527,7 @@ inline int measure_imad_peak_impl(pcgpu_ctx *ctx, double *ops_per_s) {
   EXT template int lincode_commit_impl<C>(pcgpu_ctx *, const void *, size_t, size_t, uint32_t, int, uint32_t, void *, uint8_t *, uint8_t *, uint8_t *);
 #define PCGPU_INST_IPA(C, EXT)                                                                                             \
   EXT template int ipa_begin_impl<C>(pcgpu_ctx *, const void *, size_t, const void *, size_t, const void *, uint32_t, pcgpu_ipa *); \
-  EXT template int ipa_round_lr_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, void *, uint8_t *, void *, uint8_t *); \
+  EXT template int ipa_round_lr_impl<C>(pcgpu_ctx *, pcgpu_ctx *, pcgpu_ipa *, const void *, void *, uint8_t *, void *, uint8_t *); \
   EXT template int ipa_round_fold_impl<C>(pcgpu_ctx *, pcgpu_ipa *, const void *, const void *); \
   EXT template int ipa_finish_impl<C>(pcgpu_ctx *, pcgpu_ipa *, void *, void *); \
   EXT template int ipa_check_final_key_impl<C>(pcgpu_ctx *, const pcgpu_srs *, const void *, uint32_t, void *, uint8_t *); \
