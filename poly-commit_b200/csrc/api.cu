@@ -695,19 +695,21 @@ extern "C" int pcgpu_kzg_commit_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_
   });
 }
 
-enum { PCGPU_COMMIT_OPEN_WAYS = 2 };   // polynomials in flight (two MSM pipelines each)
+enum { PCGPU_COMMIT_OPEN_WAYS = 2, PCGPU_COMMIT_OPEN_MAX_WAYS = 4 };   // polynomials in flight (two MSM pipelines each)
 
 extern "C" int pcgpu_kzg_commit_open_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *const *coeffs, const size_t *n,
                                            size_t count, const void *z, uint32_t flags, void *out_comm_xy, uint8_t *out_comm_inf,
                                            void *out_w_xy, uint8_t *out_w_inf) {
   return guarded([&]() -> int {
   if (!ctx || !powers_of_g || !z || (count && (!coeffs || !n || !out_comm_xy || !out_w_xy))) return PCGPU_E_BADARG;
-  const size_t ways = count < (size_t)PCGPU_COMMIT_OPEN_WAYS ? count : (size_t)PCGPU_COMMIT_OPEN_WAYS;
+  size_t max_ways = PCGPU_COMMIT_OPEN_WAYS;
+  if (const char *e = getenv("PCGPU_COMMIT_OPEN_WAYS")) { int v = atoi(e); if (v >= 1 && v <= PCGPU_COMMIT_OPEN_MAX_WAYS) max_ways = (size_t)v; }   // tuning knob
+  const size_t ways = count < max_ways ? count : max_ways;
   if (ways == 0) return PCGPU_OK;
   int rc = ensure_siblings(ctx, 2 * ways - 1);   // way 0: (ctx, sib[0]); way w >= 1: (sib[2w-1], sib[2w])
   if (rc) return rc;
   const size_t psz = (powers_of_g->curve == PCGPU_BLS12_381 ? 6 : 4) * 16;
-  int rcs[PCGPU_COMMIT_OPEN_WAYS] = {PCGPU_OK, PCGPU_OK};
+  int rcs[PCGPU_COMMIT_OPEN_MAX_WAYS] = {PCGPU_OK, PCGPU_OK, PCGPU_OK, PCGPU_OK};
   auto work = [&](size_t w) {
     pcgpu_ctx *a = w == 0 ? ctx : ctx->siblings[2 * w - 1], *b = ctx->siblings[w == 0 ? 0 : 2 * w];
     for (size_t i = w; i < count; i += ways) {
