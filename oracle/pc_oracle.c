@@ -4,15 +4,19 @@
  * reference legs may load this library.  The product (libpcgpu.so) never links
  * or calls it.
  *
- * PARITY STATUS: "parity unpinned" at the MSM boundary -- the reference's tests
- * hold no golden vectors for commitments or proofs and its
- * arithmetic lives in un-vendored crates (ark-ff / ark-ec / ark-poly 0.5.0) that
- * cannot be built here (no Rust toolchain).  This restatement is pinned instead
- * by (i) an independent Python big-integer implementation (oracle/pyref.py) via
- * the committed fixtures in tests/golden/, (ii) group-law identities (r*G = O,
- * on-curve, linearity), (iii) the reference's own small-integer KATs for the Fr
- * helpers (utils.rs:274-286 test_row_mul; linear_codes/utils.rs:303-331
- * test_reed_solomon's fft == evaluate property).
+ * PARITY STATUS: the reference's tests hold no golden vectors for commitments or
+ * proofs and its arithmetic lives in un-vendored crates
+ * (ark-ff / ark-ec / ark-poly 0.5.0) that cannot be built here (no Rust toolchain),
+ * so no output of the reference itself backs this file: "parity unpinned" by the
+ * reference.  It is pinned instead by (o) vectors PUBLISHED outside this
+ * repository (tests/golden/external_kats.json: EIP-196 / go-ethereum 2G, 3G and an
+ * ecMul vector through the MSM, EIP-2537 / ZCash BLS12-381 multiples, zkcrypto
+ * Montgomery constants, the published Fr roots of unity and the domain-generator
+ * rule; tests/test_external_kats.py), (i) an independent Python big-integer
+ * implementation (oracle/pyref.py) via the committed fixtures in tests/golden/,
+ * (ii) group-law identities (r*G = O, on-curve, linearity), (iii) the reference's
+ * own small-integer KATs for the Fr helpers (utils.rs:274-286 test_row_mul;
+ * linear_codes/utils.rs:303-331 test_reed_solomon's fft == evaluate property).
  *
  * Every exported function cites the reference call site whose dataflow it follows.
  * Data conventions (include/pcgpu.h): little-endian u64 limbs; field elements in
