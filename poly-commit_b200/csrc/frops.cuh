@@ -34,6 +34,14 @@ PCGPU_DEV void store_fr(uint32_t *base, size_t i, const Fp<R> &v) {
   p[0] = lo; p[1] = hi;
 }
 
+// a0 b0 + a1 b1: one Montgomery reduction for the two products when the modulus leaves the headroom (BN254, Pallas: 3r < 2^256;
+// BLS12-381's r does not), two ordinary products otherwise
+template <class R>
+PCGPU_DEV Fp<R> fr_dot2(const Fp<R> &a0, const Fp<R> &b0, const Fp<R> &a1, const Fp<R> &b1) {
+  if constexpr (mont_mul2_supported<R>()) return fp_mul2<R>(a0, b0, a1, b1);
+  else return fp_add<R>(fp_mul<R>(a0, b0), fp_mul<R>(a1, b1));
+}
+
 template <class R>
 struct FrFromMontBody {
   const uint32_t *in; uint32_t *out;
@@ -171,8 +179,15 @@ template <class R>
 struct IpPartialBody {
   const uint32_t *a; const uint32_t *b; size_t n; uint32_t *partial;
   PCGPU_KERNEL_DEV void operator()(size_t t) const {
+    // two elements per iteration: four independent loads in flight and ONE Montgomery reduction for the pair
+    // (fr_dot2 = a0 b0 + a1 b1 with a single reduction where 3r < 2^256: 192 instead of 256 wide multiplies per pair)
     Fp<R> acc = Fp<R>::zero();
-    for (size_t i = t; i < n; i += IP_THREADS) acc = fp_add<R>(acc, fp_mul<R>(load_fr<R>(a, i), load_fr<R>(b, i)));
+    size_t i = t;
+    for (; i + IP_THREADS < n; i += 2 * (size_t)IP_THREADS) {
+      const Fp<R> a0 = load_fr<R>(a, i), b0 = load_fr<R>(b, i), a1 = load_fr<R>(a, i + IP_THREADS), b1 = load_fr<R>(b, i + IP_THREADS);
+      acc = fp_add<R>(acc, fr_dot2<R>(a0, b0, a1, b1));
+    }
+    if (i < n) acc = fp_add<R>(acc, fp_mul<R>(load_fr<R>(a, i), load_fr<R>(b, i)));
     store_fr<R>(partial, t, acc);
   }
 };
@@ -223,7 +238,10 @@ struct FrRowMulBody {
   const uint32_t *v; const uint32_t *m; size_t rows, cols; uint32_t *out;
   PCGPU_KERNEL_DEV void operator()(size_t c) const {
     Fp<R> acc = Fp<R>::zero();
-    for (size_t r = 0; r < rows; r++) acc = fp_add<R>(acc, fp_mul<R>(load_fr<R>(v, r), load_fr<R>(m, r * cols + c)));
+    size_t r = 0;
+    for (; r + 2 <= rows; r += 2)      // pairs of rows: one reduction per two products (fr_dot2)
+      acc = fp_add<R>(acc, fr_dot2<R>(load_fr<R>(v, r), load_fr<R>(m, r * cols + c), load_fr<R>(v, r + 1), load_fr<R>(m, (r + 1) * cols + c)));
+    if (r < rows) acc = fp_add<R>(acc, fp_mul<R>(load_fr<R>(v, r), load_fr<R>(m, r * cols + c)));
     store_fr<R>(out, c, acc);
   }
 };

@@ -1142,9 +1142,12 @@ int ntt_batch_impl(pcgpu_ctx *ctx, const void *in, size_t n_in, size_t count, ui
     plan = &ctx->ntt_plans.back();
   }
   const bool dev = (flags & PCGPU_DEVICE_PTRS) != 0;
-  if ((rc = ctx->stage.reserve(rt::Arena::pad(N * 32) + (dev ? 0 : rt::Arena::pad(count * (n_in ? n_in : 1) * 32) + rt::Arena::pad(count * N * 32)) + 4096)))
+  const bool multi_pass = plan->m2 != 0;   // rows longer than one block pass: scratch for all rows so both passes are single launches
+  if ((rc = ctx->stage.reserve(rt::Arena::pad(N * 32) + (multi_pass ? rt::Arena::pad(count * N * 32) : 0) +
+                               (dev ? 0 : rt::Arena::pad(count * (n_in ? n_in : 1) * 32) + rt::Arena::pad(count * N * 32)) + 4096)))
     return rc;
   uint32_t *tmp = ctx->stage.take<uint32_t>(N * 8);
+  uint32_t *tmp_rows = multi_pass ? ctx->stage.take<uint32_t>(count * N * 8) : nullptr;
   const uint32_t *d_in = (const uint32_t *)in; uint32_t *d_out = (uint32_t *)out;
   if (!dev) {
     uint32_t *ti = ctx->stage.take<uint32_t>(count * (n_in ? n_in : 1) * 8); d_out = ctx->stage.take<uint32_t>(count * N * 8);
@@ -1152,7 +1155,7 @@ int ntt_batch_impl(pcgpu_ctx *ctx, const void *in, size_t n_in, size_t count, ui
     d_in = ti;
   }
   ctx->prof.begin(9, st);
-  if ((rc = ntt_run_batch<R>(*plan, d_in, n_in, count, d_out, tmp, st))) return rc;
+  if ((rc = ntt_run_batch<R>(*plan, d_in, n_in, count, d_out, tmp, st, tmp_rows))) return rc;
   ctx->prof.end(9, st);
   if (!dev && (rc = rt::copy_d2h(out, d_out, count * N * 32, st))) return rc;
   rc = rt::stream_sync(st);
@@ -1257,11 +1260,13 @@ int lincode_commit_impl(pcgpu_ctx *ctx, const void *mat, size_t n_rows, size_t n
     plan = &ctx->ntt_plans.back();
   }
   const uint64_t P = N;   // the extended width is a power of two already
-  size_t need = rt::Arena::pad(N * 32) + rt::Arena::pad(N * 32) + rt::Arena::pad((P - 1) * 32) + 4096;
+  const bool multi_pass = plan->m2 != 0;
+  size_t need = rt::Arena::pad(N * 32) + rt::Arena::pad(N * 32) + rt::Arena::pad((P - 1) * 32) + (multi_pass ? rt::Arena::pad(n_rows * N * 32) : 0) + 4096;
   if (!dev) need += rt::Arena::pad(n_rows * (n_cols ? n_cols : 1) * 32);
   if (!(dev && out_ext)) need += rt::Arena::pad(n_rows * N * 32);
   if ((rc = ctx->stage.reserve(need))) return rc;
   uint32_t *tmp = ctx->stage.take<uint32_t>(N * 8);
+  uint32_t *tmp_rows = multi_pass ? ctx->stage.take<uint32_t>(n_rows * N * 8) : nullptr;
   uint32_t *d_leaves = (dev && out_leaves) ? (uint32_t *)out_leaves : ctx->stage.take<uint32_t>(N * 8);
   uint32_t *d_nodes = (dev && out_nodes) ? (uint32_t *)out_nodes : ctx->stage.take<uint32_t>((P - 1) * 8);
   uint32_t *d_ext = (dev && out_ext) ? (uint32_t *)out_ext : ctx->stage.take<uint32_t>(n_rows * N * 8);
@@ -1272,7 +1277,7 @@ int lincode_commit_impl(pcgpu_ctx *ctx, const void *mat, size_t n_rows, size_t n
     d_in = ti;
   }
   ctx->prof.begin(9, st);
-  if ((rc = ntt_run_batch<R>(*plan, d_in, n_cols, n_rows, d_ext, tmp, st))) return rc;
+  if ((rc = ntt_run_batch<R>(*plan, d_in, n_cols, n_rows, d_ext, tmp, st, tmp_rows))) return rc;
   ctx->prof.end(9, st);
   ctx->prof.begin(14, st);
   if ((rc = hash_columns_device<C>(d_ext, n_rows, N, hash, true, d_leaves, st))) return rc;

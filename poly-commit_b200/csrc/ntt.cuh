@@ -80,8 +80,13 @@ struct NttBlockBody {
   const uint32_t *scale;                    // optional final factor
   uint64_t batch_off;                       // global index of local batch 0 (sharded passes); enters the step-2 twiddle only
   uint32_t i_valid;                         // elements i >= i_valid of every batch read as zero (row-batched transforms)
-  PCGPU_KERNEL_DEV void operator()(size_t batch, uint32_t *smem) const {
+  // several independent transforms ("rows") in one launch: block = row * batches_per_row + batch; 0 = a single transform
+  uint64_t batches_per_row = 0, in_row_stride = 0, out_row_stride = 0;
+  PCGPU_KERNEL_DEV void operator()(size_t blk, uint32_t *smem) const {
     const uint32_t M = 1u << m;
+    const uint64_t row = batches_per_row ? blk / batches_per_row : 0, batch = batches_per_row ? blk % batches_per_row : blk;
+    const uint32_t *in = this->in + 8 * row * in_row_stride;
+    uint32_t *out = this->out + 8 * row * out_row_stride;
     PCGPU_BLOCK_FOR(i, M) {
       uint64_t idx = batch * in_batch_stride + (uint64_t)i * in_stride;
       Fp<R> v = (idx < n_valid && (uint32_t)i < i_valid) ? load_fr<R>(in, idx) : Fp<R>::zero();
@@ -244,11 +249,24 @@ inline int ntt_run_pass1_peer(const NttPlan &p, uint64_t lo, uint64_t count, con
 // block pass go out as ONE launch of `count` blocks; longer rows run the four-step passes row by row (each pass already
 // fills the device).  tmp: N elements, used only when m2 != 0.
 template <class R>
-inline int ntt_run_batch(const NttPlan &p, const uint32_t *in, size_t n_in, size_t count, uint32_t *out, uint32_t *tmp, rt::stream_t st) {
+inline int ntt_run_batch(const NttPlan &p, const uint32_t *in, size_t n_in, size_t count, uint32_t *out, uint32_t *tmp, rt::stream_t st,
+                         uint32_t *tmp_rows = nullptr) {
   const uint64_t N = (uint64_t)1 << p.logn;
   if (p.m2 == 0) {
     NttBlockBody<R> b{in, out, p.m1, 1, n_in, 1, N, (uint64_t)count * n_in, p.tw1, p.lo, p.hi, 0, p.scale, 0, (uint32_t)n_in};
     return rt::launch_blocks<256>(b, count, (size_t)N * 32, st);
+  }
+  // four-step rows: all rows' pass 1 in one launch (count * N2 column blocks), all rows' pass 2 in another, through a
+  // scratch matrix of count * N elements (`tmp_rows`); without scratch the rows run one after another
+  const uint64_t N1 = (uint64_t)1 << p.m1, N2 = (uint64_t)1 << p.m2;
+  if (tmp_rows) {
+    NttBlockBody<R> b1{in, tmp_rows, p.m1, N2, 1, N2, 1, n_in, p.tw1, p.lo, p.hi, 1, nullptr, 0, ~0u};
+    b1.batches_per_row = N2; b1.in_row_stride = n_in; b1.out_row_stride = N;
+    int rc = rt::launch_blocks<256>(b1, count * N2, (size_t)N1 * 32, st);
+    if (rc) return rc;
+    NttBlockBody<R> b2{tmp_rows, out, p.m2, 1, N2, N1, 1, N1 * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0, ~0u};
+    b2.batches_per_row = N1; b2.in_row_stride = N; b2.out_row_stride = N;
+    return rt::launch_blocks<256>(b2, count * N1, (size_t)N2 * 32, st);
   }
   for (size_t r = 0; r < count; r++) {
     int rc = ntt_run<R>(p, in + r * n_in * 8, n_in, out + r * N * 8, tmp, st);

@@ -1238,3 +1238,16 @@ def test_sample_generators(eng, pc, cname, name):
     assert C.points_from_limbs(got) == exp
     assert all(C.on_curve(P) for P in exp) and len(set(exp)) == n
     assert (eng.g1_sample_generators(C.id, name, 3, first_index=20) == got[15:18]).all()
+
+
+@pytest.mark.parametrize("cname,logn,n_in,count", [("bls12_381", 12, 4000, 3), ("bn254", 13, 8192, 2), ("pallas", 12, 1, 2)])
+def test_ntt_batch_long_rows(eng, cname, logn, n_in, count):
+    """rows longer than one block pass (four-step per row): all rows' pass 1 in one launch, all rows' pass 2 in another ==
+    one transform per row (forward and inverse)"""
+    C = pyref.Curve(cname)
+    rows = util.rand_fr(cname, count * n_in, seed=400 + logn, mont=True).reshape(count, n_in, 4)
+    for inverse in (False, True):
+        got = eng.ntt_batch(C.id, rows, logn, inverse=inverse)
+        for r in range(count):
+            assert (got[r] == eng.ntt(C.id, rows[r], logn, inverse=inverse)).all()
+    assert (eng.ntt_batch(C.id, rows, logn)[0] == orc.fr_ntt(C.id, rows[0], logn)).all()
