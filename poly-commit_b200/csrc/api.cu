@@ -45,6 +45,12 @@ extern "C" int pcgpu_init(int device, pcgpu_ctx **out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PCGPU_E_CUDA;
   if (prop.major != 10) return PCGPU_E_CUDA;  // built for sm_100a only; no other code path exists
   if (cudaSetDevice(device) != cudaSuccess) return PCGPU_E_CUDA;
+  // L2 fetch granularity hint: the table gathers of the pair rounds read ONE 64-byte half record (x in pass 1, y in pass 2)
+  // per access; at the default granularity every such miss moves a whole 128-byte line from DRAM (ncu: 680 B read per slot).
+  if (const char *e = getenv("PCGPU_L2_FETCH_GRANULARITY")) {
+    int v = atoi(e);
+    if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+  }
 #endif
   pcgpu_ctx *ctx = new (std::nothrow) pcgpu_ctx();
   if (!ctx) return PCGPU_E_OOM;
@@ -695,7 +701,7 @@ extern "C" int pcgpu_kzg_commit_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_
   });
 }
 
-enum { PCGPU_COMMIT_OPEN_WAYS = 2, PCGPU_COMMIT_OPEN_MAX_WAYS = 4 };   // polynomials in flight (two MSM pipelines each)
+enum { PCGPU_COMMIT_OPEN_WAYS = 2, PCGPU_COMMIT_OPEN_MAX_WAYS = 4, PCGPU_BATCH_PAIR_TDIV = 1 };   // polynomials in flight (two MSM pipelines each)
 
 extern "C" int pcgpu_kzg_commit_open_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *const *coeffs, const size_t *n,
                                            size_t count, const void *z, uint32_t flags, void *out_comm_xy, uint8_t *out_comm_inf,
@@ -710,8 +716,13 @@ extern "C" int pcgpu_kzg_commit_open_batch(pcgpu_ctx *ctx, const pcgpu_srs *powe
   if (rc) return rc;
   const size_t psz = (powers_of_g->curve == PCGPU_BLS12_381 ? 6 : 4) * 16;
   int rcs[PCGPU_COMMIT_OPEN_MAX_WAYS] = {PCGPU_OK, PCGPU_OK, PCGPU_OK, PCGPU_OK};
+  // throughput mode of the pair rounds while several pipelines are in flight (msm.cuh); PCGPU_BATCH_TDIV overrides
+  uint32_t tdiv = ways >= 2 ? PCGPU_BATCH_PAIR_TDIV : 1;
+  if (const char *e = getenv("PCGPU_BATCH_TDIV")) { int v = atoi(e); if (v >= 1 && v <= 8) tdiv = (uint32_t)v; }
   auto work = [&](size_t w) {
     pcgpu_ctx *a = w == 0 ? ctx : ctx->siblings[2 * w - 1], *b = ctx->siblings[w == 0 ? 0 : 2 * w];
+    a->pair_tdiv = tdiv; b->pair_tdiv = tdiv;
+    struct Restore { pcgpu_ctx *a, *b; ~Restore() { a->pair_tdiv = 1; b->pair_tdiv = 1; } } restore{a, b};
     for (size_t i = w; i < count; i += ways) {
       int r = commit_open_pair(a, b, powers_of_g, coeffs[i], n[i], (const char *)z, flags, (char *)out_comm_xy + i * psz,
                                out_comm_inf ? out_comm_inf + i : nullptr, (char *)out_w_xy + i * psz, out_w_inf ? out_w_inf + i : nullptr);

@@ -140,6 +140,61 @@ struct DivChunkWriteBody {
   }
 };
 
+// Chunk carries in ONE launch (replaces the fold / carry levels above for up to DIV_SCAN_BLOCK * 4096 chunks): the chunk values
+// obey  out_c = local_c + z^K * out_{c+1}  (out beyond the top chunk = 0), a reverse linear recurrence.  One block: thread t walks
+// its segment of S consecutive chunks (Horner, top down), the DIV_SCAN_BLOCK segment values are combined by a reverse
+// Hillis-Steele scan in shared memory (E_t += W^(2^k) E_(t + 2^k), W = z^(K S)), and every thread replays its segment writing
+// the value that ENTERS each chunk (`carry`), which DivChunkWriteBody consumes.  The value leaving chunk 0 is the remainder p(z).
+enum { DIV_SCAN_BLOCK = 1024 };
+template <class R>
+struct DivBlockScanBody {
+  const uint32_t *local; size_t nchunks; const uint32_t *z; uint32_t *carry; uint32_t *rem;
+  PCGPU_KERNEL_DEV void operator()(size_t, uint32_t *smem) const {
+    const size_t S = (nchunks + DIV_SCAN_BLOCK - 1) / DIV_SCAN_BLOCK;     // chunks per thread
+    uint32_t *bufA = smem, *bufB = smem + 8 * DIV_SCAN_BLOCK, *pw = smem + 16 * DIV_SCAN_BLOCK;   // pw[0] = z^K, pw[1] = W^(2^k)
+    PCGPU_BLOCK_FOR(t, 1) {
+      Fp<R> a = load_fr<R>(z, 0);
+      for (int k = DIV_K; k > 1; k >>= 1) a = fp_sqr<R>(a);
+      store_fr<R>(pw, 0, a);                                              // z^K
+      Fp<R> w = Fp<R>::one(), b = a;                                      // W = (z^K)^S by square-and-multiply
+      for (size_t e = S; e; e >>= 1) { if (e & 1) w = fp_mul<R>(w, b); b = fp_sqr<R>(b); }
+      store_fr<R>(pw, 1, w);
+    }
+    PCGPU_BLOCK_SYNC();
+    PCGPU_BLOCK_FOR(t, DIV_SCAN_BLOCK) {
+      const size_t lo = (size_t)t * S, hi = lo + S < nchunks ? lo + S : nchunks;
+      const Fp<R> zk = load_fr<R>(pw, 0);
+      Fp<R> acc = Fp<R>::zero();
+      for (size_t c = hi; c-- > lo;) acc = fp_add<R>(fp_mul<R>(acc, zk), load_fr<R>(local, c));
+      store_fr<R>(bufA, t, acc);
+    }
+    PCGPU_BLOCK_SYNC();
+    uint32_t *x = bufA, *y = bufB;
+    for (uint32_t d = 1; d < DIV_SCAN_BLOCK; d <<= 1) {
+      PCGPU_BLOCK_FOR(t, DIV_SCAN_BLOCK) {
+        Fp<R> v = load_fr<R>(x, t);
+        if (t + d < DIV_SCAN_BLOCK) v = fp_add<R>(v, fp_mul<R>(load_fr<R>(pw, 1), load_fr<R>(x, t + d)));
+        store_fr<R>(y, t, v);
+      }
+      PCGPU_BLOCK_SYNC();
+      PCGPU_BLOCK_FOR(t, 1) { store_fr<R>(pw, 1, fp_sqr<R>(load_fr<R>(pw, 1))); }
+      PCGPU_BLOCK_SYNC();
+      uint32_t *tmp = x; x = y; y = tmp;
+    }
+    // x[t] = value leaving segment t's lowest chunk; the value entering segment t from above is x[t + 1]
+    PCGPU_BLOCK_FOR(t, DIV_SCAN_BLOCK) {
+      const size_t lo = (size_t)t * S, hi = lo + S < nchunks ? lo + S : nchunks;
+      const Fp<R> zk = load_fr<R>(pw, 0);
+      Fp<R> in = t + 1 < DIV_SCAN_BLOCK ? load_fr<R>(x, t + 1) : Fp<R>::zero();
+      for (size_t c = hi; c-- > lo;) {
+        store_fr<R>(carry, c, in);
+        in = fp_add<R>(fp_mul<R>(in, zk), load_fr<R>(local, c));
+      }
+      if (t == 0 && rem) store_fr<R>(rem, 0, in);
+    }
+  }
+};
+
 inline size_t div_scratch_words(size_t n) {
   size_t cnt = (n + DIV_K - 1) / DIV_K, tot = 0;
   for (int l = 0; l < DIV_MAX_LEVELS; l++) { tot += 2 * cnt; if (cnt <= DIV_F) break; cnt = (cnt + DIV_F - 1) / DIV_F; }
@@ -160,6 +215,12 @@ inline int fr_div_linear(const uint32_t *p, size_t n, const uint32_t *z, uint32_
     if (c <= DIV_F || levels == DIV_MAX_LEVELS) break;
   }
   int rc;
+  if (cnt[0] <= (size_t)DIV_SCAN_BLOCK * 4096) {
+    // three launches: chunk values, ONE block for all the carries, chunk replay
+    if ((rc = rt::launch<128>(DivChunkLocalBody<R>{p, n, z, local[0]}, cnt[0], st))) return rc;
+    if ((rc = rt::launch_blocks<DIV_SCAN_BLOCK>(DivBlockScanBody<R>{local[0], cnt[0], z, carry[0], rem}, 1, (16 * DIV_SCAN_BLOCK + 32) * 4, st))) return rc;
+    return rt::launch<128>(DivChunkWriteBody<R>{p, n, z, carry[0], q}, cnt[0], st);
+  }
   if ((rc = rt::launch<32>(DivPowersBody<R>{z, zp, (uint32_t)levels}, 1, st))) return rc;
   if ((rc = rt::launch<128>(DivChunkLocalBody<R>{p, n, z, local[0]}, cnt[0], st))) return rc;
   for (int l = 1; l < levels; l++)

@@ -78,6 +78,7 @@ struct pcgpu_ctx {
   rt::Arena msm_arena, stage;
   rt::Arena ipa_arena;             // state of the (one) InnerProductArgPC::open in progress on this context; reused across opens
   bool ipa_active = false;
+  uint32_t pair_tdiv = 1;          // set by the batch entry points while several pipelines are in flight (msm_run)
   void *d_slots;    // 8 XYZZ result slots + 1 affine + err word, generously sized
   Prof prof;
   uint32_t *d_pow2[3] = {nullptr, nullptr, nullptr};  // fp_inv_gcd tables (Fq), per curve
@@ -252,7 +253,7 @@ int msm_device_planes(pcgpu_ctx *ctx, const pcgpu_srs *srs, size_t base_offset, 
     if (const char *e = getenv("PCGPU_MSM_C")) { int v = atoi(e); if (v >= 8 && v <= 22) c = (uint32_t)v; }   // tuning / test knob
   }
   MsmGeom g = msm_geometry(n, c, groups, C::Fr::BITS, mont, srs->n, base_offset);
-  g.pt_words = pt_words; g.y_words = y_words;
+  g.pt_words = pt_words; g.y_words = y_words; g.pair_tdiv = ctx->pair_tdiv;
   int rc;
   // batched-affine rounds while buckets hold >= 64 points and a round still gives every thread >= 16 additions
   {

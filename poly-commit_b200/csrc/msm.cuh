@@ -47,6 +47,7 @@ struct MsmGeom {
                           // 2^h * sum_hi hi * R_hi + sum_lo (lo+1) * C_lo over row sums R and column sums C (large c)
   uint32_t pt_words;      // table record stride in 32-bit words (2N raw; 32 for 128-byte aligned BLS12-381 records)
   uint32_t y_words;       // offset of y inside a record, in words (N raw; 16 in the aligned BLS12-381 layout)
+  uint32_t pair_tdiv;     // the pair-round kernel runs with 1 / pair_tdiv of a full wave of threads (see msm_run)
 };
 
 enum : uint32_t { ENTRY_SIGN = 0x80000000u, ENTRY_GROUP_SHIFT = 26, ENTRY_IDX_MASK = (1u << 26) - 1 };
@@ -556,6 +557,7 @@ inline MsmGeom msm_geometry(size_t n, uint32_t c, uint32_t groups, uint32_t scal
   g.affine_rounds = 0;
   g.h_split = (c - 1) / 2;
   g.pt_words = 0; g.y_words = 0;  // set by the caller (table_layout)
+  g.pair_tdiv = 1;
   return g;
 }
 
@@ -682,7 +684,13 @@ inline int msm_run(const uint32_t *tables, const MsmGeom &g, const uint32_t *d_s
     size_t Tmax = 0;
     if ((rc = msm_pair_oneshot_threads<C>(&Tmax))) return rc;
     if (Tmax > (1u << 20)) Tmax = 1u << 20;
-    if (const char *e = getenv("PCGPU_MSM_AFFINE_TDIV")) { int v = atoi(e); if (v >= 1 && v <= 16) Tmax = (Tmax / v + 127) / 128 * 128; }  // tuning knob
+    // Throughput mode (several MSM pipelines in flight on sibling streams): half a wave per pair kernel, so that the pair kernels
+    // of TWO pipelines are co-resident on every SM -- a full wave owns the whole register file -- and the DRAM-bound pass 1 and
+    // the ALU-bound inversion of one overlap the multiply-bound pass 2 of the other; every thread then covers twice the slots
+    // with the same single inversion per round.
+    uint32_t tdiv = g.pair_tdiv ? g.pair_tdiv : 1;
+    if (const char *e = getenv("PCGPU_MSM_AFFINE_TDIV")) { int v = atoi(e); if (v >= 1 && v <= 16) tdiv = (uint32_t)v; }  // tuning knob
+    if (tdiv > 1) Tmax = (Tmax / tdiv + 127) / 128 * 128;
     prof.begin(11, st);
     const uint32_t *off_in = offsets;
     size_t bound = max_entries;

@@ -35,11 +35,8 @@ def main():
     z = params.random_fr(cid, 1, 4)[0]
     fl = pc.SCALARS_MONT | pc.DEVICE_PTRS
     ref = None
-    variants = [dict(PCGPU_SRS_C="16", PCGPU_PAIR_MODE="0"), dict(PCGPU_SRS_C="16", PCGPU_PAIR_MODE="1"),
-                dict(PCGPU_SRS_C="17", PCGPU_PAIR_MODE="0"), dict(PCGPU_SRS_C="17", PCGPU_PAIR_MODE="1"),
-                dict(PCGPU_SRS_C="17", PCGPU_PAIR_MODE="1", PCGPU_PAIR_K="16"), dict(PCGPU_SRS_C="17", PCGPU_PAIR_MODE="1", PCGPU_PAIR_K="32"),
-                dict(PCGPU_SRS_C="17", PCGPU_PAIR_MODE="1", PCGPU_MSM_AFFINE_ROUNDS="4"),
-                dict(PCGPU_SRS_C="18", PCGPU_PAIR_MODE="1")]
+    variants = [dict(PCGPU_SRS_C="16", PCGPU_PAIR_MODE="0"), dict(PCGPU_SRS_C="17", PCGPU_PAIR_MODE="0"),
+                dict(PCGPU_SRS_C="17", PCGPU_PAIR_MODE="0", PCGPU_MSM_AFFINE_ROUNDS="4")]
     knobs = ("PCGPU_SRS_C", "PCGPU_PAIR_MODE", "PCGPU_PAIR_K", "PCGPU_MSM_AFFINE_ROUNDS")
     srs_cache = {}
     for v in variants:

@@ -475,7 +475,7 @@ def test_fixed_base_mul(eng, cname):
 
 
 @pytest.mark.parametrize("cname", util.CURVE_NAMES)
-@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 2048, 2049, 5000])
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 2048, 2049, 5000, 70001])
 def test_fr_div_linear(eng, cname, n):
     C = pyref.Curve(cname)
     p = util.rand_fr(cname, n, seed=20 + n, mont=True)

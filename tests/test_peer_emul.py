@@ -58,7 +58,7 @@ def _run_ranks(world, fn):
     return res
 
 
-@pytest.mark.parametrize("cname,n,world,flags_name", [("bls12_381", 13500, 3, "SRS_PRECOMPUTE"), ("bn254", 9000, 2, None),
+@pytest.mark.parametrize("cname,n,world,flags_name", [("bls12_381", 9000, 2, "SRS_PRECOMPUTE"), ("bn254", 12400, 3, None),
                                                       ("pallas", 50, 2, None)])
 def test_msm_peer_threads(pc, hostcheck_path, cname, n, world, flags_name):
     """index-sharded MSM with the point-sum pushed through the peer windows: folded tables (bit planes travel), unfolded
