@@ -701,7 +701,7 @@ extern "C" int pcgpu_kzg_commit_open(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_
   });
 }
 
-enum { PCGPU_COMMIT_OPEN_WAYS = 2, PCGPU_COMMIT_OPEN_MAX_WAYS = 4, PCGPU_BATCH_PAIR_TDIV = 1 };   // polynomials in flight (two MSM pipelines each)
+enum { PCGPU_COMMIT_OPEN_WAYS = 2, PCGPU_COMMIT_OPEN_MAX_WAYS = 4, PCGPU_BATCH_PAIR_TDIV = 2 };   // half-wave pair kernels in batch mode: +2.5 % (profiles/r02_l2_tdiv_ab.txt)   // polynomials in flight (two MSM pipelines each)
 
 extern "C" int pcgpu_kzg_commit_open_batch(pcgpu_ctx *ctx, const pcgpu_srs *powers_of_g, const void *const *coeffs, const size_t *n,
                                            size_t count, const void *z, uint32_t flags, void *out_comm_xy, uint8_t *out_comm_inf,

@@ -215,8 +215,9 @@ inline int fr_div_linear(const uint32_t *p, size_t n, const uint32_t *z, uint32_
     if (c <= DIV_F || levels == DIV_MAX_LEVELS) break;
   }
   int rc;
-  if (cnt[0] <= (size_t)DIV_SCAN_BLOCK * 4096) {
-    // three launches: chunk values, ONE block for all the carries, chunk replay
+  // (a three-launch variant with ONE block scanning all chunk carries was measured slower: 0.99 ms vs 0.36 ms at 2^22 -- 128
+  // dependent products per thread twice over; the level tree below keeps every chain at DIV_F = 32)
+  if (getenv("PCGPU_DIV_BLOCK_SCAN") && cnt[0] <= (size_t)DIV_SCAN_BLOCK * 4096) {
     if ((rc = rt::launch<128>(DivChunkLocalBody<R>{p, n, z, local[0]}, cnt[0], st))) return rc;
     if ((rc = rt::launch_blocks<DIV_SCAN_BLOCK>(DivBlockScanBody<R>{local[0], cnt[0], z, carry[0], rem}, 1, (16 * DIV_SCAN_BLOCK + 32) * 4, st))) return rc;
     return rt::launch<128>(DivChunkWriteBody<R>{p, n, z, carry[0], q}, cnt[0], st);
