@@ -195,10 +195,218 @@ struct DivBlockScanBody {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// Division by (X - z) in ONE pass over the coefficients: tiles of DIVT_TILE coefficients staged through shared memory
+// (coalesced 16-byte granules in and out, padded so that a thread's private run of DIVT_L elements is bank-conflict free),
+// chained from the top tile down by a decoupled look-back (every tile publishes its aggregate, then its inclusive value;
+// a warp inspects 32 predecessors at a time).  t_i = p_i + z t_(i+1), t_n = 0;  q[i-1] = t_i,  remainder = t_0.
+//   per element: 1 product in the local Horner walk + 1 in the fix-up  (t_i = local_i + z^(L-i) * carry_into_the_run),
+//   per thread:  7 products of the block scan + 1;   traffic: 32 B read + 32 B written per coefficient.
+// Tiles are handed out by an atomic ticket, highest tile first, so a tile's predecessors are always resident or finished.
+// ---------------------------------------------------------------------------------------------
+enum { DIVT_THREADS = 128, DIVT_L = 16, DIVT_TILE = DIVT_THREADS * DIVT_L, DIVT_WINDOW = 32,
+       DIVT_POW_Z = 0,                                   // z^0 .. z^L
+       DIVT_POW_W = DIVT_POW_Z + DIVT_L + 1,             // W^0 .. W^THREADS, W = z^L  (W^THREADS = z^TILE = Z)
+       DIVT_POW_ZT = DIVT_POW_W + DIVT_THREADS + 1,      // Z^0 .. Z^WINDOW
+       DIVT_POW_COUNT = DIVT_POW_ZT + DIVT_WINDOW + 1,
+       DIVT_SPIN_LIMIT = 1 << 24 };
+// shared memory: tile (TILE elements + one 16-byte pad per thread run) | scan ping | scan pong | look-back terms | misc words
+inline size_t divt_smem_bytes() { return (size_t)(2 * DIVT_TILE + DIVT_THREADS) * 16 + 2 * DIVT_THREADS * 32 + DIVT_WINDOW * 32 + 32 * 4 + 64; }
+
+template <class R>
+PCGPU_DEV Fp<R> fr_pow_u32(Fp<R> base, uint32_t e) {
+  Fp<R> acc = Fp<R>::one();
+  while (e) { if (e & 1) acc = fp_mul<R>(acc, base); e >>= 1; if (e) base = fp_sqr<R>(base); }
+  return acc;
+}
+template <class R>
+struct DivTilePowersBody {
+  const uint32_t *z; uint32_t *pw;
+  PCGPU_KERNEL_DEV void operator()(size_t k) const {
+    uint32_t e;
+    if (k < DIVT_POW_W) e = (uint32_t)k;
+    else if (k < DIVT_POW_ZT) e = (uint32_t)(k - DIVT_POW_W) * DIVT_L;
+    else e = (uint32_t)(k - DIVT_POW_ZT) * DIVT_TILE;
+    store_fr<R>(pw, k, fr_pow_u32<R>(load_fr<R>(z, 0), e));
+  }
+};
+
+// L2-only load of an element another block published (never a stale L1 line)
+template <class R>
+PCGPU_DEV Fp<R> load_fr_cg(const uint32_t *base, size_t i) {
+#if defined(__CUDA_ARCH__)
+  const uint4 *p = reinterpret_cast<const uint4 *>(base) + 2 * i;
+  uint4 lo = __ldcg(p), hi = __ldcg(p + 1);
+  Fp<R> v;
+  v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w; v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+  return v;
+#else
+  return load_fr<R>(base, i);
+#endif
+}
+PCGPU_DEV uint32_t divt_flag_load(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return *(const volatile uint32_t *)p;
+#endif
+}
+PCGPU_DEV void divt_flag_store(uint32_t *p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  *(volatile uint32_t *)p = v;
+#endif
+}
+
+template <class R>
+struct DivTileBody {
+  const uint32_t *p; size_t n; const uint32_t *z; const uint32_t *pw;
+  uint32_t *q; uint32_t *rem;
+  uint32_t *ctl;            // [0] ticket counter, [1] error flag, [2 .. 2 + ntiles) tile status: 0 nothing, 1 aggregate, 2 inclusive
+  uint32_t *agg, *inc;      // per tile
+  uint32_t ntiles;
+  PCGPU_DEV static uint32_t gpos(uint32_t e, uint32_t h) { return 2 * e + h + e / DIVT_L; }   // 16-byte granule of half h of element e
+  PCGPU_DEV static Fp<R> lds(const u32x4 *t, uint32_t e) {
+    u32x4 lo = t[gpos(e, 0)], hi = t[gpos(e, 1)];
+    Fp<R> v;
+    v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w; v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+    return v;
+  }
+  PCGPU_DEV static void sts(u32x4 *t, uint32_t e, const Fp<R> &v) {
+    u32x4 lo, hi;
+    lo.x = v.l[0]; lo.y = v.l[1]; lo.z = v.l[2]; lo.w = v.l[3]; hi.x = v.l[4]; hi.y = v.l[5]; hi.z = v.l[6]; hi.w = v.l[7];
+    t[gpos(e, 0)] = lo; t[gpos(e, 1)] = hi;
+  }
+  PCGPU_KERNEL_DEV void operator()(size_t, uint32_t *smem) const {
+    u32x4 *tile = reinterpret_cast<u32x4 *>(smem);
+    uint32_t *scanA = smem + (size_t)(2 * DIVT_TILE + DIVT_THREADS) * 4, *scanB = scanA + 8 * DIVT_THREADS;
+    uint32_t *terms = scanB + 8 * DIVT_THREADS;          // DIVT_WINDOW elements
+    uint32_t *misc = terms + 8 * DIVT_WINDOW;            // [0] tile index, [1 .. 1 + WINDOW) status seen by the look-back lanes
+    uint32_t *carry = misc + 40;                         // the value entering this tile from above (8 words)
+    PCGPU_BLOCK_FOR(i, 1) { misc[0] = ntiles - 1 - rt::atomic_add(ctl, 1u); }
+    PCGPU_BLOCK_SYNC();
+    const uint32_t tl = misc[0];
+    const size_t base = (size_t)tl * DIVT_TILE;
+    const u32x4 *p16 = reinterpret_cast<const u32x4 *>(p);
+    // ---- 1. tile -> shared memory (zero beyond n) ----
+    // (eight independent 16-byte loads in flight per thread before the first shared-memory store: the loop is latency-bound)
+    PCGPU_BLOCK_FOR(t, DIVT_THREADS) {
+      for (uint32_t kb = 0; kb < 2 * DIVT_L; kb += 8) {
+        u32x4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint32_t g = (kb + k) * DIVT_THREADS + t, e = g >> 1;
+          v[k].x = v[k].y = v[k].z = v[k].w = 0;
+          if (base + e < n) v[k] = p16[2 * base + g];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint32_t g = (kb + k) * DIVT_THREADS + t;
+          tile[gpos(g >> 1, g & 1)] = v[k];
+        }
+      }
+    }
+    PCGPU_BLOCK_SYNC();
+    // ---- 2. every thread: Horner walk down its run, local values in place, run aggregate to the scan buffer ----
+    PCGPU_BLOCK_FOR(t, DIVT_THREADS) {
+      const Fp<R> zz = load_fr<R>(pw, DIVT_POW_Z + 1);
+      Fp<R> acc = Fp<R>::zero();
+      for (uint32_t i = DIVT_L; i-- > 0;) {
+        const uint32_t e = t * DIVT_L + i;
+        acc = fp_add<R>(fp_mul<R>(acc, zz), lds(tile, e));
+        sts(tile, e, acc);
+      }
+      store_fr<R>(scanA, t, acc);
+    }
+    PCGPU_BLOCK_SYNC();
+    // ---- 3. reverse scan of the run aggregates: E_t = A_t + W E_(t+1)  (value leaving run t, nothing entering the tile) ----
+    uint32_t *x = scanA, *y = scanB;
+    for (uint32_t d = 1; d < DIVT_THREADS; d <<= 1) {
+      PCGPU_BLOCK_FOR(t, DIVT_THREADS) {
+        Fp<R> v = load_fr<R>(x, t);
+        if (t + d < DIVT_THREADS) v = fp_add<R>(v, fp_mul<R>(load_fr<R>(pw, DIVT_POW_W + d), load_fr<R>(x, t + d)));
+        store_fr<R>(y, t, v);
+      }
+      PCGPU_BLOCK_SYNC();
+      uint32_t *tmp = x; x = y; y = tmp;
+    }
+    // ---- 4. publish the aggregate, look back for the value entering the tile, publish the inclusive value ----
+    PCGPU_BLOCK_FOR(i, 1) {
+      store_fr<R>(agg, tl, load_fr<R>(x, 0));
+      store_fr<R>(carry, 0, Fp<R>::zero());
+      if (tl + 1 == ntiles) { store_fr<R>(inc, tl, load_fr<R>(x, 0)); divt_flag_store(ctl + 2 + tl, 2u); }
+      else divt_flag_store(ctl + 2 + tl, 1u);
+    }
+    PCGPU_BLOCK_SYNC();
+    if (tl + 1 != ntiles) {
+      // window w covers tiles tl + 1 + 32 w + j, j < 32; term_j = Z^j * (inclusive or aggregate value); the first tile that
+      // shows an inclusive value ends the walk.  `done` and the running sums live in shared memory (misc / carry / terms).
+      for (uint32_t w = 0;; w++) {
+        PCGPU_BLOCK_FOR(j, DIVT_WINDOW) {
+          const uint32_t tj = tl + 1 + w * DIVT_WINDOW + j;
+          uint32_t f = 2;
+          Fp<R> v = Fp<R>::zero();
+          if (tj < ntiles) {
+            f = divt_flag_load(ctl + 2 + tj);
+            for (uint32_t spin = 0; f == 0 && spin < DIVT_SPIN_LIMIT; spin++) f = divt_flag_load(ctl + 2 + tj);
+            if (f == 0) { rt::atomic_or(ctl + 1, 1u); f = 2; }            // give up rather than hang: the caller sees PCGPU_E_CUDA
+            else v = fp_mul<R>(load_fr<R>(pw, DIVT_POW_ZT + j), load_fr_cg<R>(f == 2 ? inc : agg, tj));
+          }
+          misc[1 + j] = f;
+          store_fr<R>(terms, j, v);
+        }
+        PCGPU_BLOCK_SYNC();
+        PCGPU_BLOCK_FOR(i, 1) {
+          Fp<R> sum = Fp<R>::zero();
+          uint32_t done = 0;
+          for (uint32_t j = 0; j < DIVT_WINDOW && !done; j++) { sum = fp_add<R>(sum, load_fr<R>(terms, j)); done = misc[1 + j] == 2; }
+          // carry += (Z^32)^w * sum: the factor is kept in scanB-free space: y[0] holds (Z^32)^w (set to one at w = 0)
+          Fp<R> f = w ? load_fr<R>(y, 0) : Fp<R>::one();
+          store_fr<R>(carry, 0, fp_add<R>(load_fr<R>(carry, 0), w ? fp_mul<R>(f, sum) : sum));
+          store_fr<R>(y, 0, fp_mul<R>(f, load_fr<R>(pw, DIVT_POW_ZT + DIVT_WINDOW)));
+          misc[34] = done;
+        }
+        PCGPU_BLOCK_SYNC();
+        if (misc[34]) break;
+      }
+      PCGPU_BLOCK_FOR(i, 1) {
+        // inclusive value = E_0 + Z * carry
+        Fp<R> v = fp_add<R>(load_fr<R>(x, 0), fp_mul<R>(load_fr<R>(pw, DIVT_POW_W + DIVT_THREADS), load_fr<R>(carry, 0)));
+        store_fr<R>(inc, tl, v);
+        divt_flag_store(ctl + 2 + tl, 2u);
+      }
+    }
+    // ---- 5. fix-up: the value entering run t is E_(t+1) + W^(THREADS-1-t) * carry; t_i = local_i + z^(L-i) * that ----
+    PCGPU_BLOCK_FOR(t, DIVT_THREADS) {
+      Fp<R> c = fp_mul<R>(load_fr<R>(pw, DIVT_POW_W + (DIVT_THREADS - 1 - t)), load_fr<R>(carry, 0));
+      if (t + 1 < DIVT_THREADS) c = fp_add<R>(c, load_fr<R>(x, t + 1));
+      for (uint32_t i = 0; i < DIVT_L; i++) {
+        const uint32_t e = t * DIVT_L + i;
+        sts(tile, e, fp_add<R>(lds(tile, e), fp_mul<R>(load_fr<R>(pw, DIVT_POW_Z + DIVT_L - i), c)));
+      }
+    }
+    PCGPU_BLOCK_SYNC();
+    // ---- 6. shared memory -> q (shifted by one coefficient), remainder ----
+    u32x4 *q16 = reinterpret_cast<u32x4 *>(q), *rem16 = reinterpret_cast<u32x4 *>(rem);
+    PCGPU_BLOCK_FOR(g, 2 * DIVT_TILE) {
+      const uint32_t e = g >> 1, h = g & 1;
+      const size_t idx = base + e;
+      if (idx >= n) continue;
+      if (idx == 0) rem16[h] = tile[gpos(e, h)];
+      else q16[2 * (idx - 1) + h] = tile[gpos(e, h)];
+    }
+  }
+};
+
 inline size_t div_scratch_words(size_t n) {
   size_t cnt = (n + DIV_K - 1) / DIV_K, tot = 0;
   for (int l = 0; l < DIV_MAX_LEVELS; l++) { tot += 2 * cnt; if (cnt <= DIV_F) break; cnt = (cnt + DIV_F - 1) / DIV_F; }
-  return 8 * (tot + DIV_MAX_LEVELS + 4);
+  const size_t ntiles = (n + DIVT_TILE - 1) / DIVT_TILE;
+  return 8 * (tot + DIV_MAX_LEVELS + 4 + DIVT_POW_COUNT + 2 * ntiles + 4) + ntiles + 72;
 }
 
 // p: n coefficients, q: n-1 coefficients (n >= 1), rem: 1 element, z: 1 element; all device.
@@ -215,6 +423,18 @@ inline int fr_div_linear(const uint32_t *p, size_t n, const uint32_t *z, uint32_
     if (c <= DIV_F || levels == DIV_MAX_LEVELS) break;
   }
   int rc;
+  // one pass up to 2^21 coefficients (0.08 / 0.15 ms at 2^16 / 2^20 against 0.17 / 0.21 ms for the level tree below); beyond
+  // that the level tree's fewer products per coefficient win (0.35 against 0.41 ms at 2^22); PCGPU_DIV_MODE = tile | tree forces one
+  bool one_pass = n <= ((size_t)1 << 21);
+  if (const char *e = getenv("PCGPU_DIV_MODE")) one_pass = e[0] == 't' && e[1] == 'i';
+  if (one_pass) {
+    // one pass: powers (one small launch), control words cleared, tiles chained by a decoupled look-back
+    const uint32_t ntiles = (uint32_t)((n + DIVT_TILE - 1) / DIVT_TILE);
+    uint32_t *pw = scratch, *aggp = pw + 8 * DIVT_POW_COUNT, *incp = aggp + 8 * (size_t)ntiles, *ctl = incp + 8 * (size_t)ntiles;
+    if ((rc = rt::dev_memset(ctl, 0, (2 + (size_t)ntiles) * 4, st))) return rc;
+    if ((rc = rt::launch<64>(DivTilePowersBody<R>{z, pw}, DIVT_POW_COUNT, st))) return rc;
+    return rt::launch_blocks<DIVT_THREADS>(DivTileBody<R>{p, n, z, pw, q, rem, ctl, aggp, incp, ntiles}, ntiles, divt_smem_bytes(), st);
+  }
   // (a three-launch variant with ONE block scanning all chunk carries was measured slower: 0.99 ms vs 0.36 ms at 2^22 -- 128
   // dependent products per thread twice over; the level tree below keeps every chain at DIV_F = 32)
   if (getenv("PCGPU_DIV_BLOCK_SCAN") && cnt[0] <= (size_t)DIV_SCAN_BLOCK * 4096) {

@@ -17,7 +17,10 @@
 
 namespace pcgpu {
 
-enum { NTT_MAX_LOG_BLOCK = 11, NTT_LO_BITS = 10 };
+#ifndef PCGPU_NTT_MIN_BLOCKS
+#define PCGPU_NTT_MIN_BLOCKS 4
+#endif
+enum { NTT_MAX_LOG_BLOCK = 11, NTT_LO_BITS = 10, NTT_BLOCK = 128, NTT_MIN_BLOCKS = PCGPU_NTT_MIN_BLOCKS };
 
 template <class R>
 PCGPU_DEV Fp<R> fp_pow_u64(Fp<R> base, uint64_t e) {
@@ -69,6 +72,80 @@ PCGPU_DEV uint32_t bitrev32(uint32_t v, uint32_t bits) {
   return r;
 }
 
+// ---- the butterfly stages of one length-M transform held in shared memory -----------------------------------------------
+// Layout: limb-major planes of NTT_PLANE(M) words, element i at word NTT_POS(i) = i + i/8 of every plane (the padding keeps
+// the register rounds below bank-conflict free: a thread's 8 elements are 2^s0 apart, consecutive threads 1 or 8 * 2^s0 apart).
+// The log2(M) radix-2 stages run in ROUNDS of K <= 3 stages: a thread pulls 2^K elements into registers, runs the K stages
+// on them (12 butterflies for K = 3) and writes them back -- one shared-memory round trip and one barrier per round instead of
+// per stage.  In the first round the twiddles w^0 (7 of the 12) are skipped at compile time.
+PCGPU_DEV uint32_t ntt_pos(uint32_t i) { return i + (i >> 3); }
+PCGPU_DEV uint32_t ntt_plane(uint32_t M) { return M + (M >> 3) + 1; }
+inline size_t ntt_smem_bytes(uint64_t M) { return (size_t)(M + (M >> 3) + 1) * 32; }
+
+template <class R, int K, bool FIRST>
+PCGPU_DEV void ntt_round(uint32_t *smem, uint32_t m, uint32_t s0, const uint32_t *tw, uint32_t item) {
+  constexpr int E = 1 << K;
+  const uint32_t P = ntt_plane(1u << m);
+  const uint32_t low = FIRST ? 0u : (item & ((1u << s0) - 1u)), high = FIRST ? item : (item >> s0);
+  const uint32_t base = (high << (s0 + K)) | low;
+  Fp<R> v[E];
+#pragma unroll
+  for (int j = 0; j < E; j++) {
+    const uint32_t q = ntt_pos(base + ((uint32_t)j << s0));
+#pragma unroll
+    for (int l = 0; l < 8; l++) v[j].l[l] = smem[l * P + q];
+  }
+#pragma unroll
+  for (int q = 0; q < K; q++) {                       // stage s0 + q: partners differ in bit q of j
+    const uint32_t s = s0 + q;
+#pragma unroll
+    for (int j = 0; j < E; j++) {
+      if (j & (1 << q)) continue;
+      const int j1 = j | (1 << q);
+      const uint32_t jl = (uint32_t)(j & ((1 << q) - 1));                 // index of the pair inside its 2^s block = low + jl * 2^s0
+      Fp<R> t = v[j1];
+      if (!(FIRST && jl == 0)) t = fp_mul<R>(t, load_fr<R>(tw, (size_t)(low + (jl << s0)) << (m - 1 - s)));
+      v[j1] = fp_sub<R>(v[j], t);
+      v[j] = fp_add<R>(v[j], t);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < E; j++) {
+    const uint32_t q = ntt_pos(base + ((uint32_t)j << s0));
+#pragma unroll
+    for (int l = 0; l < 8; l++) smem[l * P + q] = v[j].l[l];
+  }
+}
+
+template <class R>
+PCGPU_DEV void ntt_block_stages(uint32_t *smem, uint32_t m, const uint32_t *tw) {
+  const uint32_t M = 1u << m;
+  for (uint32_t s = 0; s < m;) {
+    const uint32_t left = m - s;
+    const uint32_t K = (left >= 5 || left == 3) ? 3u : (left == 4 ? 2u : left);   // 10 = 3+3+2+2, 11 = 3+3+3+2
+    if (s == 0) {
+      if (K == 3) { PCGPU_BLOCK_FOR(it, M >> 3) ntt_round<R, 3, true>(smem, m, 0, tw, it); }
+      else if (K == 2) { PCGPU_BLOCK_FOR(it, M >> 2) ntt_round<R, 2, true>(smem, m, 0, tw, it); }
+      else { PCGPU_BLOCK_FOR(it, M >> 1) ntt_round<R, 1, true>(smem, m, 0, tw, it); }
+    } else {
+      if (K == 3) { PCGPU_BLOCK_FOR(it, M >> 3) ntt_round<R, 3, false>(smem, m, s, tw, it); }
+      else if (K == 2) { PCGPU_BLOCK_FOR(it, M >> 2) ntt_round<R, 2, false>(smem, m, s, tw, it); }
+      else { PCGPU_BLOCK_FOR(it, M >> 1) ntt_round<R, 1, false>(smem, m, s, tw, it); }
+    }
+    PCGPU_BLOCK_SYNC();
+    s += K;
+  }
+}
+
+// launch of a block transform: NTT_BLOCK threads, 3 or 4 resident blocks per SM (168 / 128 registers; PCGPU_NTT_OCC, tuning knob)
+template <class Body>
+inline int ntt_launch(const Body &b, size_t nblocks, size_t smem_bytes, rt::stream_t st) {
+  int occ = NTT_MIN_BLOCKS;
+  if (const char *e = getenv("PCGPU_NTT_OCC")) { int v = atoi(e); if (v == 3 || v == 4) occ = v; }
+  if (occ == 3) return rt::launch_blocks_occ<NTT_BLOCK, 3>(b, nblocks, smem_bytes, st);
+  return rt::launch_blocks_occ<NTT_BLOCK, 4>(b, nblocks, smem_bytes, st);
+}
+
 template <class R>
 struct NttBlockBody {
   const uint32_t *in; uint32_t *out;
@@ -83,37 +160,23 @@ struct NttBlockBody {
   // several independent transforms ("rows") in one launch: block = row * batches_per_row + batch; 0 = a single transform
   uint64_t batches_per_row = 0, in_row_stride = 0, out_row_stride = 0;
   PCGPU_KERNEL_DEV void operator()(size_t blk, uint32_t *smem) const {
-    const uint32_t M = 1u << m;
+    const uint32_t M = 1u << m, P = ntt_plane(M);
     const uint64_t row = batches_per_row ? blk / batches_per_row : 0, batch = batches_per_row ? blk % batches_per_row : blk;
     const uint32_t *in = this->in + 8 * row * in_row_stride;
     uint32_t *out = this->out + 8 * row * out_row_stride;
     PCGPU_BLOCK_FOR(i, M) {
       uint64_t idx = batch * in_batch_stride + (uint64_t)i * in_stride;
       Fp<R> v = (idx < n_valid && (uint32_t)i < i_valid) ? load_fr<R>(in, idx) : Fp<R>::zero();
-      uint32_t r = bitrev32(i, m);
+      uint32_t r = ntt_pos(bitrev32(i, m));
 #pragma unroll
-      for (int l = 0; l < 8; l++) smem[l * M + r] = v.l[l];
+      for (int l = 0; l < 8; l++) smem[l * P + r] = v.l[l];
     }
     PCGPU_BLOCK_SYNC();
-    for (uint32_t s = 0; s < m; s++) {
-      const uint32_t half = 1u << s;
-      PCGPU_BLOCK_FOR(b, M / 2) {
-        uint32_t pos = b & (half - 1);
-        uint32_t i0 = ((b >> s) << (s + 1)) + pos, i1 = i0 + half;
-        Fp<R> a, t;
-#pragma unroll
-        for (int l = 0; l < 8; l++) { a.l[l] = smem[l * M + i0]; t.l[l] = smem[l * M + i1]; }
-        if (s) t = fp_mul<R>(t, load_fr<R>(tw, (size_t)pos << (m - 1 - s)));  // w_M^(pos * M / (2 half)); pos = 0 at s = 0
-        Fp<R> x = fp_add<R>(a, t), y = fp_sub<R>(a, t);
-#pragma unroll
-        for (int l = 0; l < 8; l++) { smem[l * M + i0] = x.l[l]; smem[l * M + i1] = y.l[l]; }
-      }
-      PCGPU_BLOCK_SYNC();
-    }
+    ntt_block_stages<R>(smem, m, tw);
     PCGPU_BLOCK_FOR(i, M) {
       Fp<R> v;
 #pragma unroll
-      for (int l = 0; l < 8; l++) v.l[l] = smem[l * M + i];
+      for (int l = 0; l < 8; l++) v.l[l] = smem[l * P + ntt_pos(i)];
       if (step2) {
         uint64_t e = (uint64_t)i * (batch + batch_off);
         if (e) v = fp_mul<R>(v, fp_mul<R>(load_fr<R>(hi, e >> NTT_LO_BITS), load_fr<R>(lo, e & ((1u << NTT_LO_BITS) - 1))));
@@ -139,35 +202,21 @@ struct NttBlockPeerBody {
   uint32_t rows;                             // N1 / world
   const uint32_t *tw, *lo, *hi;
   PCGPU_KERNEL_DEV void operator()(size_t batch, uint32_t *smem) const {
-    const uint32_t M = 1u << m;
+    const uint32_t M = 1u << m, P = ntt_plane(M);
     const uint64_t n2 = col_lo + batch;
     PCGPU_BLOCK_FOR(i, M) {
       uint64_t idx = n2 + (uint64_t)i * N2;
       Fp<R> v = idx < n_valid ? load_fr<R>(in, idx) : Fp<R>::zero();
-      uint32_t r = bitrev32(i, m);
+      uint32_t r = ntt_pos(bitrev32(i, m));
 #pragma unroll
-      for (int l = 0; l < 8; l++) smem[l * M + r] = v.l[l];
+      for (int l = 0; l < 8; l++) smem[l * P + r] = v.l[l];
     }
     PCGPU_BLOCK_SYNC();
-    for (uint32_t s = 0; s < m; s++) {
-      const uint32_t half = 1u << s;
-      PCGPU_BLOCK_FOR(b, M / 2) {
-        uint32_t pos = b & (half - 1);
-        uint32_t i0 = ((b >> s) << (s + 1)) + pos, i1 = i0 + half;
-        Fp<R> a, t;
-#pragma unroll
-        for (int l = 0; l < 8; l++) { a.l[l] = smem[l * M + i0]; t.l[l] = smem[l * M + i1]; }
-        if (s) t = fp_mul<R>(t, load_fr<R>(tw, (size_t)pos << (m - 1 - s)));
-        Fp<R> x = fp_add<R>(a, t), y = fp_sub<R>(a, t);
-#pragma unroll
-        for (int l = 0; l < 8; l++) { smem[l * M + i0] = x.l[l]; smem[l * M + i1] = y.l[l]; }
-      }
-      PCGPU_BLOCK_SYNC();
-    }
+    ntt_block_stages<R>(smem, m, tw);
     PCGPU_BLOCK_FOR(i, M) {
       Fp<R> v;
 #pragma unroll
-      for (int l = 0; l < 8; l++) v.l[l] = smem[l * M + i];
+      for (int l = 0; l < 8; l++) v.l[l] = smem[l * P + ntt_pos(i)];
       uint64_t e = (uint64_t)i * n2;
       if (e) v = fp_mul<R>(v, fp_mul<R>(load_fr<R>(hi, e >> NTT_LO_BITS), load_fr<R>(lo, e & ((1u << NTT_LO_BITS) - 1))));
       store_fr<R>(dst[i / rows], (uint64_t)(i % rows) * N2 + n2, v);
@@ -206,13 +255,13 @@ inline int ntt_run(const NttPlan &p, const uint32_t *in, size_t n_in, uint32_t *
   const uint64_t N1 = (uint64_t)1 << p.m1, N2 = (uint64_t)1 << p.m2;
   if (p.m2 == 0) {
     NttBlockBody<R> b{in, out, p.m1, 1, 0, 1, 0, n_in, p.tw1, p.lo, p.hi, 0, p.scale, 0, ~0u};
-    return rt::launch_blocks<256>(b, 1, (size_t)N1 * 32, st);
+    return ntt_launch(b, 1, ntt_smem_bytes(N1), st);
   }
   NttBlockBody<R> b1{in, tmp, p.m1, N2, 1, N2, 1, n_in, p.tw1, p.lo, p.hi, 1, nullptr, 0, ~0u};
-  int rc = rt::launch_blocks<256>(b1, N2, (size_t)N1 * 32, st);
+  int rc = ntt_launch(b1, N2, ntt_smem_bytes(N1), st);
   if (rc) return rc;
   NttBlockBody<R> b2{tmp, out, p.m2, 1, N2, N1, 1, N1 * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0, ~0u};
-  return rt::launch_blocks<256>(b2, N1, (size_t)N2 * 32, st);
+  return ntt_launch(b2, N1, ntt_smem_bytes(N2), st);
 }
 
 // One pass of the four-step transform on a slice of its batches -- the building block of the multi-GPU NTT:
@@ -226,10 +275,10 @@ inline int ntt_run_pass(const NttPlan &p, int which, uint64_t lo, uint64_t count
   const uint64_t N1 = (uint64_t)1 << p.m1, N2 = (uint64_t)1 << p.m2;
   if (which == 1) {
     NttBlockBody<R> b{in + 8 * lo, out, p.m1, N2, 1, count, 1, n_in > lo ? n_in - lo : 0, p.tw1, p.lo, p.hi, 1, nullptr, lo, ~0u};
-    return rt::launch_blocks<256>(b, count, (size_t)N1 * 32, st);
+    return ntt_launch(b, count, ntt_smem_bytes(N1), st);
   }
   NttBlockBody<R> b{in, out, p.m2, 1, N2, count, 1, count * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0, ~0u};
-  return rt::launch_blocks<256>(b, count, (size_t)N2 * 32, st);
+  return ntt_launch(b, count, ntt_smem_bytes(N2), st);
 }
 
 template <class R>
@@ -241,7 +290,7 @@ inline int ntt_run_pass1_peer(const NttPlan &p, uint64_t lo, uint64_t count, con
   for (uint32_t d = 0; d < NTT_MAX_PEERS; d++) b.dst[d] = d < world ? dst[d] : nullptr;
   b.m = p.m1; b.N2 = N2; b.n_valid = n_in; b.col_lo = lo; b.rows = (uint32_t)(N1 / world);
   b.tw = p.tw1; b.lo = p.lo; b.hi = p.hi;
-  return rt::launch_blocks<256>(b, count, (size_t)N1 * 32, st);
+  return ntt_launch(b, count, ntt_smem_bytes(N1), st);
 }
 
 // `count` independent transforms of rows laid out back to back (row r = in[r * n_in .. (r+1) * n_in), zero-padded to N) --
@@ -254,7 +303,7 @@ inline int ntt_run_batch(const NttPlan &p, const uint32_t *in, size_t n_in, size
   const uint64_t N = (uint64_t)1 << p.logn;
   if (p.m2 == 0) {
     NttBlockBody<R> b{in, out, p.m1, 1, n_in, 1, N, (uint64_t)count * n_in, p.tw1, p.lo, p.hi, 0, p.scale, 0, (uint32_t)n_in};
-    return rt::launch_blocks<256>(b, count, (size_t)N * 32, st);
+    return ntt_launch(b, count, ntt_smem_bytes(N), st);
   }
   // four-step rows: all rows' pass 1 in one launch (count * N2 column blocks), all rows' pass 2 in another, through a
   // scratch matrix of count * N elements (`tmp_rows`); without scratch the rows run one after another
@@ -262,11 +311,11 @@ inline int ntt_run_batch(const NttPlan &p, const uint32_t *in, size_t n_in, size
   if (tmp_rows) {
     NttBlockBody<R> b1{in, tmp_rows, p.m1, N2, 1, N2, 1, n_in, p.tw1, p.lo, p.hi, 1, nullptr, 0, ~0u};
     b1.batches_per_row = N2; b1.in_row_stride = n_in; b1.out_row_stride = N;
-    int rc = rt::launch_blocks<256>(b1, count * N2, (size_t)N1 * 32, st);
+    int rc = ntt_launch(b1, count * N2, ntt_smem_bytes(N1), st);
     if (rc) return rc;
     NttBlockBody<R> b2{tmp_rows, out, p.m2, 1, N2, N1, 1, N1 * N2, p.tw2, p.lo, p.hi, 0, p.scale, 0, ~0u};
     b2.batches_per_row = N1; b2.in_row_stride = N; b2.out_row_stride = N;
-    return rt::launch_blocks<256>(b2, count * N1, (size_t)N2 * 32, st);
+    return ntt_launch(b2, count * N1, ntt_smem_bytes(N2), st);
   }
   for (size_t r = 0; r < count; r++) {
     int rc = ntt_run<R>(p, in + r * n_in * 8, n_in, out + r * N * 8, tmp, st);

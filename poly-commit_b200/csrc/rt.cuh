@@ -88,6 +88,9 @@ inline int launch_blocks(const Body &body, size_t nblocks, size_t smem_bytes, st
   return OK;
 }
 
+template <int BLOCK, int MINB, class Body>
+inline int launch_blocks_occ(const Body &body, size_t nblocks, size_t smem_bytes, stream_t s) { return launch_blocks<BLOCK>(body, nblocks, smem_bytes, s); }
+
 #else
 // ------------------------------------------------------------------ CUDA (the product)
 typedef cudaStream_t stream_t;
@@ -174,6 +177,23 @@ inline int launch_blocks(const Body &body, size_t nblocks, size_t smem_bytes, st
     if (e != cudaSuccess) return map_cuda(e);
   }
   run_block_kernel<Body, BLOCK><<<(unsigned)nblocks, BLOCK, smem_bytes, s>>>(body);
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  return last_error();
+}
+// same, with a minimum number of resident blocks per SM (caps the registers of register-heavy block-cooperative bodies)
+template <class Body, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) run_block_kernel_occ(const Body body) {
+  extern __shared__ uint4 pcgpu_smem[];
+  body((size_t)blockIdx.x, reinterpret_cast<uint32_t *>(pcgpu_smem));
+}
+template <int BLOCK, int MINB, class Body>
+inline int launch_blocks_occ(const Body &body, size_t nblocks, size_t smem_bytes, stream_t s) {
+  if (nblocks == 0) return OK;
+  if (smem_bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(run_block_kernel_occ<Body, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return map_cuda(e);
+  }
+  run_block_kernel_occ<Body, BLOCK, MINB><<<(unsigned)nblocks, BLOCK, smem_bytes, s>>>(body);
   launch_counter().fetch_add(1, std::memory_order_relaxed);
   return last_error();
 }

@@ -403,3 +403,22 @@ def test_cfg5_shape_2p22(eng, pc):
     assert (got[0] == c0[0]).all() and (got[1] == c1[0]).all() and (got[2] == cc[0]).all() and (got[3] == c0[0]).all()
     assert not inf.any()
     srs.release()
+
+
+@pytest.mark.parametrize("cname,logn", [("bls12_381", 22), ("pallas", 19)])
+def test_div_linear_one_pass_equals_level_tree(eng, cname, logn, monkeypatch):
+    """The one-pass division (tiles chained by a decoupled look-back: at 2^22 the first wave of ~450 resident tiles walks several
+    look-back windows over aggregate-only predecessors) against the level tree, bit for bit, and against p(z) from the oracle."""
+    C = pyref.Curve(cname)
+    n = (1 << logn) + 77
+    p = util.rand_fr_fast(cname, n, seed=400 + logn)
+    z = util.rand_fr(cname, 1, seed=401, mont=True)[0]
+    monkeypatch.setenv("PCGPU_DIV_MODE", "tile")
+    q1, r1 = eng.fr_div_linear(C.id, p, z)
+    for _ in range(3):      # the look-back's timing differs from run to run: repeat
+        q1b, r1b = eng.fr_div_linear(C.id, p, z)
+        assert (q1b == q1).all() and (r1b == r1).all()
+    monkeypatch.setenv("PCGPU_DIV_MODE", "tree")
+    q2, r2 = eng.fr_div_linear(C.id, p, z)
+    assert (q1 == q2).all() and (r1 == r2).all()
+    assert (r1 == orc.fr_eval(C.id, p, z)).all()
