@@ -52,8 +52,33 @@ struct GlvSplit {
   uint32_t k1[5], k2[5];   // magnitudes, 160 bits
   uint32_t neg1, neg2;     // signs
   uint32_t nbits;          // max bit length of the two magnitudes
+  // joint sparse form of (|k1|, |k2|) (Solinas): digits in {-1, 0, 1}, at most one of any two consecutive columns is
+  // non-zero in the joint sense -- on average half of the columns are (0, 0).  Bit j of *_nz / *_sg = digit j non-zero / negative.
+  uint32_t u1_nz[5], u1_sg[5], u2_nz[5], u2_sg[5];
+  uint32_t jsf_len;        // number of columns (<= nbits + 1)
   bool ok;
 };
+
+// Joint sparse form of two non-negative integers of at most 158 bits (Solinas 2001; Handbook of Elliptic and Hyperelliptic Curve
+// Cryptography, Alg. 9.27).  Returns the number of columns.
+inline uint32_t jsf_recode(UBig a, UBig b, uint32_t *u1_nz, uint32_t *u1_sg, uint32_t *u2_nz, uint32_t *u2_sg) {
+  for (int i = 0; i < 5; i++) u1_nz[i] = u1_sg[i] = u2_nz[i] = u2_sg[i] = 0;
+  auto shr1 = [](UBig &v) { for (int j = 0; j < 7; j++) v.l[j] = (v.l[j] >> 1) | (v.l[j + 1] << 63); v.l[7] >>= 1; };
+  uint32_t d1 = 0, d2 = 0, j = 0;
+  while ((!a.is_zero() || d1 || !b.is_zero() || d2) && j < 160) {
+    const uint32_t l1 = (uint32_t)((a.l[0] & 7) + d1) & 7, l2 = (uint32_t)((b.l[0] & 7) + d2) & 7;
+    int u1 = 0, u2 = 0;
+    if (l1 & 1) { u1 = 2 - (int)(l1 & 3); if ((l1 == 3 || l1 == 5) && (l2 & 3) == 2) u1 = -u1; }
+    if (l2 & 1) { u2 = 2 - (int)(l2 & 3); if ((l2 == 3 || l2 == 5) && (l1 & 3) == 2) u2 = -u2; }
+    if ((int)(2 * d1) == 1 + u1) d1 = 1 - d1;
+    if ((int)(2 * d2) == 1 + u2) d2 = 1 - d2;
+    if (u1) { u1_nz[j >> 5] |= 1u << (j & 31); if (u1 < 0) u1_sg[j >> 5] |= 1u << (j & 31); }
+    if (u2) { u2_nz[j >> 5] |= 1u << (j & 31); if (u2 < 0) u2_sg[j >> 5] |= 1u << (j & 31); }
+    shr1(a); shr1(b);
+    j++;
+  }
+  return j;
+}
 
 template <class C>
 inline GlvSplit glv_decompose(const uint64_t *k_canonical) {
@@ -96,6 +121,20 @@ inline GlvSplit glv_decompose(const uint64_t *k_canonical) {
   }
   out.neg1 = k1.neg && !k1.m.is_zero(); out.neg2 = k2.neg && !k2.m.is_zero();
   out.nbits = (uint32_t)(k1.m.bits() > k2.m.bits() ? k1.m.bits() : k2.m.bits());
+  out.jsf_len = jsf_recode(k1.m, k2.m, out.u1_nz, out.u1_sg, out.u2_nz, out.u2_sg);
+  {   // the recoding is checked before use: sum_j u[j] 2^j == |k| for both halves (signed accumulation over 192 bits)
+    for (int h = 0; h < 2; h++) {
+      const uint32_t *nz = h ? out.u2_nz : out.u1_nz, *sg = h ? out.u2_sg : out.u1_sg;
+      SBig acc{UBig::zero(), false};
+      for (uint32_t j = 0; j < out.jsf_len; j++) {
+        if (!((nz[j >> 5] >> (j & 31)) & 1)) continue;
+        UBig w = UBig::zero(); w.l[j >> 6] = (uint64_t)1 << (j & 63);
+        acc = sadd(acc, SBig{w, ((sg[j >> 5] >> (j & 31)) & 1) != 0});
+      }
+      const UBig &want = h ? k2.m : k1.m;
+      if (acc.neg || ucmp(acc.m, want) != 0) return out;
+    }
+  }
   out.ok = true;
   return out;
 }

@@ -877,6 +877,10 @@ static int ensure_pow2(pcgpu_ctx *ctx) {
   return rt::launch<32>(Pow2TableBody<QP>{ctx->d_pow2[C::ID]}, 1, ctx->stream);
 }
 
+#ifndef PCGPU_IPA_FOLD_MIN_BLOCKS
+#define PCGPU_IPA_FOLD_MIN_BLOCKS 2
+#endif
+enum { IPA_FOLD_MIN_BLOCKS = PCGPU_IPA_FOLD_MIN_BLOCKS };
 // freeze the key at its current length (<= SMALL_MAX_N): weights start at one
 template <class C>
 static int ipa_freeze(pcgpu_ctx *ctx, pcgpu_ipa *st) {
@@ -1019,9 +1023,16 @@ int ipa_round_fold_impl(pcgpu_ctx *ctx, pcgpu_ipa *st, const void *challenge, co
   }
   if (gs.ok) {
     G1FoldGlvBody<C> gb; gb.key = (Affine<C> *)st->d_key; gb.m = (uint32_t)m;
-    memcpy(gb.k1, gs.k1, sizeof gb.k1); memcpy(gb.k2, gs.k2, sizeof gb.k2);
-    gb.neg1 = gs.neg1; gb.neg2 = gs.neg2; gb.nbits = gs.nbits; gb.pow2 = ctx->d_pow2[C::ID];
-    if ((rc = rt::launch<128>(gb, m, s))) return rc;                                                        // :699-707
+    memcpy(gb.u1_nz, gs.u1_nz, sizeof gb.u1_nz); memcpy(gb.u1_sg, gs.u1_sg, sizeof gb.u1_sg);
+    memcpy(gb.u2_nz, gs.u2_nz, sizeof gb.u2_nz); memcpy(gb.u2_sg, gs.u2_sg, sizeof gb.u2_sg);
+    gb.neg1 = gs.neg1; gb.neg2 = gs.neg2; gb.ncols = gs.jsf_len; gb.pow2 = ctx->d_pow2[C::ID];
+    // registers: 190 uncapped (2 blocks of 128 threads per SM); 3 or 4 resident blocks cap them at 168 / 128 (PCGPU_IPA_FOLD_OCC)
+    int occ = IPA_FOLD_MIN_BLOCKS;
+    if (const char *e = getenv("PCGPU_IPA_FOLD_OCC")) { int v = atoi(e); if (v >= 2 && v <= 4) occ = v; }
+    if (occ == 2) rc = rt::launch<128>(gb, m, s);
+    else if (occ == 3) rc = rt::launch_occ<128, 3>(gb, m, s);
+    else rc = rt::launch_occ<128, 4>(gb, m, s);
+    if (rc) return rc;                                                                                      // :699-707
   } else {
     G1FoldBody<C> fb; fb.key = (Affine<C> *)st->d_key; fb.m = (uint32_t)m;
     memcpy(fb.chal, canon, 32); fb.pow2 = ctx->d_pow2[C::ID];

@@ -53,12 +53,14 @@ struct G1FoldBody {
 };
 
 // The same fold through the GLV endomorphism (curves with cofactor 1: Pallas, BN254): chal = k1 + k2 lambda with ~128-bit
-// k1, k2 (host_glv.hpp), chal * R = k1 * R + k2 * phi(R), phi(x, y) = (zeta x, y) -- one joint double-and-add ladder of
-// nbits <= 132 steps over {P1 = +-R, P2 = +-phi(R), P1 + P2} instead of 256 steps over {R}.  Every thread runs the same
-// scalar, so the ladder's control flow is uniform across the grid.
+// k1, k2 (host_glv.hpp), chal * R = k1 * R + k2 * phi(R), phi(x, y) = (zeta x, y) -- one joint ladder of <= 133 columns in
+// JOINT SPARSE FORM over {P1 = +-R, P2 = +-phi(R), P1 + P2, P1 - P2} instead of 256 steps over {R}: half of the columns are
+// (0, 0) on average (the plain binary joint ladder adds in three columns of four), and all four table points are AFFINE --
+// P1 + P2 and P1 - P2 share the denominator x2 - x1, so one binary-GCD inverse yields both -- so every addition is a mixed one.
+// Every thread runs the same scalar, so the ladder's control flow is uniform across the grid.
 template <class C>
 struct G1FoldGlvBody {
-  Affine<C> *key; uint32_t m; uint32_t k1[5], k2[5]; uint32_t neg1, neg2, nbits;
+  Affine<C> *key; uint32_t m; uint32_t u1_nz[5], u1_sg[5], u2_nz[5], u2_sg[5]; uint32_t neg1, neg2, ncols;
   const uint32_t *pow2;
   PCGPU_KERNEL_DEV void operator()(size_t i) const {
     using Q = typename C::Fq;
@@ -67,18 +69,32 @@ struct G1FoldGlvBody {
     if (r.is_inf()) { key[i] = l; return; }
     Fp<Q> zeta;
     for (int j = 0; j < Q::N; j++) zeta.l[j] = Q::glv_zeta(j);
-    Affine<C> p1 = r, p2;
+    Affine<C> p1 = r, p2, ps, pd;
     p1.y = fp_cneg<Q>(r.y, neg1 != 0);
     p2.x = fp_mul<Q>(r.x, zeta); p2.y = fp_cneg<Q>(r.y, neg2 != 0);
-    XYZZ<C> t = xyzz_from_affine<C>(p1);
-    xyzz_madd<C>(t, p2, false);                       // P1 + P2 (never exceptional for R != O: lambda != +-1)
+    {   // P1 + P2 and P1 - P2 (x2 != x1 for R != O: phi has no fixed point in a group of prime order)
+      const Fp<Q> inv = fp_inv_gcd<Q>(fp_sub<Q>(p2.x, p1.x), pow2);
+      const Fp<Q> xsum = fp_add<Q>(p1.x, p2.x);
+      Fp<Q> lam = fp_mul<Q>(fp_sub<Q>(p2.y, p1.y), inv);
+      ps.x = fp_sub<Q>(fp_sqr<Q>(lam), xsum);
+      ps.y = fp_sub<Q>(fp_mul<Q>(lam, fp_sub<Q>(p1.x, ps.x)), p1.y);
+      lam = fp_mul<Q>(fp_sub<Q>(fp_neg<Q>(p2.y), p1.y), inv);
+      pd.x = fp_sub<Q>(fp_sqr<Q>(lam), xsum);
+      pd.y = fp_sub<Q>(fp_mul<Q>(lam, fp_sub<Q>(p1.x, pd.x)), p1.y);
+    }
     XYZZ<C> acc = XYZZ<C>::inf();
-    for (int b = (int)nbits - 1; b >= 0; b--) {
+    for (int b = (int)ncols - 1; b >= 0; b--) {
       acc = xyzz_dbl<C>(acc);
-      const uint32_t s = ((k1[b >> 5] >> (b & 31)) & 1) | (((k2[b >> 5] >> (b & 31)) & 1) << 1);
-      if (s == 1) xyzz_madd<C>(acc, p1, false);
-      else if (s == 2) xyzz_madd<C>(acc, p2, false);
-      else if (s == 3) xyzz_add<C>(acc, t);
+      const uint32_t w = (uint32_t)b >> 5, sh = (uint32_t)b & 31;
+      const bool n1 = (u1_nz[w] >> sh) & 1, n2 = (u2_nz[w] >> sh) & 1, s1 = (u1_sg[w] >> sh) & 1, s2 = (u2_sg[w] >> sh) & 1;
+      if (!(n1 || n2)) continue;
+      // the table point is SELECTED (register moves) and added at ONE call site: with an addition inlined per case the loop
+      // body outgrows the instruction cache (measured on the small-MSM kernel: -18 % from out-of-line additions alone)
+      Affine<C> a = p1;
+      bool neg = s1;
+      if (n1 && n2) { if (s1 == s2) a = ps; else a = pd; }      // +-(P1 + P2) / +-(P1 - P2): the sign is u1's
+      else if (n2) { a = p2; neg = s2; }
+      xyzz_madd<C>(acc, a, neg);
     }
     xyzz_madd<C>(acc, l, false);
     key[i] = xyzz_to_affine_gcd<C>(acc, pow2);

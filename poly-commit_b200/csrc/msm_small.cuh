@@ -97,18 +97,18 @@ struct MsmSmallBody {
     }
     PCGPU_BLOCK_SYNC();
     for (uint32_t half = SMALL_SLICES / 2; half >= 1; half >>= 1) {
-      PCGPU_BLOCK_FOR(t, SMALL_NB * half) { XYZZ<C> x = sh[t], y = sh[t + SMALL_NB * half]; xyzz_add<C>(x, y); sh[t] = x; }
+      PCGPU_BLOCK_FOR(t, SMALL_NB * half) { XYZZ<C> x = sh[t], y = sh[t + SMALL_NB * half]; xyzz_add_ool<C>(x, y); sh[t] = x; }
       PCGPU_BLOCK_SYNC();
     }
     // suffix sums S_b = sum_{m >= b} B_m (ping-pong between the two halves of sh[0 .. 2 NB)), then their total
     XYZZ<C> *src = sh, *dst = sh + SMALL_NB;
     for (uint32_t d = 1; d < SMALL_NB; d <<= 1) {
-      PCGPU_BLOCK_FOR(b, SMALL_NB) { XYZZ<C> x = src[b]; if (b + d < SMALL_NB) { XYZZ<C> y = src[b + d]; xyzz_add<C>(x, y); } dst[b] = x; }
+      PCGPU_BLOCK_FOR(b, SMALL_NB) { XYZZ<C> x = src[b]; if (b + d < SMALL_NB) { XYZZ<C> y = src[b + d]; xyzz_add_ool<C>(x, y); } dst[b] = x; }
       PCGPU_BLOCK_SYNC();
       XYZZ<C> *tmp = src; src = dst; dst = tmp;
     }
     for (uint32_t half = SMALL_NB / 2; half >= 1; half >>= 1) {
-      PCGPU_BLOCK_FOR(b, half) { XYZZ<C> x = src[b], y = src[b + half]; xyzz_add<C>(x, y); src[b] = x; }
+      PCGPU_BLOCK_FOR(b, half) { XYZZ<C> x = src[b], y = src[b + half]; xyzz_add_ool<C>(x, y); src[b] = x; }
       PCGPU_BLOCK_SYNC();
     }
     PCGPU_BLOCK_FOR(b, 1) { store_xyzz<C>(out + blk, src[0]); }

@@ -51,7 +51,7 @@ extern "C" int hostcheck_field_op(int field, int which, const uint32_t *a, const
   return 0;
 }
 
-// GLV split of one canonical scalar (host_glv.hpp): curve 1 = BN254, 2 = Pallas.  out: k1[5], k2[5], neg1, neg2, nbits, ok
+// GLV split of one canonical scalar (host_glv.hpp): curve 1 = BN254, 2 = Pallas.  out: k1[5], k2[5], neg1, neg2, nbits, ok, jsf_len, u1_nz[5], u1_sg[5], u2_nz[5], u2_sg[5]
 #include "../../poly-commit_b200/csrc/host_glv.hpp"
 extern "C" int hostcheck_glv(int curve, const uint64_t *k, uint32_t *out) {
   host::GlvSplit g;
@@ -60,6 +60,8 @@ extern "C" int hostcheck_glv(int curve, const uint64_t *k, uint32_t *out) {
   else return -1;
   for (int i = 0; i < 5; i++) { out[i] = g.k1[i]; out[5 + i] = g.k2[i]; }
   out[10] = g.neg1; out[11] = g.neg2; out[12] = g.nbits; out[13] = g.ok ? 1 : 0;
+  out[14] = g.jsf_len;   // joint sparse form of (|k1|, |k2|): non-zero / sign masks of the two digit strings
+  for (int i = 0; i < 5; i++) { out[15 + i] = g.u1_nz[i]; out[20 + i] = g.u1_sg[i]; out[25 + i] = g.u2_nz[i]; out[30 + i] = g.u2_sg[i]; }
   return 0;
 }
 

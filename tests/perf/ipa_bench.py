@@ -25,18 +25,23 @@ def main():
     t_begin = time.perf_counter() - t0
     t_lr = t_fold = t_hash = 0.0
     rc = 7
+    per_round = []
     while eng.ipa_len(st) > 1:
+        per_round.append([eng.ipa_len(st), 0.0, 0.0])
         t1 = time.perf_counter(); l, li, r, ri = eng.ipa_round_lr(C.id, st, h_prime, with_inf=True); t_lr += time.perf_counter() - t1
+        per_round[-1][1] = round((time.perf_counter() - t1) * 1e3, 3)
         t1 = time.perf_counter()
         rc = ipa_pc.compute_random_oracle_challenge(C.id, ipa_pc.round_transcript(eng, C.id, rc, l, li, r, ri)); t_hash += time.perf_counter() - t1
         inv = pow(rc, -1, C.r)
         t1 = time.perf_counter(); eng.ipa_round_fold(st, ipa_pc._fr_mont(C.id, rc), ipa_pc._fr_mont(C.id, inv)); t_fold += time.perf_counter() - t1
+        per_round[-1][2] = round((time.perf_counter() - t1) * 1e3, 3)
     t1 = time.perf_counter(); eng.ipa_finish(C.id, st); t_fin = time.perf_counter() - t1
     tot = time.perf_counter() - t0
     print(json.dumps({"workload": "IPA open halving loop, Pallas, 2^18, 18 rounds (host buffers in, device-resident rounds)",
                       "total_ms": round(tot * 1e3, 2), "begin_upload_ms": round(t_begin * 1e3, 2),
                       "lr_msm_ip_ms": round(t_lr * 1e3, 2), "folds_ms": round(t_fold * 1e3, 2),
-                      "transcript_ms": round(t_hash * 1e3, 2), "finish_ms": round(t_fin * 1e3, 2), "freeze": os.environ.get("PCGPU_IPA_FREEZE", "1")}))
+                      "transcript_ms": round(t_hash * 1e3, 2), "finish_ms": round(t_fin * 1e3, 2), "freeze": os.environ.get("PCGPU_IPA_FREEZE", "1"),
+                      "per_round_n_lr_ms_fold_ms": per_round}))
 
 if __name__ == "__main__":
     main()

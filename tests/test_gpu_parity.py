@@ -422,3 +422,38 @@ def test_div_linear_one_pass_equals_level_tree(eng, cname, logn, monkeypatch):
     q2, r2 = eng.fr_div_linear(C.id, p, z)
     assert (q1 == q2).all() and (r1 == r2).all()
     assert (r1 == orc.fr_eval(C.id, p, z)).all()
+
+
+def test_concurrent_host_threads(eng, pc):
+    """Re-entrancy (SURVEY 8b): HyraxPC::commit calls msm from inside a Rayon par_iter (hyrax/mod.rs:233-242).  Eight host
+    threads -- four sharing ONE context (calls serialised by its mutex), four with a context each -- run MSMs of different
+    scalar vectors over one registered SRS at the same time; every result equals the oracle's."""
+    import threading
+    cname = "bn254"
+    C = pyref.Curve(cname)
+    n = (1 << 14) + 3
+    bases = gpu_srs(eng, cname, n, seed=77)
+    srs = eng.srs_register(C.id, bases, flags=pc.SRS_PRECOMPUTE)
+    scalars = [util.rand_fr(cname, n, seed=900 + t, mont=False) for t in range(8)]
+    expected = [orc.msm(C.id, bases, s) for s in scalars]
+    own = [pc.Engine(0) for _ in range(4)]
+    engines = [eng] * 4 + own
+    got, errors = [None] * 8, []
+
+    def work(t):
+        try:
+            for _ in range(6):
+                got[t] = engines[t].msm(srs, scalars[t])
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for e in own:
+        e.close()
+    assert not errors, errors
+    for t in range(8):
+        assert (got[t][0] == expected[t][0]).all() and got[t][1] == expected[t][1], f"thread {t}"

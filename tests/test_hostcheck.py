@@ -965,9 +965,23 @@ def test_glv_split_of_the_fold_challenge(hostcheck_path, cname):
     used = None
     for k in ks:
         kin = np.array([(k >> (64 * j)) & (2**64 - 1) for j in range(4)], dtype=np.uint64)
-        out = np.zeros(14, dtype=np.uint32)
+        out = np.zeros(35, dtype=np.uint32)
         assert lib.hostcheck_glv(C.id, kin.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == 0
         assert out[13] == 1, k
+        # joint sparse form of (|k1|, |k2|) used by the fold kernel: digits in {-1, 0, 1} that reconstruct both magnitudes,
+        # and of any two consecutive columns at most one is non-zero in the joint sense -- unless the pattern is the allowed
+        # (+-1, 0), (+-1, +-1)-type pair of Solinas' form; the joint weight stays near one half of the columns
+        ncols = int(out[14])
+        mask = lambda base, j: (int(out[base + (j >> 5)]) >> (j & 31)) & 1  # noqa: E731
+        u1 = [mask(15, j) * (-1 if mask(20, j) else 1) for j in range(ncols)]
+        u2 = [mask(25, j) * (-1 if mask(30, j) else 1) for j in range(ncols)]
+        m1 = sum(int(out[i]) << (32 * i) for i in range(5))
+        m2 = sum(int(out[5 + i]) << (32 * i) for i in range(5))
+        assert sum(d << j for j, d in enumerate(u1)) == m1 and sum(d << j for j, d in enumerate(u2)) == m2
+        assert ncols <= int(out[12]) + 1
+        if ncols > 100:
+            weight = sum(1 for a, b in zip(u1, u2) if a or b)
+            assert weight <= 0.62 * ncols, (weight, ncols)
         k1 = sum(int(out[i]) << (32 * i) for i in range(5)) * (-1 if out[10] else 1)
         k2 = sum(int(out[5 + i]) << (32 * i) for i in range(5)) * (-1 if out[11] else 1)
         assert abs(k1) < 1 << 130 and abs(k2) < 1 << 130 and out[12] == max(abs(k1).bit_length(), abs(k2).bit_length())
