@@ -205,7 +205,10 @@ int msm_small_to_host(pcgpu_ctx *ctx, const MsmSmallProblem<C> *probs, uint32_t 
   if (nprob == 0 || nprob > SMALL_MAX_PROB) return PCGPU_E_BADARG;
   uint32_t nmax = 0;
   for (uint32_t p = 0; p < nprob; p++) nmax = probs[p].n > nmax ? probs[p].n : nmax;
-  const uint32_t split = nmax >= SMALL_SPLIT_MIN_N ? SMALL_SPLIT : 1;
+  // blocks per window: 1 below 512 terms, 3 up to SMALL_MAX_N, 6 beyond (the IPA's l / r commitments of 8192 terms: a block's
+  // share stays at <= 1366 terms, which is what bounds its chain of dependent additions and its digit buffer)
+  if (nmax > 2 * SMALL_MAX_N) return PCGPU_E_BADARG;
+  const uint32_t split = nmax > SMALL_MAX_N ? 2 * SMALL_SPLIT : (nmax >= SMALL_SPLIT_MIN_N ? SMALL_SPLIT : 1);
   const size_t npts = (size_t)nprob * W * split;
   if ((rc = ctx->msm_arena.reserve(rt::Arena::pad(npts * sizeof(XYZZ<C>)) + 4096))) return rc;
   uint32_t *d_err = ctx->msm_arena.take<uint32_t>(16);
@@ -954,8 +957,9 @@ int ipa_round_lr_impl(pcgpu_ctx *ctx, pcgpu_ctx *sib, pcgpu_ipa *st, const void 
     host::to_affine<C>(lr[1], out_r_xy, out_r_inf);
     return PCGPU_OK;
   }
-  if (m < SMALL_MAX_N && msm_small_enabled()) {
-    // late rounds: both commitments, each with its  + h' * <.,.>  term, in ONE launch; the inner products never leave HBM
+  if (m <= 2 * SMALL_MAX_N && msm_small_enabled()) {
+    // rounds of <= 8192-term commitments (1.6 ms each through the bucket pipeline, whose fixed cost dominates at this size;
+    // 0.5 - 0.7 ms here): both commitments, each with its  + h' * <.,.>  term, in ONE launch; the inner products never leave HBM
     uint32_t *d_h = st->d_scr + 8 * (IP_THREADS + IP_THREADS / IP_BLOCK + 12);   // 3 slots, clear of d_ip / d_ch
     if ((rc = fr_inner_product<R>(cr, zl, m, d_ip, st->d_scr, s))) return rc;
     if ((rc = fr_inner_product<R>(cl, zr, m, d_ip + 8, st->d_scr, s))) return rc;

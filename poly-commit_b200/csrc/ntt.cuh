@@ -137,13 +137,18 @@ PCGPU_DEV void ntt_block_stages(uint32_t *smem, uint32_t m, const uint32_t *tw) 
   }
 }
 
-// launch of a block transform: NTT_BLOCK threads, 3 or 4 resident blocks per SM (168 / 128 registers; PCGPU_NTT_OCC, tuning knob)
+// launch of a block transform of length M: a register round keeps M / 8 threads busy, so the block is M / 8 threads wide
+// (32 .. 128) and the resident blocks per SM are raised to match (128 registers per thread throughout) -- the short
+// transforms of the Ligero row encoding (2^15 = 256 x 128) would otherwise leave three warps of four idle
 template <class Body>
 inline int ntt_launch(const Body &b, size_t nblocks, size_t smem_bytes, rt::stream_t st) {
-  int occ = NTT_MIN_BLOCKS;
-  if (const char *e = getenv("PCGPU_NTT_OCC")) { int v = atoi(e); if (v == 3 || v == 4) occ = v; }
-  if (occ == 3) return rt::launch_blocks_occ<NTT_BLOCK, 3>(b, nblocks, smem_bytes, st);
-  return rt::launch_blocks_occ<NTT_BLOCK, 4>(b, nblocks, smem_bytes, st);
+  const uint32_t M = 1u << b.m;
+  // (only when the grid is large enough to fill the device with narrow blocks; a small grid is latency-bound and wants the
+  // wide block's parallel loads and stores: 2^16 = 256 x 256 runs 0.055 ms with 128 threads, 0.069 ms with 32)
+  if (nblocks < 4096) return rt::launch_blocks_occ<NTT_BLOCK, NTT_MIN_BLOCKS>(b, nblocks, smem_bytes, st);
+  if (M <= 256) return rt::launch_blocks_occ<32, 16>(b, nblocks, smem_bytes, st);
+  if (M <= 512) return rt::launch_blocks_occ<64, 8>(b, nblocks, smem_bytes, st);
+  return rt::launch_blocks_occ<NTT_BLOCK, NTT_MIN_BLOCKS>(b, nblocks, smem_bytes, st);
 }
 
 template <class R>
