@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""A/B of the pair-round kernels' software prefetch (PCGPU_PAIR_PREFETCH: distance in slots, +16 = into L1) on one B200:
+"""One-knob A/B of the pair-round kernels on one B200 (AB_KNOB names the environment variable; written for the software-prefetch
+experiment, PCGPU_PAIR_PREFETCH = distance in slots, +16 = into L1 -- measured slower and removed, profiles/r02_pair_prefetch_ab.jsonl):
 single-MSM stage timings (CUDA events of the library's profiler) and the batch commit+open entry point, every variant checked
 against the first.  python tests/perf/prefetch_ab.py [log_n] [values...] > gpurun_out/prefetch_ab.jsonl"""
 import json
