@@ -409,6 +409,26 @@ inline size_t div_scratch_words(size_t n) {
   return 8 * (tot + DIV_MAX_LEVELS + 4 + DIVT_POW_COUNT + 2 * ntiles + 4) + ntiles + 72;
 }
 
+// which division runs for n coefficients (see fr_div_linear)
+inline bool div_one_pass(size_t n) {
+  bool one_pass = n <= ((size_t)1 << 21);
+  if (const char *e = getenv("PCGPU_DIV_MODE")) one_pass = e[0] == 't' && e[1] == 'i';
+  return one_pass;
+}
+// The one-pass kernel's look-back is a BOUNDED spin: a tile that never sees its predecessor publish (which would take a lost
+// block, i.e. a device fault) gives up, raises ctl[1] and lets the kernel finish -- never a hang.  Callers read the word back
+// here once the stream is idle and turn it into an error code instead of returning a wrong quotient.
+inline int fr_div_check(const uint32_t *scratch, size_t n, rt::stream_t st) {
+  if (n == 0 || !div_one_pass(n)) return rt::OK;
+  const size_t ntiles = (n + DIVT_TILE - 1) / DIVT_TILE;
+  const uint32_t *ctl = scratch + 8 * DIVT_POW_COUNT + 16 * ntiles;
+  uint32_t h = 0;
+  int rc = rt::copy_d2h(&h, ctl + 1, sizeof h, st);
+  if (!rc) rc = rt::stream_sync(st);
+  if (rc) return rc;
+  return h ? rt::E_CUDA : rt::OK;
+}
+
 // p: n coefficients, q: n-1 coefficients (n >= 1), rem: 1 element, z: 1 element; all device.
 template <class R>
 inline int fr_div_linear(const uint32_t *p, size_t n, const uint32_t *z, uint32_t *q, uint32_t *rem,
@@ -425,9 +445,7 @@ inline int fr_div_linear(const uint32_t *p, size_t n, const uint32_t *z, uint32_
   int rc;
   // one pass up to 2^21 coefficients (0.08 / 0.15 ms at 2^16 / 2^20 against 0.17 / 0.21 ms for the level tree below); beyond
   // that the level tree's fewer products per coefficient win (0.35 against 0.41 ms at 2^22); PCGPU_DIV_MODE = tile | tree forces one
-  bool one_pass = n <= ((size_t)1 << 21);
-  if (const char *e = getenv("PCGPU_DIV_MODE")) one_pass = e[0] == 't' && e[1] == 'i';
-  if (one_pass) {
+  if (div_one_pass(n)) {
     // one pass: powers (one small launch), control words cleared, tiles chained by a decoupled look-back
     const uint32_t ntiles = (uint32_t)((n + DIVT_TILE - 1) / DIVT_TILE);
     uint32_t *pw = scratch, *aggp = pw + 8 * DIVT_POW_COUNT, *incp = aggp + 8 * (size_t)ntiles, *ctl = incp + 8 * (size_t)ntiles;

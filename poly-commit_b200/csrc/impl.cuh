@@ -641,6 +641,7 @@ int fr_div_impl(pcgpu_ctx *ctx, const void *p, size_t n, const void *z, void *q,
   uint32_t hrem[8];
   if ((rc = rt::copy_d2h(hrem, d_rem, 32, st))) return rc;
   if ((rc = rt::stream_sync(st))) return rc;
+  if ((rc = fr_div_check(scratch, n, st))) return rc;
   if (rem) memcpy(rem, hrem, 32);
   ctx->prof.collect();
   return PCGPU_OK;
@@ -761,9 +762,11 @@ int kzg_open_impl(pcgpu_ctx *ctx, const pcgpu_srs *pg, const void *coeffs, size_
   ctx->prof.end(7, st);
   host::HXYZZ<C> w, rw;
   if ((rc = msm_to_host<C>(ctx, pg, 0, d_q, n ? n - 1 : 0, true, &w))) return rc;     // :255-258
+  if ((rc = fr_div_check(scratch, n, st))) return rc;
   if (n_blind) {
     if ((rc = fr_div_linear<R>(d_b, n_blind, d_z, d_bq, d_rv, scratch, st))) return rc;  // rem = blind(z), :264
     if ((rc = msm_to_host<C>(ctx, gamma, 0, d_bq, n_blind - 1, true, &rw))) return rc;  // :270-273
+    if ((rc = fr_div_check(scratch, n_blind, st))) return rc;
     if (out_random_v) {
       if ((rc = rt::copy_d2h(out_random_v, d_rv, 32, st))) return rc;
       if ((rc = rt::stream_sync(st))) return rc;
@@ -854,6 +857,7 @@ int kzg_commit_open_impl(pcgpu_ctx *ctx, pcgpu_ctx *sib, const pcgpu_srs *pg, co
   host::HXYZZ<C> comm, w;
   if ((rc = msm_collect<C>(ctx, &pc, &comm))) return rc;
   if ((rc = msm_collect<C>(sib, &pw, &w))) return rc;
+  if ((rc = fr_div_check(scratch, n, sb))) return rc;
   host::to_affine<C>(comm, out_c_xy, out_c_inf);                                      // :209
   host::to_affine<C>(w, out_w_xy, out_w_inf);                                         // :281
   return PCGPU_OK;
