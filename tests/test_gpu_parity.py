@@ -457,3 +457,23 @@ def test_concurrent_host_threads(eng, pc):
     assert not errors, errors
     for t in range(8):
         assert (got[t][0] == expected[t][0]).all() and got[t][1] == expected[t][1], f"thread {t}"
+
+
+def test_randomised_sweep(capsys):
+    """A short run of tests/perf/fuzz_gpu.py (random shapes across the small-path / split / bucket-pipeline boundaries, scalar
+    mixtures, base offsets, the three division modes, NTT + inverse, hiding commits / opens), bit-exact against the C oracle;
+    profiles/r02_fuzz_gpu.log holds two 400-case runs."""
+    import importlib.util
+    import os
+    import sys
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "perf", "fuzz_gpu.py")
+    spec = importlib.util.spec_from_file_location("fuzz_gpu", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    argv = sys.argv
+    try:
+        sys.argv = [path, "80", "4242"]
+        mod.main()
+    finally:
+        sys.argv = argv
+    assert '"ok": true' in capsys.readouterr().out
