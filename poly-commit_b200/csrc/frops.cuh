@@ -474,31 +474,32 @@ inline int fr_div_linear(const uint32_t *p, size_t n, const uint32_t *z, uint32_
 // ---------------------------------------------------------------------------------------------
 // inner product: strided per-thread partial sums (coalesced), then block-level shared-memory trees
 // ---------------------------------------------------------------------------------------------
-enum { IP_THREADS = 65536, IP_BLOCK = 256 };
+enum { IP_THREADS = 262144, IP_BLOCK = 256, IP_CHUNK = 1024 };   // IP_THREADS: the most partial sums a call produces (scratch sizing)
 template <class R>
 struct IpPartialBody {
-  const uint32_t *a; const uint32_t *b; size_t n; uint32_t *partial;
+  const uint32_t *a; const uint32_t *b; size_t n; uint32_t *partial; uint32_t T;   // T threads, thread t owns t, t + T, t + 2T, ...
   PCGPU_KERNEL_DEV void operator()(size_t t) const {
     // two elements per iteration: four independent loads in flight and ONE Montgomery reduction for the pair
     // (fr_dot2 = a0 b0 + a1 b1 with a single reduction where 3r < 2^256: 192 instead of 256 wide multiplies per pair)
     Fp<R> acc = Fp<R>::zero();
     size_t i = t;
-    for (; i + IP_THREADS < n; i += 2 * (size_t)IP_THREADS) {
-      const Fp<R> a0 = load_fr<R>(a, i), b0 = load_fr<R>(b, i), a1 = load_fr<R>(a, i + IP_THREADS), b1 = load_fr<R>(b, i + IP_THREADS);
+    for (; i + T < n; i += 2 * (size_t)T) {
+      const Fp<R> a0 = load_fr<R>(a, i), b0 = load_fr<R>(b, i), a1 = load_fr<R>(a, i + T), b1 = load_fr<R>(b, i + T);
       acc = fp_add<R>(acc, fr_dot2<R>(a0, b0, a1, b1));
     }
     if (i < n) acc = fp_add<R>(acc, fp_mul<R>(load_fr<R>(a, i), load_fr<R>(b, i)));
     store_fr<R>(partial, t, acc);
   }
 };
-// block b sums in[b*IP_BLOCK .. +IP_BLOCK) (count m) into out[b]
+// block b sums in[b * chunk .. min(m, (b + 1) * chunk)) into out[b]: strided per-thread partial sums, then a shared-memory tree
 template <class R>
 struct FrBlockSumBody {
-  const uint32_t *in; size_t m; uint32_t *out;
+  const uint32_t *in; size_t m; uint32_t *out; uint32_t chunk;
   PCGPU_KERNEL_DEV void operator()(size_t b, uint32_t *smem) const {
     PCGPU_BLOCK_FOR(i, IP_BLOCK) {
-      size_t idx = b * IP_BLOCK + i;
-      Fp<R> v = idx < m ? load_fr<R>(in, idx) : Fp<R>::zero();
+      const size_t lo = b * (size_t)chunk, hi = lo + chunk < m ? lo + chunk : m;
+      Fp<R> v = Fp<R>::zero();
+      for (size_t idx = lo + i; idx < hi; idx += IP_BLOCK) v = fp_add<R>(v, load_fr<R>(in, idx));
 #pragma unroll
       for (int l = 0; l < 8; l++) smem[l * IP_BLOCK + i] = v.l[l];
     }
@@ -522,14 +523,21 @@ struct FrBlockSumBody {
     }
   }
 };
-// scratch: (IP_THREADS + IP_THREADS / IP_BLOCK) elements
+// scratch: (IP_THREADS + IP_THREADS / IP_BLOCK) elements.  The thread count follows n (two elements per thread per iteration, at
+// most IP_THREADS: 2^22 elements keep ~55 warps per SM streaming instead of 14), the partial sums are folded in one or two
+// block-tree launches.
 template <class R>
 inline int fr_inner_product(const uint32_t *a, const uint32_t *b, size_t n, uint32_t *out, uint32_t *scratch, rt::stream_t st) {
   int rc;
-  uint32_t *lvl1 = scratch + 8 * IP_THREADS;
-  if ((rc = rt::launch<128>(IpPartialBody<R>{a, b, n, scratch}, IP_THREADS, st))) return rc;
-  if ((rc = rt::launch_blocks<IP_BLOCK>(FrBlockSumBody<R>{scratch, IP_THREADS, lvl1}, IP_THREADS / IP_BLOCK, IP_BLOCK * 32, st))) return rc;
-  return rt::launch_blocks<IP_BLOCK>(FrBlockSumBody<R>{lvl1, IP_THREADS / IP_BLOCK, out}, 1, IP_BLOCK * 32, st);
+  size_t T = ((n + 1) / 2 + IP_CHUNK - 1) / IP_CHUNK * IP_CHUNK;
+  if (T < IP_CHUNK) T = IP_CHUNK;
+  if (T > IP_THREADS) T = IP_THREADS;
+  const size_t nblk = T / IP_CHUNK;
+  uint32_t *lvl1 = scratch + 8 * (size_t)IP_THREADS;
+  if ((rc = rt::launch<128>(IpPartialBody<R>{a, b, n, scratch, (uint32_t)T}, T, st))) return rc;
+  if (nblk == 1) return rt::launch_blocks<IP_BLOCK>(FrBlockSumBody<R>{scratch, T, out, IP_CHUNK}, 1, IP_BLOCK * 32, st);
+  if ((rc = rt::launch_blocks<IP_BLOCK>(FrBlockSumBody<R>{scratch, T, lvl1, IP_CHUNK}, nblk, IP_BLOCK * 32, st))) return rc;
+  return rt::launch_blocks<IP_BLOCK>(FrBlockSumBody<R>{lvl1, nblk, out, (uint32_t)nblk}, 1, IP_BLOCK * 32, st);
 }
 
 // out[c] = sum_r v[r] * M[r*cols + c]   (thread per column; coalesced across columns)
