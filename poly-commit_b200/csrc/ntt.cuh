@@ -20,7 +20,11 @@ namespace pcgpu {
 #ifndef PCGPU_NTT_MIN_BLOCKS
 #define PCGPU_NTT_MIN_BLOCKS 4
 #endif
-enum { NTT_MAX_LOG_BLOCK = 11, NTT_LO_BITS = 10, NTT_BLOCK = 128, NTT_MIN_BLOCKS = PCGPU_NTT_MIN_BLOCKS };
+#ifndef PCGPU_NTT_FULL_TABLE_MAX_LOG
+#define PCGPU_NTT_FULL_TABLE_MAX_LOG 20
+#endif
+enum { NTT_MAX_LOG_BLOCK = 11, NTT_LO_BITS = 10, NTT_BLOCK = 128, NTT_MIN_BLOCKS = PCGPU_NTT_MIN_BLOCKS,
+       NTT_FULL_TABLE_MAX_LOG = PCGPU_NTT_FULL_TABLE_MAX_LOG };
 
 template <class R>
 PCGPU_DEV Fp<R> fp_pow_u64(Fp<R> base, uint64_t e) {
@@ -184,7 +188,7 @@ struct NttBlockBody {
       for (int l = 0; l < 8; l++) v.l[l] = smem[l * P + ntt_pos(i)];
       if (step2) {
         uint64_t e = (uint64_t)i * (batch + batch_off);
-        if (e) v = fp_mul<R>(v, fp_mul<R>(load_fr<R>(hi, e >> NTT_LO_BITS), load_fr<R>(lo, e & ((1u << NTT_LO_BITS) - 1))));
+        if (e) v = fp_mul<R>(v, lo ? fp_mul<R>(load_fr<R>(hi, e >> NTT_LO_BITS), load_fr<R>(lo, e & ((1u << NTT_LO_BITS) - 1))) : load_fr<R>(hi, e));
       }
       if (scale) v = fp_mul<R>(v, load_fr<R>(scale, 0));
       store_fr<R>(out, batch * out_batch_stride + (uint64_t)i * out_stride, v);
@@ -223,7 +227,7 @@ struct NttBlockPeerBody {
 #pragma unroll
       for (int l = 0; l < 8; l++) v.l[l] = smem[l * P + ntt_pos(i)];
       uint64_t e = (uint64_t)i * n2;
-      if (e) v = fp_mul<R>(v, fp_mul<R>(load_fr<R>(hi, e >> NTT_LO_BITS), load_fr<R>(lo, e & ((1u << NTT_LO_BITS) - 1))));
+      if (e) v = fp_mul<R>(v, lo ? fp_mul<R>(load_fr<R>(hi, e >> NTT_LO_BITS), load_fr<R>(lo, e & ((1u << NTT_LO_BITS) - 1))) : load_fr<R>(hi, e));
       store_fr<R>(dst[i / rows], (uint64_t)(i % rows) * N2 + n2, v);
     }
   }
@@ -240,7 +244,11 @@ inline int ntt_build_plan(NttPlan &p, int curve, uint32_t logn, int inverse, rt:
   p.curve = curve; p.logn = logn; p.inverse = inverse;
   ntt_split(logn, &p.m1, &p.m2);
   size_t n1h = (size_t)1 << (p.m1 ? p.m1 - 1 : 0), n2h = p.m2 ? (size_t)1 << (p.m2 - 1) : 1;
-  size_t nlo = (size_t)1 << NTT_LO_BITS, nhi = logn > NTT_LO_BITS ? (size_t)1 << (logn - NTT_LO_BITS) : 1;
+  // step-2 twiddles w_N^e: up to N = 2^NTT_FULL_TABLE_MAX_LOG the whole table (32 MB at 2^20, L2-resident next to the vector: one
+  // load and ONE product per element of pass 1); beyond, hi[e >> 10] * lo[e & 1023] (two products)
+  const bool full = p.m2 != 0 && logn <= NTT_FULL_TABLE_MAX_LOG;
+  size_t nlo = full ? 0 : (size_t)1 << NTT_LO_BITS;
+  size_t nhi = full ? (size_t)1 << logn : (logn > NTT_LO_BITS ? (size_t)1 << (logn - NTT_LO_BITS) : 1);
   size_t words = 8 * (4 + n1h + n2h + nlo + nhi);
   int rc = rt::dev_malloc((void **)&p.base, words * 4);
   if (rc) return rc;
@@ -250,6 +258,10 @@ inline int ntt_build_plan(NttPlan &p, int curve, uint32_t logn, int inverse, rt:
   if ((rc = rt::launch<32>(NttRootsBody<R>{logn, inverse, roots}, 1, st))) return rc;
   if ((rc = rt::launch<128>(NttTableBody<R>{roots, (uint64_t)1 << (logn - p.m1), p.tw1}, n1h, st))) return rc;
   if ((rc = rt::launch<128>(NttTableBody<R>{roots, (uint64_t)1 << (logn - p.m2), p.tw2}, n2h, st))) return rc;
+  if (full) {
+    p.lo = nullptr;                                                      // the bodies read hi[e] directly when lo is null
+    return rt::launch<128>(NttTableBody<R>{roots, 1, p.hi}, nhi, st);
+  }
   if ((rc = rt::launch<128>(NttTableBody<R>{roots, 1, p.lo}, nlo, st))) return rc;
   return rt::launch<128>(NttTableBody<R>{roots, (uint64_t)1 << NTT_LO_BITS, p.hi}, nhi, st);
 }
