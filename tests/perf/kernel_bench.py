@@ -71,10 +71,14 @@ def main():
     report("fr_from_mont, 2^22", timeit(lambda: eng.fr_from_mont(C.id, x.data_ptr(), n=n, flags=F, out=q.data_ptr())), 64 * n)
     report("fr_div_linear (p/(X-z)), 2^22", timeit(lambda: eng.fr_div_linear(C.id, x.data_ptr(), z, n=n, flags=F, q=q.data_ptr())), 64 * n)
     report("fr_inner_product, 2^22", timeit(lambda: eng.fr_inner_product(C.id, x.data_ptr(), y.data_ptr(), n=n, flags=F)), 64 * n)
+    nb = 1 << 20   # the benchmark's polynomial size: the one-pass division (tiles + decoupled look-back) runs up to 2^21 coefficients
+    report("fr_div_linear (p/(X-z)), 2^20 (one pass)", timeit(lambda: eng.fr_div_linear(C.id, x.data_ptr(), z, n=nb, flags=F, q=q.data_ptr())), 64 * nb,
+           {"note": "2 products per coefficient + 8 per thread: multiply-bound (fmaheavy 40 %), not HBM-bound"})
+    report("fr_inner_product, 2^20", timeit(lambda: eng.fr_inner_product(C.id, x.data_ptr(), y.data_ptr(), n=nb, flags=F)), 64 * nb)
     for ln in (20, 22):
         m = 1 << ln
         report(f"ntt forward, 2^{ln}", timeit(lambda: eng.ntt(C.id, x.data_ptr(), ln, n_in=m, flags=F, out=q.data_ptr())), 64 * m,
-               {"note": "(N/2)log2(N)+2N modmuls; two passes over HBM"})
+               {"note": "(N/2)log2(N) - 7N/8 + N (2N beyond 2^20) modmuls; two passes over HBM"})
     del y
     # MSM variants at 2^20
     nm = (1 << 20) + 1
