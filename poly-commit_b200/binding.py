@@ -553,12 +553,16 @@ class Engine:
         return out, int(inf[0])
 
     # ---- IPA halving loop (device-resident state) ----
-    def ipa_begin(self, curve, comm_key_xy, coeffs, point, n=None, flags=0):
+    def ipa_begin(self, curve, comm_key_xy, coeffs, point, n=None, flags=0, n_coeffs=None):
+        """comm_key_xy / coeffs: host arrays, or device pointers (ints) with DEVICE_PTRS -- a committer key that stays resident in
+        a device buffer across openings, like a registered SRS -- in which case n and n_coeffs are required."""
         comm_key_xy, coeffs, point = _u64(comm_key_xy), _u64(coeffs), _u64(point)
         if n is None:
             n = comm_key_xy.size // (2 * fq_limbs(curve))
+        if n_coeffs is None:
+            n_coeffs = coeffs.size // 4
         h = _vp()
-        self._ck(self.lib.pcgpu_ipa_begin(self.ctx, curve, _ptr(comm_key_xy), n, _ptr(coeffs), coeffs.size // 4, _ptr(point), flags,
+        self._ck(self.lib.pcgpu_ipa_begin(self.ctx, curve, _ptr(comm_key_xy), n, _ptr(coeffs), n_coeffs, _ptr(point), flags,
                                           ctypes.byref(h)))
         return IpaState(self, h, curve)
 
